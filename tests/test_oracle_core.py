@@ -1,0 +1,157 @@
+"""Known-answer tests of the oracle built from the reference-internal cross-checks of SURVEY.md section 4
+and the bit-exact integer items of BASELINE.md section 4."""
+import numpy as np
+import pytest
+
+
+def test_level_schedule_matches_reference_replay(oracle_lib):
+    # SURVEY.md 8a row P1 (computed by replaying pyramid.cu:223-236,463-468 in float32)
+    s = oracle_lib.schedule(256, 256, 1)
+    assert [(e["w"], e["h"], e["d"]) for e in s] == [(256, 256, 1)] + [(256 >> k, 256 >> k, 1) for k in range(6)]
+    s = oracle_lib.schedule(512, 512, 1)
+    assert len(s) == 8 and (s[-1]["w"], s[-1]["h"]) == (8, 8)
+    s = oracle_lib.schedule(1920, 1080, 1)
+    assert [(e["w"], e["h"]) for e in s[1:]] == [(1920, 1080), (960, 540), (480, 270), (240, 135), (120, 68), (60, 34), (30, 17), (15, 9)]
+    s = oracle_lib.schedule(1280, 720, 120, voxel_cap=10 ** 12)
+    assert [(e["w"], e["h"], e["d"]) for e in s[1:]] == [(1280, 720, 120), (640, 360, 120), (320, 180, 120), (160, 90, 120),
+                                                          (80, 45, 120), (40, 23, 61), (20, 12, 31), (10, 6, 16)]
+    assert [e["factor_d"] for e in s] == [8, 8, 8, 8, 8, 8, 4, 2, 1]
+    s = oracle_lib.schedule(1280, 720, 120)          # reference voxel cap 14e6 -> decres_fa 2.81
+    assert [(e["w"], e["h"], e["d"]) for e in s[1:]] == [(455, 256, 120), (228, 128, 120), (114, 64, 120), (57, 32, 61), (29, 16, 31), (15, 8, 16)]
+    s = oracle_lib.schedule(3840, 2160, 240)
+    assert (s[1]["w"], s[1]["h"]) == (322, 181) and (s[-1]["w"], s[-1]["h"]) == (11, 6)
+
+
+def test_strides(oracle_lib):
+    o = oracle_lib.Oracle()
+    o.alloc(1920, 1080, 1)
+    i = o.info(8)
+    assert (i["w"], i["h"], i["rowstride"], i["pagestride"]) == (15, 9, 32, 32 * 9)
+    assert i["impmask_rowstride"] == (15 + 4) // 5 + 2 and i["impmask_pagestride"] == 5 * ((9 + 4) // 5 + 2)
+    i = o.info(1)
+    assert i["rowstride"] == 1920 and abs(i["inv_wh"] - 1.0 / (1920 * 1080)) < 1e-12
+
+
+def _dense_tps_matrix(w, h):
+    """A / w_tps of Morph::cpu_optimize_level (morph.cu:440-469)."""
+    n = w * h
+    A = np.zeros((n, n), np.float64)
+    for y in range(h):
+        for x in range(w):
+            i = y * w + x
+            def add(cond, items):
+                if cond:
+                    for dj, val in items:
+                        A[i, i + dj] += val * 2.0
+            add(x > 1, [(-2, 1), (-1, -2), (0, 1)])
+            add(0 < x < w - 1, [(-1, -2), (0, 4), (1, -2)])
+            add(x < w - 2, [(0, 1), (1, -2), (2, 1)])
+            add(y > 1, [(-2 * w, 1), (-w, -2), (0, 1)])
+            add(0 < y < h - 1, [(-w, -2), (0, 4), (w, -2)])
+            add(y < h - 2, [(0, 1), (w, -2), (2 * w, 1)])
+            add(x > 0 and y > 0, [(-w - 1, 2), (-w, -2), (-1, -2), (0, 2)])
+            add(x < w - 1 and y > 0, [(-w, -2), (-w + 1, 2), (0, 2), (1, -2)])
+            add(x > 0 and y < h - 1, [(-1, -2), (0, 2), (w - 1, 2), (w, -2)])
+            add(x < w - 1 and y < h - 1, [(0, 2), (1, -2), (w, -2), (w + 1, 2)])
+    return A
+
+
+def test_tps_stencil_equals_dense_matrix_rows(oracle_lib):
+    # SURVEY.md section 4 cross-check 1: calc_tps_stencil (stencils.cpp:156-261) vs morph.cu:446-467
+    _, _, tps = oracle_lib.stencils()
+    np.testing.assert_array_equal(tps[2][2], np.array([[0, 0, 2, 0, 0], [0, 4, -16, 4, 0], [2, -16, 40, -16, 2],
+                                                       [0, 4, -16, 4, 0], [0, 0, 2, 0, 0]], np.float32))
+    w = h = 9
+    A = _dense_tps_matrix(w, h)
+    np.testing.assert_allclose(A, A.T)
+    cls = lambda p, n: p if p < 2 else (2 if p < n - 2 else 3 + p - (n - 2))
+    for y in range(h):
+        for x in range(w):
+            row = np.zeros((5, 5))
+            for i in range(5):
+                for j in range(5):
+                    yy, xx = y + i - 2, x + j - 2
+                    if 0 <= yy < h and 0 <= xx < w:
+                        row[i, j] = A[y * w + x, yy * w + xx]
+            np.testing.assert_array_equal(row, tps[cls(y, h)][cls(x, w)], err_msg=f"pixel {(x, y)}")
+
+
+def test_calc_border_closed_form_equals_if_chain(oracle_lib):
+    # SURVEY.md section 4 cross-check 2 (morph.cu:45-53 vs 56-78)
+    import ctypes as C
+    L = oracle_lib.lib()
+    out = (C.c_int * 4)()
+    for (w, h) in [(5, 5), (8, 6), (16, 16), (69, 21), (455, 256)]:
+        for y in list(range(min(h, 4))) + list(range(max(h - 4, 0), h)):
+            for x in range(w):
+                L.vo_calc_border(x, y, w, h, out)
+                assert (out[0], out[1]) == (out[2], out[3]), (x, y, w, h)
+
+
+def test_iomask_and_improvmask(oracle_lib):
+    io, im, _ = oracle_lib.stencils()
+    assert io[2][2].sum() == 25 and io[0][0].sum() == 9 and io[4][1].sum() == 3 * 4
+    # every one of the 25 window pixels lands in exactly one bit of one of the 3x3 cells
+    for i in range(5):
+        for j in range(5):
+            assert sum(bin(int(v)).count("1") for v in im[i][j].ravel()) == 25
+
+
+def test_ssim_identities(oracle_lib):
+    L = oracle_lib.lib()
+    assert L.vo_ssim(1, 1, 1, 1, 1, 1, 0) == 0.0                       # counter <= 1
+    # identical windows: var equal, cross == var  ->  c = s = 1
+    vals = np.arange(25, dtype=np.float32) * 3 + 7
+    m, v = float(vals.sum()), float((vals * vals).sum())
+    assert abs(L.vo_ssim(m, m, v, v, v, 25, 0) - 1.0) < 1e-6
+    assert L.vo_ssim(m, m, v, v, v, 25, 0) <= 1.0
+
+
+def test_incremental_stats_equal_direct_init(oracle_lib):
+    # SURVEY.md section 4 cross-check 3: committing moves keeps ssim sums equal (up to rounding) to a direct re-init
+    from videomorphing_b200 import synth
+    rgb0, rgb1, _ = synth.image_pair(48, 40, 11, 12, 3.0)
+    o = oracle_lib.Oracle(dict(max_iter=8, start_res=8))
+    n = o.build(rgb0, rgb1)
+    o.coarse_solve()
+    l = n - 2
+    o.upsample(l)
+    o.initialize_level(l)
+    it = o.optimize_frame(l, 0, False, 6)
+    assert it >= 1
+    inc = {k: o.get(l, k) for k in ("mean", "var", "cross", "value", "tps_b", "luma")}
+    v = o.get(l, "v")
+    o.initialize_level(l)            # direct recomputation from the optimised v
+    for k in inc:
+        np.testing.assert_allclose(inc[k], o.get(l, k), rtol=2e-4, atol=0.25 if k in ("var", "cross") else 2e-3, err_msg=k)
+    np.testing.assert_array_equal(v, o.get(l, "v"))
+
+
+def test_blocks_are_independent_thread_count_invariance(oracle_lib):
+    from videomorphing_b200 import synth
+    rgb0, rgb1, _ = synth.image_pair(150, 50, 21, 22, 3.0)
+    res = []
+    for nt in (1, 4):
+        oracle_lib.lib().vo_set_num_threads(nt)
+        o = oracle_lib.Oracle(dict(max_iter=4))
+        o.build(rgb0, rgb1)
+        o.run()
+        res.append(o.get(1, "v"))
+    oracle_lib.lib().vo_set_num_threads(8)
+    np.testing.assert_array_equal(res[0], res[1])
+
+
+def test_no_constraints_coarse_solution_is_zero_and_constraints_pull(oracle_lib):
+    from videomorphing_b200 import synth
+    rgb0, rgb1, field = synth.image_pair(64, 64, 31, 32, 4.0)
+    o = oracle_lib.Oracle()
+    n = o.build(rgb0, rgb1)
+    o.coarse_solve()
+    assert not o.get(n - 1, "v").any()
+    lp, lw, rp, rw = synth.point_pairs(6, 64, 64, 33, field, margin=8)
+    o.set_constraints(lp, lw, rp, rw)
+    o.coarse_solve()
+    v = o.get(n - 1, "v")[0, :8, :8]
+    # halfway vector at the coarse level ~ (rp-lp)/2 scaled by 8/64
+    exp = ((rp[:, :2] - lp[:, :2]) / 2.0 / 8.0).mean(0)
+    assert np.abs(v.mean((0, 1)) - exp).max() < 0.2
