@@ -1,0 +1,180 @@
+/* ============================================================================
+ * include/vmorph.h -- C ABI of libvmorph (B200 / sm_100a).
+ *
+ * Drop-in boundary for the hot path of liaojing/videomorphing: the coarse-to-fine
+ * halfway-domain correspondence optimizer and the morph renderer, behind the
+ * reference's Algorithm/ operator surface.  The reference has no FFI layer; the
+ * boundary is the set of C++ symbols its Qt side calls.  Every
+ * entry point below names the reference interface it replaces (file:line relative
+ * to the reference tree).  INTEGRATION.md shows the C++ shim a maintainer would
+ * add to re-create Pyramid / Morph / render_halfway_image on top of this ABI.
+ *
+ * Conventions: opaque handles; every call returns VM_OK (0) or a negative status
+ * and records a message retrievable with vm_last_error(); no exceptions cross the
+ * boundary; plain pointers and sizes only.  `stream` arguments are cudaStream_t
+ * passed as void* (NULL = the legacy default stream).  Host pointers unless the
+ * name says `dev`.  All pixel coordinates / vectors are in pixels of the level
+ * they belong to; float2 arrays are interleaved (x,y).
+ * There is no CPU fallback: without a CUDA device every compute call fails with
+ * VM_ERR_CUDA.
+ * ==========================================================================*/
+#ifndef VMORPH_H
+#define VMORPH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VM_OK 0
+#define VM_ERR_ARG (-1)
+#define VM_ERR_CUDA (-2)
+#define VM_ERR_STATE (-3)
+#define VM_ERR_PARSE (-4)
+#define VM_ERR_CANCELLED (-5)
+
+/* parameters.h:9-14 */
+enum { VM_BCOND_NONE = 0, VM_BCOND_CORNER = 1, VM_BCOND_BORDER = 2 };
+
+/* parameters.h:22-26  Conp { int4 p; float weight; }  p = (x, y, frame, keyflag), level-0 pixels */
+typedef struct vm_conp { int32_t x, y, z, w; float weight; } vm_conp;
+/* parameters.h:16-20  Connect { int2 li; int2 ri; }  (track, index) into lp / rp */
+typedef struct vm_connect { int32_t li_track, li_idx, ri_track, ri_idx; } vm_connect;
+
+/* parameters.h:29-52 (hot-path fields of Parameters) */
+typedef struct vm_params {
+    float w_ui, w_tps, w_ssim, w_temp;
+    float ssim_clamp;
+    float eps;
+    int32_t max_iter;
+    int32_t start_res;
+    float max_iter_drop_factor;
+    int32_t bcond;
+} vm_params;
+
+/* Level array identifiers for vm_level_get / vm_level_set (Pyramid.h:56-89). */
+enum {
+    VM_FIELD_V = 0, VM_FIELD_SSIM_MEAN = 1, VM_FIELD_SSIM_VAR = 2, VM_FIELD_SSIM_LUMA = 3, VM_FIELD_SSIM_CROSS = 4,
+    VM_FIELD_SSIM_VALUE = 5, VM_FIELD_SSIM_COUNTER = 6, VM_FIELD_TPS_AXY = 7, VM_FIELD_TPS_B = 8, VM_FIELD_UI_AXY = 9,
+    VM_FIELD_UI_B = 10, VM_FIELD_TEMP_REF = 11, VM_FIELD_TEMP_MASK = 12, VM_FIELD_IMPROVING_MASK = 13,
+    VM_FIELD_IMG0 = 14, VM_FIELD_IMG1 = 15, VM_FIELD_F0 = 16, VM_FIELD_F1 = 17, VM_FIELD_B0 = 18, VM_FIELD_B1 = 19,
+    VM_FIELD_COUNT = 20
+};
+
+/* Pyramid.h:60-66 + pyramid.cu:531-543 */
+typedef struct vm_level_info {
+    int32_t width, height, depth;
+    int32_t rowstride, pagestride;
+    int32_t impmask_rowstride, impmask_pagestride;
+    int32_t has_images;
+    int32_t factor_t;
+    float factor_d, inv_wh;
+} vm_level_info;
+
+typedef struct vm_pyramid vm_pyramid;
+typedef struct vm_morph vm_morph;
+
+const char *vm_last_error(void);
+/* number of CUDA devices visible (0 => every compute call fails with VM_ERR_CUDA) */
+int vm_device_count(void);
+/* library build id string ("vmorph sm_100a ...") */
+const char *vm_version(void);
+
+/* ---- Parameters (parameters.h:29-52; defaults UI/MdiEditor.cpp:131-140) ---- */
+int vm_params_default(vm_params *out);
+/* param_io.h:8  parse_config_xml(Parameters&, const std::string&): reads the live settings.xml schema written by
+ * MdiEditor::WriteXmlFile (UI/MdiEditor.cpp:751-1040).  Tracks are returned through vm_morph_set_tracks-style
+ * arrays allocated by the library; free with vm_tracks_free. */
+typedef struct vm_tracks {
+    int32_t n_left, n_right, n_groups;      /* #tracks in lp, rp; #connection groups in cnt */
+    int32_t *left_len, *right_len, *group_len;
+    vm_conp *left, *right;                  /* concatenated tracks */
+    vm_connect *connects;                   /* concatenated groups */
+} vm_tracks;
+int vm_params_parse_xml(const char *path, vm_params *out, vm_tracks *tracks_out);
+void vm_tracks_free(vm_tracks *t);
+
+/* ---- Pyramid (Pyramid.h:14-49; Pyramid::build pyramid.cu:166-485) ---- */
+int vm_pyramid_create(int device, vm_pyramid **out);
+void vm_pyramid_destroy(vm_pyramid *p);
+/* pyramid.cu:219-236,463-477: level sizes only.  whd_out: 3 ints per level; returns #levels (<= max_levels)
+ * or a negative status.  voxel_cap = 14000000 reproduces the reference (pyramid.cu:8). Pure host arithmetic. */
+int vm_level_schedule(int w, int h, int d, int start_res, int64_t voxel_cap, int max_levels, int32_t *whd_out, float *factor_d_out);
+/* Allocates all levels for w x h x d input (no image data yet). */
+int vm_pyramid_alloc(vm_pyramid *p, int w, int h, int d, int start_res, int64_t voxel_cap);
+/* Pyramid::build (Pyramid.h:28): video0/video1 = d frames of h*w*3 RGB8; f0,f1,b0,b1 = d frames of h*w float2
+ * optical flow (may all be NULL when d == 1).  Builds every level's gray images and flows on the GPU. */
+int vm_pyramid_build(vm_pyramid *p, const uint8_t *video0, const uint8_t *video1, const float *f0, const float *f1,
+                     const float *b0, const float *b1, int w, int h, int d, int start_res, int64_t voxel_cap, void *stream);
+int vm_pyramid_num_levels(const vm_pyramid *p);
+int vm_pyramid_level_info(const vm_pyramid *p, int level, vm_level_info *out);
+/* Raw access to a level array (all frames).  Layout: images/flows tight (d,h,w[,2]); state (d,h,rowstride[,2]);
+ * improving mask (d, impmask_pagestride).  nbytes must equal the array size.  Synchronous. */
+int vm_level_get(vm_pyramid *p, int level, int field, void *host_out, size_t nbytes);
+int vm_level_set(vm_pyramid *p, int level, int field, const void *host_in, size_t nbytes);
+
+/* ---- Morph (morph.h:10-31) ---- */
+/* Morph::Morph(Parameters&, Pyramid&, bool& run_flag) morph.cu:122-141.  run_flag may be NULL; when given it is
+ * polled (non-zero = keep running) between iterations exactly like m_cb (morph.cu:156,1390,1396). */
+int vm_morph_create(const vm_params *prm, vm_pyramid *pyr, volatile int *run_flag, vm_morph **out);
+void vm_morph_destroy(vm_morph *m);
+/* Parameters::lp / rp / cnt (parameters.h:45-47) in the reference's own ragged layout. */
+int vm_morph_set_tracks(vm_morph *m, int n_left, const int32_t *left_len, const vm_conp *left, int n_right,
+                        const int32_t *right_len, const vm_conp *right, int n_groups, const int32_t *group_len,
+                        const vm_connect *connects);
+/* Convenience: n already-resolved connections (left point, right point). */
+int vm_morph_set_constraints(vm_morph *m, int n, const vm_conp *left, const vm_conp *right);
+/* Morph::calculate_halfway_parametrization morph.cu:150-168 (blocks until done; result stays in level 1's v). */
+int vm_morph_run(vm_morph *m, void *stream);
+/* morph.h:17-20 public progress fields, readable from another thread while vm_morph_run executes. */
+int vm_morph_progress(const vm_morph *m, int *total_l, int *current_l, double *total_iter, double *current_iter, float *max_iter);
+/* sum over levels/frames of width*height*iterations actually executed (BASELINE.md metric numerator) */
+double vm_morph_executed_pixel_iters(const vm_morph *m);
+/* (level, frame, iterations) triples logged by optimize_level; returns count */
+int vm_morph_iters_log(const vm_morph *m, int max_triples, int32_t *out);
+/* operator-level entry points (for unit parity with the reference operators) */
+int vm_level_cpu_solve(vm_morph *m, void *stream);                       /* Morph::cpu_optimize_level morph.cu:419-590 (runs on the GPU here) */
+int vm_level_upsample(vm_morph *m, int dest_level, void *stream);        /* upsample(PyramidLevel&,PyramidLevel&) upsample.cu:260-340 */
+int vm_level_initialize(vm_morph *m, int level, void *stream);           /* Morph::initialize_level morph.cu:264-390 */
+int vm_level_init_temp(vm_morph *m, int level, int frame, int dir, void *stream);  /* initialize_temp upsample.cu:214-258 */
+/* per-frame do/while of Morph::optimize_level (morph.cu:1377-1391); returns iterations executed in *iters_out */
+int vm_level_optimize_frame(vm_morph *m, int level, int frame, int flag, float max_iter, int *iters_out, void *stream);
+int vm_level_optimize(vm_morph *m, int level, float max_iter, void *stream);       /* Morph::optimize_level morph.cu:1353-1441 */
+/* total energy of SURVEY.md A.6 for one frame; terms_out[4] = ssim, ui, temp, tps parts */
+int vm_level_energy(vm_morph *m, int level, int frame, int flag, double *energy_out, double *terms_out);
+/* CMatchingThread::update_result (MatchingThread.cpp:22-84): level-1 v -> level-0 sized vectors, d0*h0*w0 float2 */
+int vm_morph_get_vectors(vm_morph *m, float *host_out, void *stream);
+/* stencil tables (stencils.h:13-19): iomask[5][5][5][5], improvmask[5][5][3][3], tps[5][5][5][5]; host arithmetic */
+int vm_stencils_get(int32_t *iomask625, int32_t *improvmask225, float *tps625);
+
+/* ---- Renderer ---- */
+/* render_halfway_image (render.cu:62-96, UI/RenderWidget.h:52-57).  Device-resident variant: all pointers are
+ * device pointers: out = uchar3 rows of `rowstride` pixels; ext0/ext1 = RGBA8 (w+2ex) x (h+2ex) (Pyramid::_extends);
+ * vector/qpath = w*h float2 (qpath may be NULL = zeros).  color_from 0/1/2 = video0 / blend / video1. */
+int vm_render_halfway_dev(uint8_t *out_dev, int rowstride, int w, int h, int ex, float color_fa, float geo_fa,
+                          int color_from, const uint8_t *ext0_dev, const uint8_t *ext1_dev, const float *vector_dev,
+                          const float *qpath_dev, void *stream);
+/* Host-buffer variant = RenderWidget::RenderStage2 (UI/RenderWidget.cpp:229-266): uploads, renders, downloads
+ * h*w*3 tightly packed RGB8 into out. */
+int vm_render_halfway(int device, uint8_t *out, int w, int h, int ex, float color_fa, float geo_fa, int color_from,
+                      const uint8_t *ext0, const uint8_t *ext1, const float *vector, const float *qpath, void *stream);
+
+/* ---- QuadraticPath (QuadraticPath.h:10-14, QuadraticPath.cpp:24-318) ---- */
+/* one frame: vector (w*h float2, host) -> qpath (w*h float2, host). max_iter=10000, tol=1e-12 reproduce the reference */
+int vm_qpath_optimize(int device, const float *vector, float *qpath, int w, int h, int max_iter, float tol, int *iters_out, void *stream);
+
+/* device memory helpers for callers that keep inputs resident (bench, multi-frame render) */
+int vm_dev_alloc(int device, size_t nbytes, void **out_dev);
+int vm_dev_free(int device, void *dev);
+int vm_dev_upload(int device, void *dst_dev, const void *src_host, size_t nbytes, void *stream);
+int vm_dev_download(int device, void *dst_host, const void *src_dev, size_t nbytes, void *stream);
+int vm_stream_sync(int device, void *stream);
+/* counts kernels launched by this library since process start (bench.py's gpu_launches claim) */
+uint64_t vm_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMORPH_H */

@@ -355,8 +355,11 @@ void coarse_solve(Pyramid &P) {
 
 // ----------------------------------------------------------------- upsample
 // upsample.cu:28-62 (temp_ref): forward splat of neighbour frame's v advected by the flows.
-// D2: contributors visited in row-major order of the source pixel.
-static void temp_ref_splat(const Level &L, const f2 *v_prev, f2 *v_cur, float *weight, const float *ssim_val,
+// D2: the reference scatters with float atomics (order undefined).  Contributions are accumulated as 2^-32
+// fixed-point 64-bit integers, which makes the sum order-independent (the CUDA path does the same arithmetic).
+// acc layout: [0..ps) x, [ps..2ps) y, [2ps..3ps) weight.
+static const double FIX_SCALE = 4294967296.0;
+static void temp_ref_splat(const Level &L, const f2 *v_prev, long long *acc, const float *ssim_val,
                            const f2 *F0, const f2 *F1) {
     for (int py = 0; py < L.h; py++)
         for (int px = 0; px < L.w; px++) {
@@ -373,17 +376,22 @@ static void temp_ref_splat(const Level &L, const f2 *v_prev, f2 *v_cur, float *w
                     float ssim_fa = 1;
                     if (ssim_val) ssim_fa = ssim_val[py * L.rs + px];
                     float fa = (float)((double)ssim_fa * (1.0 - (double)std::fabs((float)x - prx)) * (1.0 - (double)std::fabs((float)y - pry)));
-                    int q = y * L.rs + x;
-                    v_cur[q].x += vrx * fa; v_cur[q].y += vry * fa;
-                    weight[q] += fa;
+                    size_t q = (size_t)y * L.rs + x;
+                    acc[q] += llrint((double)(vrx * fa) * FIX_SCALE);
+                    acc[L.ps + q] += llrint((double)(vry * fa) * FIX_SCALE);
+                    acc[2 * (size_t)L.ps + q] += llrint((double)fa * FIX_SCALE);
                 }
         }
 }
-// upsample.cu:64-77
-static void interpolate_temp_ref(const Level &L, f2 *v_cur, const float *weight) {
+// accumulator read-out + interpolate_temp_ref (upsample.cu:64-77)
+static void splat_finish(const Level &L, const long long *acc, f2 *v_cur, float *weight) {
     for (int y = 0; y < L.h; y++) for (int x = 0; x < L.w; x++) {
-        int idx = y * L.rs + x;
-        if (weight[idx] > 0) { v_cur[idx].x /= weight[idx]; v_cur[idx].y /= weight[idx]; }
+        size_t q = (size_t)y * L.rs + x;
+        float wgt = (float)((double)acc[2 * (size_t)L.ps + q] * (1.0 / FIX_SCALE));
+        float vx = (float)((double)acc[q] * (1.0 / FIX_SCALE)), vy = (float)((double)acc[L.ps + q] * (1.0 / FIX_SCALE));
+        if (wgt > 0) { vx = vx / wgt; vy = vy / wgt; }
+        v_cur[q] = mk2(vx, vy);
+        weight[q] = wgt;
     }
 }
 
@@ -409,13 +417,14 @@ void upsample_level(Pyramid &P, int dst) {
         for (int i = 1; i < dest.d; i += factor) {
             if (i == dest.d - 1) continue;
             std::vector<float> weight(dest.ps, 0.0f);
+            std::vector<long long> acc(3 * (size_t)dest.ps, 0);
             f2 *vi = dest.v.data() + (size_t)i * dest.ps;
             size_t fs = (size_t)dest.w * dest.h;
-            temp_ref_splat(dest, dest.v.data() + (size_t)(i - 1) * dest.ps, vi, weight.data(), nullptr,
+            temp_ref_splat(dest, dest.v.data() + (size_t)(i - 1) * dest.ps, acc.data(), nullptr,
                            dest.f0.data() + (i - 1) * fs, dest.f1.data() + (i - 1) * fs);
-            temp_ref_splat(dest, dest.v.data() + (size_t)(i + 1) * dest.ps, vi, weight.data(), nullptr,
+            temp_ref_splat(dest, dest.v.data() + (size_t)(i + 1) * dest.ps, acc.data(), nullptr,
                            dest.b0.data() + (i + 1) * fs, dest.b1.data() + (i + 1) * fs);
-            interpolate_temp_ref(dest, vi, weight.data());
+            splat_finish(dest, acc.data(), vi, weight.data());
             std::vector<f2> vo(dest.ps, mk2(0, 0));
             // smooth (upsample.cu:80-111)
             for (int py = 0; py < dest.h; py++) for (int px = 0; px < dest.w; px++) {
@@ -529,12 +538,13 @@ void initialize_temp(Pyramid &P, int l, int i, int dir) {
     Level &L = P.lv[l];
     std::vector<float> weight(L.ps, 0.0f);
     std::vector<f2> ref_v(L.ps, mk2(0, 0));
+    std::vector<long long> acc(3 * (size_t)L.ps, 0);
     size_t fs = (size_t)L.w * L.h;
     int n = i + dir;
     const f2 *F0 = (dir < 0 ? L.f0.data() : L.b0.data()) + n * fs;
     const f2 *F1 = (dir < 0 ? L.f1.data() : L.b1.data()) + n * fs;
-    temp_ref_splat(L, L.v.data() + (size_t)n * L.ps, ref_v.data(), weight.data(), L.value.data() + (size_t)n * L.ps, F0, F1);
-    interpolate_temp_ref(L, ref_v.data(), weight.data());
+    temp_ref_splat(L, L.v.data() + (size_t)n * L.ps, acc.data(), L.value.data() + (size_t)n * L.ps, F0, F1);
+    splat_finish(L, acc.data(), ref_v.data(), weight.data());
     for (int y = 0; y < L.h; y++) for (int x = 0; x < L.w; x++) {      // kernel_initialize_temp, A.8-Q9
         size_t idx = (size_t)y * L.rs + x + (size_t)L.ps * i;
         int q = y * L.rs + x;

@@ -1,0 +1,659 @@
+// vm_host.cu -- host side of libvmorph: error handling, stencil tables, level schedule, Pyramid / Morph objects and
+// the C ABI of include/vmorph.h.  Mirrors the reference's Algorithm/ operator surface (Pyramid.h, morph.h,
+// MatchingThread.cpp) for the hot path; see INTEGRATION.md for the C++ shim on top of it.
+#include "vm_host.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <mutex>
+
+namespace vm {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void set_error(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return VM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ stencils (own formulation)
+// iomask: a window offset is usable iff it stays inside the image for a pixel of that border class
+// (class 0,1 = distance 0,1 to the low border; 3,4 = distance 1,0 to the high border; 2 = interior).
+// improvmask: which bits of the 3x3 surrounding 5x5-pixel mask cells the 5x5 window of a pixel at (ox,oy) in its cell touches.
+// tps: Hessian row of  sum (dxx v)^2 + (dyy v)^2 + 2 (dxy v)^2  over all difference stencils that fit in the image
+// (dxx = [1 -2 1], dxy = 2x2 cross difference), evaluated on a 9x9 grid at the pixel representing the border class.
+void build_stencils(HostStencils &s) {
+    memset(&s, 0, sizeof(s));
+    auto ok = [](int cls, int off) {   // off in -2..2
+        if (cls == 0) return off >= 0; if (cls == 1) return off >= -1; if (cls == 3) return off <= 1; if (cls == 4) return off <= 0; return true; };
+    for (int By = 0; By < 5; By++) for (int Bx = 0; Bx < 5; Bx++)
+        for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) s.iomask[By][Bx][i][j] = (ok(By, i - 2) && ok(Bx, j - 2)) ? 1 : 0;
+    for (int oy = 0; oy < 5; oy++) for (int ox = 0; ox < 5; ox++)
+        for (int dy = -2; dy <= 2; dy++) for (int dx = -2; dx <= 2; dx++) {
+            int ax = ox + 5 + dx, ay = oy + 5 + dy;
+            s.improvmask[oy][ox][ay / 5][ax / 5] |= 1 << ((ax % 5) + (ay % 5) * 5);
+        }
+    const int N = 9; const int pos[5] = {0, 1, 4, 7, 8};
+    for (int By = 0; By < 5; By++) for (int Bx = 0; Bx < 5; Bx++) {
+        int cx = pos[Bx], cy = pos[By];
+        double row[N][N]; memset(row, 0, sizeof(row));
+        auto add = [&](const int (*pts)[2], const double *coef, int n, double wgt) {
+            double cp = 0; bool has = false;
+            for (int k = 0; k < n; k++) if (pts[k][0] == cx && pts[k][1] == cy) { cp = coef[k]; has = true; }
+            if (!has) return;
+            for (int k = 0; k < n; k++) row[pts[k][1]][pts[k][0]] += 2.0 * wgt * cp * coef[k];
+        };
+        const double c3[3] = {1, -2, 1}, c4[4] = {1, -1, -1, 1};
+        for (int y = 0; y < N; y++) for (int x = 0; x < N; x++) {
+            if (x >= 1 && x <= N - 2) { int pts[3][2] = {{x - 1, y}, {x, y}, {x + 1, y}}; add(pts, c3, 3, 1.0); }
+            if (y >= 1 && y <= N - 2) { int pts[3][2] = {{x, y - 1}, {x, y}, {x, y + 1}}; add(pts, c3, 3, 1.0); }
+            if (x + 1 < N && y + 1 < N) { int pts[4][2] = {{x, y}, {x + 1, y}, {x, y + 1}, {x + 1, y + 1}}; add(pts, c4, 4, 2.0); }
+        }
+        for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) {
+            int x = cx + j - 2, y = cy + i - 2;
+            s.tps[By][Bx][i][j] = (x >= 0 && x < N && y >= 0 && y < N) ? (float)row[y][x] : 0.0f;
+        }
+    }
+}
+
+void pack_stencils(const HostStencils &s, StencilTables &t) {
+    memset(&t, 0, sizeof(t));
+    for (int By = 0; By < 5; By++) for (int Bx = 0; Bx < 5; Bx++) {
+        int B = By * 5 + Bx;
+        for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) {
+            t.tps[B][i * 5 + j] = s.tps[By][Bx][i][j];
+            if (s.iomask[By][Bx][i][j]) t.iomask[B] |= 1u << (i * 5 + j);
+        }
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) t.improv[B][i * 3 + j] = (unsigned)s.improvmask[By][Bx][i][j];
+    }
+}
+
+// ------------------------------------------------------------------ level schedule
+// pyramid.cu:219-236 + 463-477, all in float32 like the reference (log via logf ratio, float->int truncation).
+static float log2_f32(float v) { return logf(v) / logf(2.0f); }
+std::vector<SchedEntry> level_schedule(int w, int h, int d, int start_res, int64_t voxel_cap) {
+    std::vector<SchedEntry> out;
+    out.push_back({w, h, d, 1.0f, 1});
+    float decres = (float)((int64_t)w * h * d) / (float)voxel_cap;
+    float sq = sqrtf(decres);
+    decres = sq > 1.0f ? sq : 1.0f;
+    w = (int)((float)w / decres);
+    h = (int)((float)h / decres);
+    int el_t = (int)(log2_f32((float)d) - log2_f32((float)start_res) + 1);
+    int el_y = (int)(log2_f32((float)h) - log2_f32((float)start_res) + 1);
+    int el_x = (int)(log2_f32((float)w) - log2_f32((float)start_res) + 1);
+    el_x = el_y = std::max(el_x, el_y);
+    int maxl = std::max(el_x, el_t), factor_t = 1;
+    for (int el = 0; el < maxl; el++) {
+        out.push_back({w, h, d, 1.0f, factor_t});
+        if (maxl - el <= el_x) w = (int)ceilf(w / 2.0f);
+        if (maxl - el <= el_y) h = (int)ceilf(h / 2.0f);
+        if (maxl - el <= el_t) { d = (int)ceilf((d + 1) / 2.0f); factor_t = 2; } else factor_t = 1;
+    }
+    for (int i = (int)out.size() - 2; i >= 0; i--)
+        out[i].factor_d = (out[i + 1].d != out[i].d) ? out[i + 1].factor_d * 2 : out[i + 1].factor_d;
+    return out;
+}
+
+// ------------------------------------------------------------------ views
+LevelView make_view(vm_pyramid *p, int level) {
+    const Level &l = p->lv[level];
+    LevelView V;
+    V.w = l.w; V.h = l.h; V.d = l.d; V.rs = l.rs; V.ps = l.ps; V.irs = l.irs; V.ips = l.ips;
+    V.inv_wh = l.inv_wh; V.factor_d = l.factor_d;
+    V.v = l.v.as<float2>();
+    V.mean = p->mean.as<float2>(); V.var = p->var.as<float2>(); V.luma = p->luma.as<float2>();
+    V.tps_b = p->tps_b.as<float2>(); V.ui_b = p->ui_b.as<float2>(); V.temp_ref = p->temp_ref.as<float2>();
+    V.cross = p->cross.as<float>(); V.value = p->value.as<float>(); V.counter = p->counter.as<float>();
+    V.tps_axy = p->tps_axy.as<float>(); V.ui_axy = p->ui_axy.as<float>(); V.temp_mask = p->temp_mask.as<float>();
+    V.impmask = p->impmask.as<unsigned int>();
+    V.img0 = l.img0.as<float>(); V.img1 = l.img1.as<float>();
+    V.f0 = l.f0.as<float2>(); V.f1 = l.f1.as<float2>(); V.b0 = l.b0.as<float2>(); V.b1 = l.b1.as<float2>();
+    return V;
+}
+
+static KParams kparams(const vm_params &p) {
+    KParams k; k.w_temp = p.w_temp; k.w_ui = p.w_ui; k.w_tps = p.w_tps; k.w_ssim = p.w_ssim; k.ssim_clamp = p.ssim_clamp; k.eps = p.eps; k.bcond = p.bcond;
+    return k;
+}
+
+static int use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { set_error("no CUDA device available (%s): libvmorph has no CPU fallback", e == cudaSuccess ? "count 0" : cudaGetErrorString(e)); return VM_ERR_CUDA; }
+    if (device < 0 || device >= n) { set_error("device %d out of range (%d devices)", device, n); return VM_ERR_ARG; }
+    VM_CUDA(cudaSetDevice(device));
+    return VM_OK;
+}
+
+}  // namespace vm
+
+using namespace vm;
+
+// =====================================================================================================
+extern "C" {
+
+const char *vm_last_error(void) { return g_err; }
+int vm_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+const char *vm_version(void) { return "vmorph 0.1 (sm_100a, fp32 IEEE, -fmad=false)"; }
+uint64_t vm_kernel_launch_count(void) { return g_launches.load(); }
+
+int vm_params_default(vm_params *out) {            // UI/MdiEditor.cpp:131-140
+    if (!out) { set_error("null params"); return VM_ERR_ARG; }
+    out->w_ssim = 100.0f; out->ssim_clamp = 0.0f; out->w_tps = 0.05f; out->w_ui = 100000.0f; out->w_temp = 10.0f;
+    out->max_iter = 1000; out->max_iter_drop_factor = 2; out->eps = 0.01f; out->start_res = 8; out->bcond = VM_BCOND_NONE;
+    return VM_OK;
+}
+
+int vm_stencils_get(int32_t *iomask625, int32_t *improvmask225, float *tps625) {
+    HostStencils s; build_stencils(s);
+    if (iomask625) memcpy(iomask625, s.iomask, sizeof(s.iomask));
+    if (improvmask225) memcpy(improvmask225, s.improvmask, sizeof(s.improvmask));
+    if (tps625) memcpy(tps625, s.tps, sizeof(s.tps));
+    return VM_OK;
+}
+
+int vm_level_schedule(int w, int h, int d, int start_res, int64_t voxel_cap, int max_levels, int32_t *whd_out, float *factor_d_out) {
+    if (w <= 0 || h <= 0 || d <= 0 || start_res <= 0 || voxel_cap <= 0) { set_error("bad schedule arguments"); return VM_ERR_ARG; }
+    auto s = level_schedule(w, h, d, start_res, voxel_cap);
+    if ((int)s.size() > max_levels) { set_error("schedule needs %d levels", (int)s.size()); return VM_ERR_ARG; }
+    for (size_t i = 0; i < s.size(); i++) {
+        if (whd_out) { whd_out[3 * i] = s[i].w; whd_out[3 * i + 1] = s[i].h; whd_out[3 * i + 2] = s[i].d; }
+        if (factor_d_out) factor_d_out[i] = s[i].factor_d;
+    }
+    return (int)s.size();
+}
+
+// ---------------------------------------------------------------- pyramid
+int vm_pyramid_create(int device, vm_pyramid **out) {
+    if (!out) { set_error("null out"); return VM_ERR_ARG; }
+    int rc = use_device(device); if (rc) return rc;
+    vm_pyramid *p = new vm_pyramid();
+    p->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
+    build_stencils(p->hst);
+    StencilTables t; pack_stencils(p->hst, t);
+    cudaError_t e = p->stencils.ensure(sizeof(t));
+    if (e == cudaSuccess) e = cudaMemcpy(p->stencils.p, &t, sizeof(t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete p; return cuda_fail(e, "stencil upload"); }
+    *out = p;
+    return VM_OK;
+}
+void vm_pyramid_destroy(vm_pyramid *p) { if (p) { cudaSetDevice(p->device); delete p; } }
+
+int vm_pyramid_alloc(vm_pyramid *p, int w, int h, int d, int start_res, int64_t voxel_cap) {
+    if (!p || w <= 0 || h <= 0 || d <= 0 || start_res <= 0 || voxel_cap <= 0) { set_error("bad pyramid_alloc arguments"); return VM_ERR_ARG; }
+    int rc = use_device(p->device); if (rc) return rc;
+    auto s = level_schedule(w, h, d, start_res, voxel_cap);
+    if (s.size() < 3) { set_error("input %dx%dx%d too small for start_res %d (need >= 2 pyramid levels)", w, h, d, start_res); return VM_ERR_ARG; }
+    p->lv.clear(); p->lv.resize(s.size());
+    p->w0 = w; p->h0 = h; p->d0 = d; p->state_level = -1;
+    size_t max_state = 0, max_ps = 0, max_imp = 0;
+    for (size_t i = 0; i < s.size(); i++) {
+        Level &L = p->lv[i];
+        L.w = s[i].w; L.h = s[i].h; L.d = s[i].d; L.factor_d = s[i].factor_d; L.factor_t = s[i].factor_t;
+        L.rs = (L.w + 31) / 32 * 32; L.ps = L.rs * L.h;                        // pyramid.cu:535-536
+        L.inv_wh = 1.0f / (float)(L.w * L.h);                                   // pyramid.cu:537
+        L.irs = (L.w + 4) / 5 + 2; L.ips = L.irs * ((L.h + 4) / 5 + 2);         // pyramid.cu:538-539
+        L.has_images = (i >= 1 && i + 1 < s.size());                            // level 0 dims only; coarsest has no images (pyramid.cu:329)
+        if (i >= 1) {
+            VM_CUDA(L.v.ensure(sizeof(float2) * (size_t)L.ps * L.d));
+            VM_CUDA(cudaMemset(L.v.p, 0, sizeof(float2) * (size_t)L.ps * L.d));
+        }
+        if (L.has_images) {
+            size_t fs = (size_t)L.w * L.h * L.d;
+            VM_CUDA(L.img0.ensure(sizeof(float) * fs)); VM_CUDA(L.img1.ensure(sizeof(float) * fs));
+            if (d > 1) { VM_CUDA(L.f0.ensure(sizeof(float2) * fs)); VM_CUDA(L.f1.ensure(sizeof(float2) * fs)); VM_CUDA(L.b0.ensure(sizeof(float2) * fs)); VM_CUDA(L.b1.ensure(sizeof(float2) * fs)); }
+            max_state = std::max(max_state, (size_t)L.ps * L.d);
+            max_ps = std::max(max_ps, (size_t)L.ps);
+            max_imp = std::max(max_imp, (size_t)L.ips * L.d);
+        }
+    }
+    VM_CUDA(p->mean.ensure(8 * max_state)); VM_CUDA(p->var.ensure(8 * max_state)); VM_CUDA(p->luma.ensure(8 * max_state));
+    VM_CUDA(p->tps_b.ensure(8 * max_state)); VM_CUDA(p->ui_b.ensure(8 * max_state)); VM_CUDA(p->temp_ref.ensure(8 * max_state));
+    VM_CUDA(p->cross.ensure(4 * max_state)); VM_CUDA(p->value.ensure(4 * max_state)); VM_CUDA(p->counter.ensure(4 * max_state));
+    VM_CUDA(p->tps_axy.ensure(4 * max_state)); VM_CUDA(p->ui_axy.ensure(4 * max_state)); VM_CUDA(p->temp_mask.ensure(4 * max_state));
+    VM_CUDA(p->impmask.ensure(4 * max_imp));
+    VM_CUDA(p->tmp_a.ensure(sizeof(long long) * 3 * max_ps)); VM_CUDA(p->tmp_b.ensure(sizeof(float2) * max_ps)); VM_CUDA(p->tmp_c.ensure(sizeof(float) * max_ps));
+    return (int)s.size();
+}
+
+int vm_pyramid_num_levels(const vm_pyramid *p) { return p ? (int)p->lv.size() : VM_ERR_ARG; }
+
+int vm_pyramid_level_info(const vm_pyramid *p, int level, vm_level_info *out) {
+    if (!p || !out || level < 0 || level >= (int)p->lv.size()) { set_error("bad level %d", level); return VM_ERR_ARG; }
+    const Level &L = p->lv[level];
+    out->width = L.w; out->height = L.h; out->depth = L.d; out->rowstride = L.rs; out->pagestride = L.ps;
+    out->impmask_rowstride = L.irs; out->impmask_pagestride = L.ips; out->has_images = L.has_images; out->factor_t = L.factor_t;
+    out->factor_d = L.factor_d; out->inv_wh = L.inv_wh;
+    return VM_OK;
+}
+
+static int field_ptr(vm_pyramid *p, int level, int field, void **ptr, size_t *bytes) {
+    if (!p || level < 0 || level >= (int)p->lv.size()) { set_error("bad level %d", level); return VM_ERR_ARG; }
+    Level &L = p->lv[level];
+    size_t n = (size_t)L.ps * L.d, fs = (size_t)L.w * L.h * L.d;
+    bool state = field >= VM_FIELD_SSIM_MEAN && field <= VM_FIELD_IMPROVING_MASK;
+    if (state && !(L.has_images)) { set_error("level %d has no optimizer state", level); return VM_ERR_STATE; }
+    if (state && p->state_level != level && p->state_level != -1) { /* arena describes another level: still addressable with this level's strides */ }
+    switch (field) {
+    case VM_FIELD_V: *ptr = L.v.p; *bytes = 8 * n; break;
+    case VM_FIELD_SSIM_MEAN: *ptr = p->mean.p; *bytes = 8 * n; break;
+    case VM_FIELD_SSIM_VAR: *ptr = p->var.p; *bytes = 8 * n; break;
+    case VM_FIELD_SSIM_LUMA: *ptr = p->luma.p; *bytes = 8 * n; break;
+    case VM_FIELD_SSIM_CROSS: *ptr = p->cross.p; *bytes = 4 * n; break;
+    case VM_FIELD_SSIM_VALUE: *ptr = p->value.p; *bytes = 4 * n; break;
+    case VM_FIELD_SSIM_COUNTER: *ptr = p->counter.p; *bytes = 4 * n; break;
+    case VM_FIELD_TPS_AXY: *ptr = p->tps_axy.p; *bytes = 4 * n; break;
+    case VM_FIELD_TPS_B: *ptr = p->tps_b.p; *bytes = 8 * n; break;
+    case VM_FIELD_UI_AXY: *ptr = p->ui_axy.p; *bytes = 4 * n; break;
+    case VM_FIELD_UI_B: *ptr = p->ui_b.p; *bytes = 8 * n; break;
+    case VM_FIELD_TEMP_REF: *ptr = p->temp_ref.p; *bytes = 8 * n; break;
+    case VM_FIELD_TEMP_MASK: *ptr = p->temp_mask.p; *bytes = 4 * n; break;
+    case VM_FIELD_IMPROVING_MASK: *ptr = p->impmask.p; *bytes = 4 * (size_t)L.ips * L.d; break;
+    case VM_FIELD_IMG0: *ptr = L.img0.p; *bytes = 4 * fs; break;
+    case VM_FIELD_IMG1: *ptr = L.img1.p; *bytes = 4 * fs; break;
+    case VM_FIELD_F0: *ptr = L.f0.p; *bytes = 8 * fs; break;
+    case VM_FIELD_F1: *ptr = L.f1.p; *bytes = 8 * fs; break;
+    case VM_FIELD_B0: *ptr = L.b0.p; *bytes = 8 * fs; break;
+    case VM_FIELD_B1: *ptr = L.b1.p; *bytes = 8 * fs; break;
+    default: set_error("unknown field %d", field); return VM_ERR_ARG;
+    }
+    if (!*ptr) { set_error("field %d of level %d is not allocated", field, level); return VM_ERR_STATE; }
+    return VM_OK;
+}
+
+int vm_level_get(vm_pyramid *p, int level, int field, void *host_out, size_t nbytes) {
+    void *ptr; size_t bytes;
+    int rc = field_ptr(p, level, field, &ptr, &bytes); if (rc) return rc;
+    if (nbytes != bytes || !host_out) { set_error("field %d level %d: %zu bytes expected, %zu given", field, level, bytes, nbytes); return VM_ERR_ARG; }
+    rc = use_device(p->device); if (rc) return rc;
+    VM_CUDA(cudaDeviceSynchronize());
+    VM_CUDA(cudaMemcpy(host_out, ptr, bytes, cudaMemcpyDeviceToHost));
+    return VM_OK;
+}
+int vm_level_set(vm_pyramid *p, int level, int field, const void *host_in, size_t nbytes) {
+    void *ptr; size_t bytes;
+    int rc = field_ptr(p, level, field, &ptr, &bytes); if (rc) return rc;
+    if (nbytes != bytes || !host_in) { set_error("field %d level %d: %zu bytes expected, %zu given", field, level, bytes, nbytes); return VM_ERR_ARG; }
+    rc = use_device(p->device); if (rc) return rc;
+    VM_CUDA(cudaDeviceSynchronize());
+    VM_CUDA(cudaMemcpy(ptr, host_in, bytes, cudaMemcpyHostToDevice));
+    if (field == VM_FIELD_V) p->lv[level].v_valid = true;
+    return VM_OK;
+}
+
+// ---------------------------------------------------------------- morph
+int vm_morph_create(const vm_params *prm, vm_pyramid *pyr, volatile int *run_flag, vm_morph **out) {
+    if (!prm || !pyr || !out) { set_error("null argument"); return VM_ERR_ARG; }
+    if (pyr->lv.size() < 3) { set_error("pyramid not allocated"); return VM_ERR_STATE; }
+    if (prm->max_iter < 1 || prm->max_iter > 4000 || prm->max_iter_drop_factor <= 0 || prm->eps <= 0) { set_error("bad parameters (max_iter 1..4000, drop > 0, eps > 0)"); return VM_ERR_ARG; }
+    int rc = use_device(pyr->device); if (rc) return rc;
+    vm_morph *m = new vm_morph();
+    m->prm = *prm; m->pyr = pyr; m->run_flag = run_flag;
+    if (run_flag) {
+        if (cudaHostRegister((void *)run_flag, sizeof(int), cudaHostRegisterMapped) == cudaSuccess) {
+            m->run_flag_registered = true;
+            if (cudaHostGetDevicePointer((void **)&m->run_flag_dev, (void *)run_flag, 0) != cudaSuccess) m->run_flag_dev = nullptr;
+        } else cudaGetLastError();
+    }
+    cudaError_t e = cudaHostAlloc((void **)&m->progress_host, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) { m->progress_host[0] = 0; e = cudaHostGetDevicePointer((void **)&m->progress_dev, m->progress_host, 0); }
+    if (e == cudaSuccess) e = m->ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(prm->max_iter + 1));
+    if (e != cudaSuccess) { vm_morph_destroy(m); return cuda_fail(e, "morph_create"); }
+    // morph.cu:128-140
+    m->total_l = (int)pyr->lv.size() - 1;
+    m->max_iter_now = (float)prm->max_iter;
+    int iter_num = prm->max_iter;
+    for (int el = m->total_l - 1; el >= 0; el--)
+        if (el > 0) { m->total_iter += (double)iter_num * pyr->lv[el].w * pyr->lv[el].h * pyr->lv[el].d; iter_num = (int)(iter_num / prm->max_iter_drop_factor); }
+    *out = m;
+    return VM_OK;
+}
+
+void vm_morph_destroy(vm_morph *m) {
+    if (!m) return;
+    cudaSetDevice(m->pyr->device);
+    cudaDeviceSynchronize();
+    if (m->run_flag_registered) cudaHostUnregister((void *)m->run_flag);
+    if (m->progress_host) cudaFreeHost(m->progress_host);
+    delete m;
+}
+
+static int upload_cons(vm_morph *m) {
+    if (m->cons.empty()) return VM_OK;
+    VM_CUDA(m->cons_dev.ensure(sizeof(Conn) * m->cons.size()));
+    VM_CUDA(cudaMemcpy(m->cons_dev.p, m->cons.data(), sizeof(Conn) * m->cons.size(), cudaMemcpyHostToDevice));
+    return VM_OK;
+}
+
+int vm_morph_set_constraints(vm_morph *m, int n, const vm_conp *left, const vm_conp *right) {
+    if (!m || n < 0 || (n > 0 && (!left || !right))) { set_error("bad constraints"); return VM_ERR_ARG; }
+    int rc = use_device(m->pyr->device); if (rc) return rc;
+    m->cons.resize(n);
+    for (int i = 0; i < n; i++) { m->cons[i].l = left[i]; m->cons[i].r = right[i]; }
+    return upload_cons(m);
+}
+
+int vm_morph_set_tracks(vm_morph *m, int n_left, const int32_t *left_len, const vm_conp *left, int n_right,
+                        const int32_t *right_len, const vm_conp *right, int n_groups, const int32_t *group_len,
+                        const vm_connect *connects) {
+    if (!m || n_left < 0 || n_right < 0 || n_groups < 0) { set_error("bad tracks"); return VM_ERR_ARG; }
+    std::vector<size_t> lo(n_left + 1, 0), ro(n_right + 1, 0);
+    for (int i = 0; i < n_left; i++) lo[i + 1] = lo[i] + left_len[i];
+    for (int i = 0; i < n_right; i++) ro[i + 1] = ro[i] + right_len[i];
+    std::vector<Conn> cons;
+    size_t c = 0;
+    for (int k = 0; k < n_groups; k++)                       // iteration order of morph.cu:354-355
+        for (int l = 0; l < group_len[k]; l++, c++) {
+            const vm_connect &cn = connects[c];
+            if (cn.li_track < 0 || cn.li_track >= n_left || cn.ri_track < 0 || cn.ri_track >= n_right ||
+                cn.li_idx < 0 || cn.li_idx >= left_len[cn.li_track] || cn.ri_idx < 0 || cn.ri_idx >= right_len[cn.ri_track]) {
+                set_error("connection %zu references a point outside the tracks", c); return VM_ERR_ARG;
+            }
+            Conn q; q.l = left[lo[cn.li_track] + cn.li_idx]; q.r = right[ro[cn.ri_track] + cn.ri_idx];
+            cons.push_back(q);
+        }
+    int rc = use_device(m->pyr->device); if (rc) return rc;
+    m->cons = cons;
+    return upload_cons(m);
+}
+
+static bool keep_running(vm_morph *m) { return !m->run_flag || *m->run_flag != 0; }
+
+int vm_level_cpu_solve(vm_morph *m, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    int rc = use_device(p->device); if (rc) return rc;
+    int l = (int)p->lv.size() - 1;
+    Level &L = p->lv[l];
+    size_t n = (size_t)L.w * L.h;
+    if (n > 4096) { set_error("coarsest level %dx%d too large for the dense solve", L.w, L.h); return VM_ERR_ARG; }
+    int factor = (int)(p->lv[0].factor_d / L.factor_d);                          // morph.cu:425
+    size_t need_a = sizeof(float) * n * n * L.d, need_b = sizeof(double) * n * n * L.d, need_c = sizeof(double) * 4 * n * L.d + sizeof(int) * L.d;
+    VM_CUDA(p->tmp_a.ensure(need_a)); VM_CUDA(p->tmp_b.ensure(need_b)); VM_CUDA(p->tmp_c.ensure(need_c));
+    VM_CUDA(cudaMemsetAsync(L.v.p, 0, sizeof(float2) * (size_t)L.ps * L.d, s));   // morph.cu:428-429
+    LevelView V = make_view(p, l);
+    int *status = reinterpret_cast<int *>(p->tmp_c.as<double>() + 4 * n * L.d);
+    VM_CUDA(launch_coarse_solve(V, kparams(m->prm), m->cons_dev.as<Conn>(), (int)m->cons.size(), factor, p->lv[0].w, p->lv[0].h, p->lv[0].d,
+                                p->tmp_a.as<float>(), p->tmp_b.as<double>(), p->tmp_c.as<double>(), status, s));
+    L.v_valid = true;
+    return VM_OK;
+}
+
+int vm_level_upsample(vm_morph *m, int dest_level, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    if (dest_level < 1 || dest_level + 1 >= (int)p->lv.size()) { set_error("bad upsample level %d", dest_level); return VM_ERR_ARG; }
+    int rc = use_device(p->device); if (rc) return rc;
+    Level &D = p->lv[dest_level]; Level &O = p->lv[dest_level + 1];
+    if (!O.v_valid) { set_error("level %d has no vector field to upsample", dest_level + 1); return VM_ERR_STATE; }
+    VM_CUDA(cudaMemsetAsync(D.v.p, 0, sizeof(float2) * (size_t)D.ps * D.d, s));   // upsample.cu:262-263
+    int factor = D.d > O.d ? 2 : 1;
+    LevelView V = make_view(p, dest_level);
+    VM_CUDA(launch_upsample(V, O.v.as<float2>(), O.w, O.h, O.rs, O.ps, O.d, factor, s));
+    if (factor > 1) {
+        if (!D.f0.p) { set_error("temporal upsample needs optical flows on level %d", dest_level); return VM_ERR_STATE; }
+        VM_CUDA(p->tmp_a.ensure(sizeof(long long) * 3 * (size_t)D.ps)); VM_CUDA(p->tmp_b.ensure(sizeof(float2) * (size_t)D.ps)); VM_CUDA(p->tmp_c.ensure(sizeof(float) * (size_t)D.ps));
+        VM_CUDA(launch_temporal_infill(V, p->tmp_a.as<long long>(), p->tmp_b.as<float2>(), p->tmp_c.as<float>(), s));
+    }
+    D.v_valid = true;
+    return VM_OK;
+}
+
+int vm_level_initialize(vm_morph *m, int level, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    if (level < 1 || level + 1 >= (int)p->lv.size()) { set_error("bad level %d", level); return VM_ERR_ARG; }
+    int rc = use_device(p->device); if (rc) return rc;
+    Level &L = p->lv[level];
+    if (!L.img0.p || !L.img1.p) { set_error("level %d has no images", level); return VM_ERR_STATE; }
+    size_t n = (size_t)L.ps * L.d;
+    // morph.cu:280-314: (re)size + zero-fill of every per-level array (the arena is reused across levels)
+    VM_CUDA(cudaMemsetAsync(p->mean.p, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(p->var.p, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(p->luma.p, 0, 8 * n, s));
+    VM_CUDA(cudaMemsetAsync(p->cross.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(p->value.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(p->counter.p, 0, 4 * n, s));
+    VM_CUDA(cudaMemsetAsync(p->tps_axy.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(p->tps_b.p, 0, 8 * n, s));
+    VM_CUDA(cudaMemsetAsync(p->ui_axy.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(p->ui_b.p, 0, 8 * n, s));
+    VM_CUDA(cudaMemsetAsync(p->temp_ref.p, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(p->temp_mask.p, 0, 4 * n, s));
+    VM_CUDA(cudaMemsetAsync(p->impmask.p, 0, 4 * (size_t)L.ips * L.d, s));
+    LevelView V = make_view(p, level);
+    VM_CUDA(launch_initialize_level(V, p->stencils.as<StencilTables>(), m->prm.ssim_clamp, s));
+    int factor = (int)(p->lv[0].factor_d / L.factor_d);                          // morph.cu:350
+    VM_CUDA(launch_ui_splat(V, m->cons_dev.as<Conn>(), (int)m->cons.size(), factor, p->lv[0].w, p->lv[0].h, p->lv[0].d, s));
+    p->state_level = level;
+    return VM_OK;
+}
+
+int vm_level_init_temp(vm_morph *m, int level, int frame, int dir, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
+    Level &L = p->lv[level];
+    if ((dir != 1 && dir != -1) || frame < 0 || frame >= L.d || frame + dir < 0 || frame + dir >= L.d) { set_error("bad frame/dir %d/%d", frame, dir); return VM_ERR_ARG; }
+    if (!L.f0.p) { set_error("level %d has no optical flows", level); return VM_ERR_STATE; }
+    int rc = use_device(p->device); if (rc) return rc;
+    VM_CUDA(p->tmp_a.ensure(sizeof(long long) * 3 * (size_t)L.ps));
+    VM_CUDA(launch_initialize_temp(make_view(p, level), frame, dir, p->tmp_a.as<long long>(), s));
+    return VM_OK;
+}
+
+// enqueue one frame's optimisation; iterations land in log_dev[seq]
+static int enqueue_frame(vm_morph *m, int level, int frame, int flag, float max_iter, cudaStream_t s, int *seq_out) {
+    vm_pyramid *p = m->pyr;
+    Level &L = p->lv[level];
+    int seq = (int)m->seqs.size();
+    if (seq >= (1 << 19)) { set_error("too many sweep launches"); return VM_ERR_STATE; }
+    size_t need = sizeof(unsigned) * (size_t)(seq + 1024);
+    if (m->log_dev.bytes < need) {
+        DevBuf nb; VM_CUDA(nb.ensure(need * 2));
+        VM_CUDA(cudaStreamSynchronize(s));
+        if (m->log_dev.p) VM_CUDA(cudaMemcpy(nb.p, m->log_dev.p, m->log_dev.bytes, cudaMemcpyDeviceToDevice));
+        std::swap(nb.p, m->log_dev.p); std::swap(nb.bytes, m->log_dev.bytes);
+    }
+    int iters_cap = (int)ceilf(max_iter) + 1;
+    if (iters_cap < 1) iters_cap = 1;
+    VM_CUDA(m->ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(iters_cap)));
+    VM_CUDA(cudaMemsetAsync(m->ctrl.p, 0, sizeof(unsigned) * sweep_ctrl_words(iters_cap), s));
+    m->seqs.push_back({level, frame, (double)L.w * L.h, max_iter});
+    VM_CUDA(launch_sweep(make_view(p, level), kparams(m->prm), p->stencils.as<StencilTables>(), frame, flag, max_iter,
+                         m->ctrl.as<unsigned>(), m->run_flag_dev, m->progress_dev, seq, p->sm_count, s));
+    VM_CUDA(cudaMemcpyAsync(m->log_dev.as<unsigned>() + seq, m->ctrl.as<unsigned>() + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
+    if (seq_out) *seq_out = seq;
+    return VM_OK;
+}
+
+// fetch iteration counts of launches [from, seqs.size()) and fold them into the counters
+static int collect_log(vm_morph *m, size_t from, cudaStream_t s) {
+    size_t n = m->seqs.size();
+    if (from >= n) return VM_OK;
+    std::vector<unsigned> it(n - from);
+    VM_CUDA(cudaStreamSynchronize(s));
+    VM_CUDA(cudaMemcpy(it.data(), m->log_dev.as<unsigned>() + from, sizeof(unsigned) * (n - from), cudaMemcpyDeviceToHost));
+    for (size_t k = from; k < n; k++) {
+        m->executed_pixel_iters += m->seqs[k].wh * it[k - from];
+        m->iters_log.push_back(m->seqs[k].level); m->iters_log.push_back(m->seqs[k].frame); m->iters_log.push_back((int)it[k - from]);
+    }
+    return VM_OK;
+}
+
+int vm_level_optimize_frame(vm_morph *m, int level, int frame, int flag, float max_iter, int *iters_out, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
+    if (frame < 0 || frame >= p->lv[level].d || !(max_iter > 0) || max_iter > 4000) { set_error("bad frame %d / max_iter %g", frame, max_iter); return VM_ERR_ARG; }
+    int rc = use_device(p->device); if (rc) return rc;
+    size_t from = m->seqs.size();
+    rc = enqueue_frame(m, level, frame, flag, max_iter, s, nullptr); if (rc) return rc;
+    rc = collect_log(m, from, s); if (rc) return rc;
+    if (iters_out) *iters_out = m->iters_log.back();
+    return VM_OK;
+}
+
+// Morph::optimize_level (morph.cu:1353-1441): middle frame, then forward chain, then backward chain.
+static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s) {
+    vm_pyramid *p = m->pyr; Level &L = p->lv[level];
+    int mid = L.d / 2, rc;
+    rc = enqueue_frame(m, level, mid, 0, max_iter, s, nullptr); if (rc) return rc;
+    for (int i = mid + 1; i < L.d; i++) {
+        if (!keep_running(m)) break;
+        rc = vm_level_init_temp(m, level, i, -1, s); if (rc) return rc;
+        rc = enqueue_frame(m, level, i, 1, max_iter, s, nullptr); if (rc) return rc;
+    }
+    for (int i = mid - 1; i >= 0; i--) {
+        if (!keep_running(m)) break;
+        rc = vm_level_init_temp(m, level, i, 1, s); if (rc) return rc;
+        rc = enqueue_frame(m, level, i, 1, max_iter, s, nullptr); if (rc) return rc;
+    }
+    return VM_OK;
+}
+
+int vm_level_optimize(vm_morph *m, int level, float max_iter, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
+    if (!(max_iter > 0) || max_iter > 4000) { set_error("bad max_iter %g", max_iter); return VM_ERR_ARG; }
+    int rc = use_device(p->device); if (rc) return rc;
+    size_t from = m->seqs.size();
+    rc = enqueue_level(m, level, max_iter, s); if (rc) return rc;
+    return collect_log(m, from, s);
+}
+
+// Morph::calculate_halfway_parametrization (morph.cu:150-168)
+int vm_morph_run(vm_morph *m, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    int rc = use_device(p->device); if (rc) return rc;
+    for (int l = 1; l + 1 < (int)p->lv.size(); l++)
+        if (!p->lv[l].img0.p) { set_error("level %d has no images: call vm_pyramid_build first", l); return VM_ERR_STATE; }
+    size_t from = m->seqs.size();
+    m->cancelled = false;
+    float max_iter = (float)m->prm.max_iter;
+    rc = vm_level_cpu_solve(m, s); if (rc) return rc;
+    for (int l = m->total_l - 1; l > 0; l--) {
+        if (!keep_running(m)) { m->cancelled = true; continue; }                // morph.cu:156
+        m->max_iter_now = max_iter;
+        rc = vm_level_upsample(m, l, s); if (rc) return rc;
+        rc = vm_level_initialize(m, l, s); if (rc) return rc;
+        rc = enqueue_level(m, l, max_iter, s); if (rc) return rc;
+        max_iter /= m->prm.max_iter_drop_factor;                                  // morph.cu:163
+    }
+    rc = collect_log(m, from, s); if (rc) return rc;
+    return VM_OK;                                                                  // the reference returns true always
+}
+
+int vm_morph_progress(const vm_morph *m, int *total_l, int *current_l, double *total_iter, double *current_iter, float *max_iter) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    int word = m->progress_host ? *(volatile int *)m->progress_host : 0;
+    size_t seq = (size_t)(word >> 12); int it = word & 4095;
+    double cur = 0; int lvl = m->total_l; float mi = m->max_iter_now;
+    size_t n = m->seqs.size();
+    for (size_t k = 0; k < n && k < seq; k++) cur += m->seqs[k].wh * m->seqs[k].max_iter;      // morph.cu:1391
+    if (seq < n) { cur += m->seqs[seq].wh * it; lvl = m->seqs[seq].level; mi = m->seqs[seq].max_iter; }
+    if (total_l) *total_l = m->total_l;
+    if (current_l) *current_l = lvl;
+    if (total_iter) *total_iter = m->total_iter;
+    if (current_iter) *current_iter = cur;
+    if (max_iter) *max_iter = mi;
+    return VM_OK;
+}
+double vm_morph_executed_pixel_iters(const vm_morph *m) { return m ? m->executed_pixel_iters : 0.0; }
+int vm_morph_iters_log(const vm_morph *m, int max_triples, int32_t *out) {
+    if (!m) return VM_ERR_ARG;
+    int n = (int)m->iters_log.size() / 3;
+    for (int i = 0; i < n && i < max_triples; i++) for (int k = 0; k < 3; k++) out[i * 3 + k] = m->iters_log[i * 3 + k];
+    return n;
+}
+
+int vm_level_energy(vm_morph *m, int level, int frame, int flag, double *energy_out, double *terms_out) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr;
+    if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
+    if (frame < 0 || frame >= p->lv[level].d) { set_error("bad frame"); return VM_ERR_ARG; }
+    int rc = use_device(p->device); if (rc) return rc;
+    VM_CUDA(cudaDeviceSynchronize());
+    DevBuf out; VM_CUDA(out.ensure(4 * sizeof(double)));
+    VM_CUDA(launch_energy(make_view(p, level), kparams(m->prm), frame, flag, out.as<double>(), 0));
+    double t[4];
+    VM_CUDA(cudaMemcpy(t, out.p, sizeof(t), cudaMemcpyDeviceToHost));
+    if (terms_out) for (int k = 0; k < 4; k++) terms_out[k] = t[k];
+    if (energy_out) *energy_out = t[0] + t[1] + t[2] + t[3];
+    return VM_OK;
+}
+
+int vm_morph_get_vectors(vm_morph *m, float *host_out, void *stream) {
+    if (!m || !host_out) { set_error("null argument"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    int rc = use_device(p->device); if (rc) return rc;
+    Level &L0 = p->lv[0]; Level &L1 = p->lv[1];
+    if (!L1.v_valid) { set_error("level 1 has no result yet"); return VM_ERR_STATE; }
+    int factor = (int)(L0.factor_d / L1.factor_d);
+    if (factor != 1) { set_error("level 1 is temporally subsampled (factor %d): unsupported", factor); return VM_ERR_STATE; }
+    size_t bytes = sizeof(float2) * (size_t)L0.w * L0.h * L0.d;
+    DevBuf out; VM_CUDA(out.ensure(bytes));
+    VM_CUDA(launch_extract(make_view(p, 1), out.as<float2>(), L0.w, L0.h, L0.d, factor, s));
+    VM_CUDA(cudaMemcpyAsync(host_out, out.p, bytes, cudaMemcpyDeviceToHost, s));
+    VM_CUDA(cudaStreamSynchronize(s));
+    return VM_OK;
+}
+
+// ---------------------------------------------------------------- render
+int vm_render_halfway_dev(uint8_t *out_dev, int rowstride, int w, int h, int ex, float color_fa, float geo_fa, int color_from,
+                          const uint8_t *ext0_dev, const uint8_t *ext1_dev, const float *vector_dev, const float *qpath_dev, void *stream) {
+    if (!out_dev || !ext0_dev || !ext1_dev || !vector_dev || w <= 0 || h <= 0 || ex < 0 || rowstride < w || color_from < 0 || color_from > 2) {
+        set_error("bad render arguments"); return VM_ERR_ARG; }
+    if (vm_device_count() == 0) { set_error("no CUDA device available: libvmorph has no CPU fallback"); return VM_ERR_CUDA; }
+    VM_CUDA(launch_render(out_dev, rowstride, w, h, ex, color_fa, geo_fa, color_from, ext0_dev, ext1_dev,
+                          reinterpret_cast<const float2 *>(vector_dev), reinterpret_cast<const float2 *>(qpath_dev), (cudaStream_t)stream));
+    return VM_OK;
+}
+
+int vm_render_halfway(int device, uint8_t *out, int w, int h, int ex, float color_fa, float geo_fa, int color_from,
+                      const uint8_t *ext0, const uint8_t *ext1, const float *vector, const float *qpath, void *stream) {
+    if (!out || !ext0 || !ext1 || !vector || w <= 0 || h <= 0 || ex < 0) { set_error("bad render arguments"); return VM_ERR_ARG; }
+    int rc = use_device(device); if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rowstride = (w + 31) / 32 * 32;                                          // UI/RenderWidget.cpp:235
+    size_t eb = (size_t)(w + 2 * ex) * (h + 2 * ex) * 4, vb = sizeof(float2) * (size_t)w * h, ob = (size_t)rowstride * h * 3;
+    DevBuf d_e0, d_e1, d_v, d_q, d_o;
+    VM_CUDA(d_e0.ensure(eb)); VM_CUDA(d_e1.ensure(eb)); VM_CUDA(d_v.ensure(vb)); VM_CUDA(d_o.ensure(ob));
+    VM_CUDA(cudaMemcpyAsync(d_e0.p, ext0, eb, cudaMemcpyHostToDevice, s));
+    VM_CUDA(cudaMemcpyAsync(d_e1.p, ext1, eb, cudaMemcpyHostToDevice, s));
+    VM_CUDA(cudaMemcpyAsync(d_v.p, vector, vb, cudaMemcpyHostToDevice, s));
+    if (qpath) { VM_CUDA(d_q.ensure(vb)); VM_CUDA(cudaMemcpyAsync(d_q.p, qpath, vb, cudaMemcpyHostToDevice, s)); }
+    rc = vm_render_halfway_dev(d_o.as<uint8_t>(), rowstride, w, h, ex, color_fa, geo_fa, color_from, d_e0.as<uint8_t>(), d_e1.as<uint8_t>(),
+                               d_v.as<float>(), qpath ? d_q.as<float>() : nullptr, stream);
+    if (rc) return rc;
+    VM_CUDA(cudaMemcpy2DAsync(out, (size_t)w * 3, d_o.p, (size_t)rowstride * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s));   // RenderWidget.cpp:258
+    VM_CUDA(cudaStreamSynchronize(s));
+    return VM_OK;
+}
+
+// ---------------------------------------------------------------- device memory helpers
+int vm_dev_alloc(int device, size_t nbytes, void **out_dev) {
+    if (!out_dev || nbytes == 0) { set_error("bad alloc"); return VM_ERR_ARG; }
+    int rc = use_device(device); if (rc) return rc;
+    VM_CUDA(cudaMalloc(out_dev, nbytes));
+    return VM_OK;
+}
+int vm_dev_free(int device, void *dev) { int rc = use_device(device); if (rc) return rc; VM_CUDA(cudaFree(dev)); return VM_OK; }
+int vm_dev_upload(int device, void *dst_dev, const void *src_host, size_t nbytes, void *stream) {
+    int rc = use_device(device); if (rc) return rc;
+    VM_CUDA(cudaMemcpyAsync(dst_dev, src_host, nbytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return VM_OK;
+}
+int vm_dev_download(int device, void *dst_host, const void *src_dev, size_t nbytes, void *stream) {
+    int rc = use_device(device); if (rc) return rc;
+    VM_CUDA(cudaMemcpyAsync(dst_host, src_dev, nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return VM_OK;
+}
+int vm_stream_sync(int device, void *stream) { int rc = use_device(device); if (rc) return rc; VM_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return VM_OK; }
+
+}  // extern "C"

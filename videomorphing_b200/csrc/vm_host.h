@@ -1,0 +1,125 @@
+// vm_host.h -- host-side declarations shared by the libvmorph translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include <atomic>
+#include "vm_device.cuh"
+#include "../../include/vmorph.h"
+
+namespace vm {
+
+void count_launch(int n = 1);
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);     // records the error, returns VM_ERR_CUDA
+
+#define VM_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ::vm::cuda_fail(e__, #call); } while (0)
+
+// ---- host-side stencil tables (our own formulation; stencils.cpp is the reference) ----
+struct HostStencils {
+    int iomask[5][5][5][5];
+    int improvmask[5][5][3][3];
+    float tps[5][5][5][5];
+};
+void build_stencils(HostStencils &s);
+void pack_stencils(const HostStencils &s, StencilTables &t);
+
+// ---- level schedule (pyramid.cu:219-236,463-477) ----
+struct SchedEntry { int w, h, d; float factor_d; int factor_t; };
+std::vector<SchedEntry> level_schedule(int w, int h, int d, int start_res, int64_t voxel_cap);
+
+// ---- device buffer ----
+struct DevBuf {
+    void *p = nullptr; size_t bytes = 0;
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete; DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; } return *this; }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// One pyramid level (Pyramid.h:51-95).  Images/flows and v are per level; the optimizer's scratch state lives in
+// the pyramid-wide arena (re-initialised by initialize_level for whichever level is current).
+struct Level {
+    int w = 0, h = 0, d = 0, rs = 0, ps = 0, irs = 0, ips = 0;
+    float factor_d = 1.f, inv_wh = 0.f;
+    int factor_t = 1;
+    bool has_images = false;
+    DevBuf img0, img1, f0, f1, b0, b1, v;
+    bool v_valid = false, flows_valid = false;
+};
+
+struct Conn { vm_conp l, r; };
+
+}  // namespace vm
+
+struct vm_pyramid {
+    int device = 0;
+    int sm_count = 148;
+    std::vector<vm::Level> lv;
+    int w0 = 0, h0 = 0, d0 = 0;
+    // optimizer scratch arena, sized for the largest optimised level
+    vm::DevBuf mean, var, luma, tps_b, ui_b, temp_ref, cross, value, counter, tps_axy, ui_axy, temp_mask, impmask;
+    int state_level = -1;                 // which level the arena currently describes
+    vm::DevBuf stencils;                  // StencilTables on the device
+    vm::DevBuf tmp_a, tmp_b, tmp_c;       // transient scratch (splat accumulators, coarse solve, resampler planes)
+    vm::HostStencils hst;
+};
+
+struct vm_morph {
+    vm_params prm;
+    vm_pyramid *pyr = nullptr;
+    volatile int *run_flag = nullptr;     // caller's flag (host memory); registered as mapped memory when possible
+    int *run_flag_dev = nullptr;          // device alias of run_flag (NULL: polled on the host between launches only)
+    bool run_flag_registered = false;
+    int *progress_host = nullptr;         // cudaHostAllocMapped word written by the sweep kernel: (seq << 12) | iteration
+    int *progress_dev = nullptr;
+    std::vector<vm::Conn> cons;
+    vm::DevBuf cons_dev;
+    vm::DevBuf ctrl;                      // sweep control block
+    vm::DevBuf log_dev;                   // iterations executed per sweep launch (one word per launch)
+    // launch table for progress reporting: seq -> (level, frame, w*h, max_iter)
+    struct Seq { int level, frame; double wh; float max_iter; };
+    std::vector<Seq> seqs;
+    // morph.h:17-20 progress fields
+    int total_l = 0;
+    double total_iter = 0;
+    float max_iter_now = 0;
+    double executed_pixel_iters = 0;
+    std::vector<int32_t> iters_log;
+    bool cancelled = false;
+};
+
+namespace vm {
+
+LevelView make_view(vm_pyramid *p, int level);
+
+// kernels (launchers) -- vm_kernels.cu / vm_sweep.cu / vm_render.cu / vm_resample.cu
+cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
+                         unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, cudaStream_t stream);
+size_t sweep_ctrl_words(int max_iter_ceil);
+
+cudaError_t launch_initialize_level(const LevelView &L, const StencilTables *st, float ssim_clamp, cudaStream_t s);
+cudaError_t launch_ui_splat(const LevelView &L, const Conn *cons_dev, int ncons, int factor, int w0, int h0, int d0, cudaStream_t s);
+cudaError_t launch_upsample(const LevelView &dst, const float2 *src_v, int sw, int sh, int srs, int sps, int sd, int factor, cudaStream_t s);
+cudaError_t launch_temporal_infill(const LevelView &dst, long long *acc /*3*ps*/, float2 *vtmp /*ps*/, float *wtmp /*ps*/, cudaStream_t s);
+cudaError_t launch_initialize_temp(const LevelView &L, int frame, int dir, long long *acc /*3*ps*/, cudaStream_t s);
+cudaError_t launch_coarse_solve(const LevelView &L, const KParams &P, const Conn *cons_dev, int ncons, int factor, int w0, int h0, int d0,
+                                float *Af, double *Ad, double *rhs, int *status, cudaStream_t s);
+cudaError_t launch_energy(const LevelView &L, const KParams &P, int frame, int flag, double *out4_dev, cudaStream_t s);
+cudaError_t launch_extract(const LevelView &L1, float2 *out, int w0, int h0, int d0, int factor, cudaStream_t s);
+cudaError_t launch_render(uint8_t *out, int rowstride, int w, int h, int ex, float color_fa, float geo_fa, int color_from,
+                          const uint8_t *ext0, const uint8_t *ext1, const float2 *vec, const float2 *qpath, cudaStream_t s);
+
+}  // namespace vm

@@ -1,0 +1,481 @@
+// vm_sweep.cu -- the halfway-domain optimizer sweep for sm_100a.
+//
+// Replaces kernel_optimize_level and its device functions (Algorithm/morph.cu:594-1345) and the host iteration loop of
+// Morph::optimize_level (morph.cu:1377-1391).  It is NOT a port of that kernel:
+//   * one persistent cooperative launch per (level, frame) runs ALL iterations x 4 offset steps on the device, with a
+//     grid barrier between steps and a device-side "did anything improve" vote -- the reference pays 4 launches, a
+//     cudaDeviceSynchronize and a mapped-host read per iteration (morph.cu:1380-1390);
+//   * each 68x20 tile (SSIM sums, counter and the TPS linear term) is staged in shared memory once per step;
+//   * active pixels of a colour sub-phase are compacted into a queue and each is optimised by one WARP: lane k owns
+//     window k of the 5x5 SSIM neighbourhood in registers, the 25-term energy sum is a butterfly warp reduction,
+//     so the ~21 energy evaluations of gradient + golden-section search touch no shared memory at all;
+//   * commits are deterministic gathers (fixed row-major contributor order) instead of float atomics
+//     (morph.cu:982-984,1013), so the result is reproducible and equals the CPU oracle op for op;
+//   * tiles whose improving-mask words are all clear are skipped without touching their state.
+// The schedule -- tile origins bx*69+off-2, offsets (0,0),(64,0),(0,16),(64,16), sub-phase order i outer / j inner,
+// stride-2 pixel lattice, improving-mask cell layout -- is the reference's, bit for bit.
+#include "vm_device.cuh"
+#include "vm_host.h"
+
+namespace vm {
+
+constexpr int OPT_BW = 32, OPT_BH = 8, SPACING = 5;        // morph.cu:594-598
+constexpr int TW = OPT_BW * 2 + 4, TH = OPT_BH * 2 + 4;    // 68 x 20 tile (morph.cu:600-609)
+constexpr int TCELLS = TW * TH;
+constexpr int NPIX = OPT_BW * OPT_BH;                      // pixels per colour sub-phase
+
+struct SweepSmem {
+    float2 mean[TCELLS], var[TCELLS], tpsb[TCELLS];
+    float cross[TCELLS], value[TCELLS], cnt[TCELLS];
+    float2 s_d[NPIX], s_dm[NPIX], s_dv[NPIX];
+    float s_dc[NPIX];
+    unsigned char status[NPIX];      // 0 = no mask index, 1 = has index / not accepted, 2 = accepted
+    unsigned char bcls[NPIX];        // By*5+Bx of the pixel
+    unsigned short queue[NPIX];
+    float tps[25 * 25];
+    unsigned int iomask[25];
+    int qcount;
+    int tile_flag;
+    int sub_flag;
+    int cta_improving;
+};
+
+// ------------------------------------------------------------------ grid barrier
+// Monotonic counter; all CTAs of the cooperative launch are co-resident.
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &epoch, unsigned int nblocks) {
+    __syncthreads();
+    epoch += nblocks;
+    if (nblocks > 1) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(counter, 1u);
+            while (*((volatile unsigned int *)counter) < epoch) { __nanosleep(32); }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+// morph.cu:621-646
+__device__ __forceinline__ int get_improve_mask_idx(const LevelView &L, const StencilTables *__restrict__ st, int page, int px, int py) {
+    int bx = px / 5, by = py / 5, ox = px - bx * 5, oy = py - by * 5;
+    int begi = oy >= 2 ? 1 : 0, begj = ox >= 2 ? 1 : 0;
+    int impmask_idx = page * L.ips + (by + 1) * L.irs + (bx + 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            int ii = begi + i, jj = begj + j;
+            int d = impmask_idx + (ii - 1) * L.irs + (jj - 1);
+            if (__ldcg(L.impmask + d) & __ldg(&st->improv[oy * 5 + ox][ii * 3 + jj])) return impmask_idx;
+        }
+    return -1;
+}
+
+// morph.cu:648-667 (the BCOND_CORNER '&&' typo is kept: only the two x==0 corners lock, unless h==1)
+__device__ __forceinline__ bool pixel_on_border(const LevelView &L, int bcond, int px, int py) {
+    int W = L.w, H = L.h;
+    if (bcond == 1) return (px == 0 && py == 0) || (px == 0 && py == H - 1) || (px == W - 1 && py == 0 && px == W - 1 && py == H - 1);
+    if (bcond == 2) return px == 0 || py == 0 || px == W - 1 || py == H - 1;
+    return false;
+}
+
+__device__ __forceinline__ float warp_sum_tree(float t) {
+    // 32-leaf butterfly: lane k ends with ((t_k + t_{k^16}) + ...) -- identical on every lane (fp add commutes)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) t = t + __shfl_xor_sync(0xffffffffu, t, off);
+    return t;
+}
+
+// Per-warp state for one pixel; scalar members are identical on all lanes, w_* are per-lane (window k = lane).
+struct PixelEval {
+    const float *I0, *I1;
+    int W, H, px, py;
+    float2 v, old_luma;
+    float tps_axy, ui_axy, tmask;
+    float2 tps_b, ui_b, tref;
+    float2 w_mean, w_var;
+    float w_cross, w_value, w_cnt;
+    bool w_valid, flag;
+    float w_ui, w_tps, w_ssim, w_temp, ssim_clamp, inv_wh, factor_d;
+
+    // morph.cu:672-761 (ssim_change + energy_change)
+    __device__ __forceinline__ float energy(float2 d) const {
+        float2 nv = make_float2(v.x + d.x, v.y + d.y);
+        float2 luma;
+        luma.x = tex2d<true>(I0, W, H, (float)px - nv.x + 0.5f, (float)py - nv.y + 0.5f);
+        luma.y = tex2d<true>(I1, W, H, (float)px + nv.x + 0.5f, (float)py + nv.y + 0.5f);
+        float term = 0.0f;
+        if (w_valid) {
+            float2 dmean = make_float2(luma.x - old_luma.x, luma.y - old_luma.y);
+            float2 dvar = make_float2(luma.x * luma.x - old_luma.x * old_luma.x, luma.y * luma.y - old_luma.y * old_luma.y);
+            float dcross = luma.x * luma.y - old_luma.x * old_luma.y;
+            float2 m = make_float2(w_mean.x + dmean.x, w_mean.y + dmean.y);
+            float2 vr = make_float2(w_var.x + dvar.x, w_var.y + dvar.y);
+            float cr = w_cross + dcross;
+            term = w_value - ssim_value(m, vr, cr, w_cnt, ssim_clamp);
+        }
+        float v_ssim = warp_sum_tree(term);
+        float dd = d.x * d.x + d.y * d.y;
+        float v_tps = tps_axy * dd;
+        v_tps += tps_b.x * d.x;
+        v_tps += tps_b.y * d.y;
+        float v_ui = ui_axy * dd;
+        v_ui += ui_b.x * d.x;
+        v_ui += ui_b.y * d.y;
+        float v_temp = 0.0f;
+        if (flag) {
+            v_temp += fabsf(v.x + d.x - tref.x) - fabsf(v.x - tref.x);
+            v_temp += fabsf(v.y + d.y - tref.y) - fabsf(v.y - tref.y);
+        }
+        return (w_ui * v_ui + w_ssim * v_ssim + w_temp * v_temp * tmask * factor_d) * inv_wh + w_tps * v_tps;
+    }
+};
+
+// morph.cu:794-831
+__device__ __forceinline__ void fover_update_isec_min(float2 c, float2 grad, float2 e0, float2 e1, float &t_min) {
+    float2 de = make_float2(e1.x - e0.x, e1.y - e0.y), dce = make_float2(c.x - e0.x, c.y - e0.y);
+    float d = de.y * grad.x - de.x * grad.y;
+    float td = -1;
+    float ud = grad.x * dce.y - grad.y * dce.x;
+    int sign = (__float_as_int(d) < 0) ? 1 : 0;      // signbit(d), true for -0.0 too
+    if (sign) { ud = -ud; d = -d; }
+    if (ud >= 0 && ud <= d) {
+        td = de.x * dce.y - de.y * dce.x;
+        td *= (float)(-sign * 2 + 1);
+        if (td >= 0 && td < t_min * d) t_min = td / d;
+    }
+}
+
+// morph.cu:782-792 + 833-870.  nb[8] = v of the 8 neighbours in the order (-1,-1),(0,-1),(1,-1),(1,0),(1,1),(0,1),(-1,1),(-1,0),
+// inb bit k = neighbour k inside the image.  Quirk kept: vertex position is p-off with the vector of p+off.
+__device__ __forceinline__ void fover_calc_isec_min(int SIGN, int px, int py, const float2 *nb, unsigned inb, float2 v, float2 grad, float &t_min) {
+    const int OX[8] = {-1, 0, 1, 1, 1, 0, -1, -1}, OY[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+    float2 c = make_float2((float)px + v.x, (float)py + v.y);
+    float2 first, prev;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        float2 vv = v;
+        if ((inb >> k) & 1) vv = make_float2((float)SIGN * nb[k].x, (float)SIGN * nb[k].y);
+        float2 e = make_float2(vv.x + (float)(px - OX[k]), vv.y + (float)(py - OY[k]));
+        if (k == 0) first = e; else fover_update_isec_min(c, grad, prev, e, t_min);
+        prev = e;
+    }
+    fover_update_isec_min(c, grad, prev, first, t_min);
+}
+
+// One warp optimises one pixel (morph.cu:1030-1083: compute_gradient, prevent_foldover, golden_section_search).
+// Returns true (uniformly) if the move is accepted; d_out = step.
+__device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float eps, const float2 *nb, unsigned inb, float2 &d_out) {
+    float2 g;
+    g.x = E.energy(make_float2(eps, 0.0f)) - E.energy(make_float2(-eps, 0.0f));
+    g.y = E.energy(make_float2(0.0f, eps)) - E.energy(make_float2(0.0f, -eps));
+    float2 grad = make_float2(-g.x, -g.y);
+    float ng = sqrtf(grad.x * grad.x + grad.y * grad.y);
+    if (ng == 0.0f) return false;
+    grad.x = grad.x / ng; grad.y = grad.y / ng;
+    // prevent_foldover, morph.cu:872-883
+    float t_min = 10.0f;
+    fover_calc_isec_min(-1, E.px, E.py, nb, inb, make_float2(-E.v.x, -E.v.y), make_float2(-grad.x, -grad.y), t_min);
+    fover_calc_isec_min(1, E.px, E.py, nb, inb, E.v, grad, t_min);
+    float c = maxf_std(t_min - eps, 0.0f);
+    // golden_section_search, morph.cu:885-947
+    const float R = 0.618033989f, C = 1.0f - R;
+    float a = 0.0f;
+    float b = a * R + c * C, x = b * R + c * C;
+    float fb = E.energy(make_float2(grad.x * b, grad.y * b)), fx = E.energy(make_float2(grad.x * x, grad.y * x));
+    while (c - a > eps) {
+        bool lt = fx < fb;
+        if (lt) { a = b; b = x; x = b * R + c * C; }
+        else { c = x; x = b * R + a * C; }
+        float f = E.energy(make_float2(grad.x * x, grad.y * x));
+        if (lt) { fb = fx; fx = f; }
+        else { float t = b; b = x; x = t; fx = fb; fb = f; }
+    }
+    float tmin, fmin;
+    if (fx < fb) { tmin = x; fmin = fx; } else { tmin = b; fmin = fb; }
+    if (fmin < 0.0f) { d_out = make_float2(grad.x * tmin, grad.y * tmin); return true; }
+    return false;
+}
+
+// One tile of one offset step (one block of one launch of the reference, morph.cu:1281-1345).
+template <int NW>
+__device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, const StencilTables *__restrict__ st,
+                          int page, bool flag, int ox, int oy) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = NW * 32;
+    const size_t poff = (size_t)page * L.ps;
+    const float *I0 = L.img0 + (size_t)page * L.w * L.h, *I1 = L.img1 + (size_t)page * L.w * L.h;
+
+    // --- tile skip: no improving bit anywhere near the processed region => no pixel can be active (exact)
+    {
+        int cx0 = max(ox, 0) / 5, cx1 = min(ox + TW - 1, L.w - 1) / 5;
+        int cy0 = max(oy, 0) / 5, cy1 = min(oy + TH - 1, L.h - 1) / 5;
+        int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1;
+        int any = 0;
+        for (int k = tid; k < ncx * ncy; k += NT) {
+            int cy = cy0 + k / ncx, cx = cx0 + k % ncx;
+            any |= __ldcg(L.impmask + page * L.ips + (cy + 1) * L.irs + (cx + 1)) != 0u;
+        }
+        if (!__syncthreads_or(any)) return;
+    }
+    // --- LoadSSIM (morph.cu:1214-1234) + counter + tps.b
+    for (int c = tid; c < TCELLS; c += NT) {
+        int sy = c / TW, sx = c - sy * TW;
+        int x = ox + sx, y = oy + sy;
+        if (x >= 0 && x < L.w && y >= 0 && y < L.h) {
+            size_t i = (size_t)y * L.rs + x + poff;
+            S.mean[c] = __ldcg(L.mean + i); S.var[c] = __ldcg(L.var + i); S.tpsb[c] = __ldcg(L.tps_b + i);
+            S.cross[c] = __ldcg(L.cross + i); S.value[c] = __ldcg(L.value + i); S.cnt[c] = __ldcg(L.counter + i);
+        } else {
+            S.mean[c] = S.var[c] = S.tpsb[c] = make_float2(0.f, 0.f);
+            S.cross[c] = S.value[c] = S.cnt[c] = 0.f;
+        }
+    }
+    if (tid == 0) S.tile_flag = 0;
+    __syncthreads();
+
+    for (int si = 0; si < 2; ++si)
+        for (int sj = 0; sj < 2; ++sj) {
+            // ---- filter: which pixels of this colour have an improving neighbourhood (morph.cu:1041-1054)
+            if (tid == 0) { S.qcount = 0; S.sub_flag = 0; }
+            __syncthreads();
+            if (tid < NPIX) {
+                int tx = tid & 31, ty = tid >> 5;
+                int px = ox + tx * 2 + sj + 2, py = oy + ty * 2 + si + 2;
+                unsigned char stt = 0;
+                bool act = false;
+                if (px >= 0 && px < L.w && py >= 0 && py < L.h) {
+                    int idx = get_improve_mask_idx(L, st, page, px, py);
+                    if (idx >= 0) { stt = 1; act = !pixel_on_border(L, P.bcond, px, py); }
+                    S.bcls[tid] = (unsigned char)(border_class(py, L.h) * 5 + border_class(px, L.w));
+                }
+                S.status[tid] = stt;
+                unsigned bal = __ballot_sync(0xffffffffu, act);
+                int base = 0;
+                if (lane == 0 && bal) base = atomicAdd(&S.qcount, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (act) S.queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)tid;
+            }
+            __syncthreads();
+            // ---- compute: one warp per active pixel, all from the pre-sub-phase state
+            const int qn = S.qcount;
+            for (int q = warp; q < qn; q += NW) {
+                int slot = S.queue[q];
+                int tx = slot & 31, ty = slot >> 5;
+                int lx = tx * 2 + sj + 2, ly = ty * 2 + si + 2;
+                int px = ox + lx, py = oy + ly;
+                size_t idx = (size_t)py * L.rs + px + poff;
+                PixelEval E;
+                E.I0 = I0; E.I1 = I1; E.W = L.w; E.H = L.h; E.px = px; E.py = py;
+                E.v = __ldcg(L.v + idx); E.old_luma = __ldcg(L.luma + idx);
+                E.tps_axy = __ldcg(L.tps_axy + idx); E.ui_axy = __ldcg(L.ui_axy + idx);
+                E.ui_b = __ldcg(L.ui_b + idx);
+                E.tps_b = S.tpsb[ly * TW + lx];
+                E.flag = flag;
+                E.tref = make_float2(0.f, 0.f); E.tmask = 0.f;
+                if (flag) { E.tref = __ldcg(L.temp_ref + idx); E.tmask = __ldcg(L.temp_mask + idx); }
+                E.w_ui = P.w_ui; E.w_tps = P.w_tps; E.w_ssim = P.w_ssim; E.w_temp = P.w_temp; E.ssim_clamp = P.ssim_clamp;
+                E.inv_wh = L.inv_wh; E.factor_d = L.factor_d;
+                int B = S.bcls[slot];
+                E.w_valid = false; E.w_mean = E.w_var = make_float2(0.f, 0.f); E.w_cross = E.w_value = 0.f; E.w_cnt = 0.f;
+                if (lane < 25) {
+                    int wi = lane / 5, wj = lane - wi * 5;
+                    if ((S.iomask[B] >> lane) & 1u) {
+                        int c = (ly + wi - 2) * TW + (lx + wj - 2);
+                        E.w_valid = true;
+                        E.w_mean = S.mean[c]; E.w_var = S.var[c]; E.w_cross = S.cross[c]; E.w_value = S.value[c]; E.w_cnt = S.cnt[c];
+                    }
+                }
+                // neighbour vectors for the fold-over test (morph.cu:788-789)
+                float2 nb[8]; unsigned inb = 0;
+                {
+                    const int OX[8] = {-1, 0, 1, 1, 1, 0, -1, -1}, OY[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        int nx = px + OX[k], ny = py + OY[k];
+                        nb[k] = make_float2(0.f, 0.f);
+                        if (nx >= 0 && nx < L.w && ny >= 0 && ny < L.h) { inb |= 1u << k; nb[k] = __ldcg(L.v + (size_t)ny * L.rs + nx + poff); }
+                    }
+                }
+                float2 d;
+                bool ok = optimize_pixel_warp(E, P.eps, nb, inb, d);
+                if (ok && lane == 0) { S.status[slot] = 2; S.s_d[slot] = d; }
+            }
+            __syncthreads();
+            // ---- commit A: per accepted pixel own-cell updates (morph.cu:951-971,1017-1025,1320-1332)
+            if (tid < NPIX) {
+                int stt = S.status[tid];
+                if (stt) {
+                    int tx = tid & 31, ty = tid >> 5;
+                    int px = ox + tx * 2 + sj + 2, py = oy + ty * 2 + si + 2;
+                    int bx = px / 5, by = py / 5;
+                    unsigned bit = 1u << ((px - bx * 5) + (py - by * 5) * 5);
+                    unsigned *mw = L.impmask + page * L.ips + (by + 1) * L.irs + (bx + 1);
+                    if (stt == 2) {
+                        size_t idx = (size_t)py * L.rs + px + poff;
+                        float2 d = S.s_d[tid];
+                        float2 v = __ldcg(L.v + idx), old_luma = __ldcg(L.luma + idx);
+                        float2 newv = make_float2(v.x + d.x, v.y + d.y);
+                        float2 luma;
+                        luma.x = tex2d<true>(I0, L.w, L.h, (float)px - newv.x + 0.5f, (float)py - newv.y + 0.5f);
+                        luma.y = tex2d<true>(I1, L.w, L.h, (float)px + newv.x + 0.5f, (float)py + newv.y + 0.5f);
+                        L.luma[idx] = luma;
+                        S.s_dm[tid] = make_float2(luma.x - old_luma.x, luma.y - old_luma.y);
+                        S.s_dv[tid] = make_float2(luma.x * luma.x - old_luma.x * old_luma.x, luma.y * luma.y - old_luma.y * old_luma.y);
+                        S.s_dc[tid] = luma.x * luma.y - old_luma.x * old_luma.y;
+                        float axy = __ldcg(L.ui_axy + idx);
+                        float2 ub = __ldcg(L.ui_b + idx);
+                        ub.x += 2 * d.x * axy; ub.y += 2 * d.y * axy;
+                        L.ui_b[idx] = ub;
+                        L.v[idx] = newv;
+                        atomicOr(mw, bit);
+                        S.tile_flag = 1; S.sub_flag = 1;
+                    } else {
+                        atomicAnd(mw, ~bit);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- commit B: deterministic gather of the SSIM-sum and TPS deltas into the tile, then UpdateSSIM
+            //      (morph.cu:973-987,1006-1015,1258-1279).  Contributors in row-major order of the source pixel.
+            if (S.sub_flag) {
+                for (int c = tid; c < TCELLS; c += NT) {
+                    int sy = c / TW, sx = c - sy * TW;
+                    float2 m = S.mean[c], vr = S.var[c], tb = S.tpsb[c];
+                    float cr = S.cross[c];
+                    bool ch_s = false, ch_t = false;
+#pragma unroll
+                    for (int dy = -2; dy <= 2; dy++) {
+                        int t = sy + dy - si - 2;
+                        if (t < 0 || (t & 1) || (t >> 1) >= OPT_BH) continue;
+#pragma unroll
+                        for (int dx = -2; dx <= 2; dx++) {
+                            int s = sx + dx - sj - 2;
+                            if (s < 0 || (s & 1) || (s >> 1) >= OPT_BW) continue;
+                            int slot = (t >> 1) * OPT_BW + (s >> 1);
+                            if (S.status[slot] != 2) continue;
+                            int B = S.bcls[slot];
+                            int k = (2 - dy) * 5 + (2 - dx);
+                            if ((S.iomask[B] >> k) & 1u) {
+                                float2 dm = S.s_dm[slot], dv = S.s_dv[slot];
+                                m.x += dm.x; m.y += dm.y; vr.x += dv.x; vr.y += dv.y; cr += S.s_dc[slot];
+                                ch_s = true;
+                            }
+                            float T = S.tps[B * 25 + k];
+                            if (T != 0.0f) { float2 d = S.s_d[slot]; tb.x += d.x * T; tb.y += d.y * T; ch_t = true; }
+                        }
+                    }
+                    if (ch_s) {
+                        S.mean[c] = m; S.var[c] = vr; S.cross[c] = cr;
+                        S.value[c] = ssim_value(m, vr, cr, S.cnt[c], P.ssim_clamp);
+                    }
+                    if (ch_t) S.tpsb[c] = tb;
+                }
+            }
+            __syncthreads();
+        }
+    // --- SaveSSIM (morph.cu:1236-1256) + tps.b, only when something was committed
+    if (S.tile_flag) {
+        for (int c = tid; c < TCELLS; c += NT) {
+            int sy = c / TW, sx = c - sy * TW;
+            int x = ox + sx, y = oy + sy;
+            if (x >= 0 && x < L.w && y >= 0 && y < L.h) {
+                size_t i = (size_t)y * L.rs + x + poff;
+                L.mean[i] = S.mean[c]; L.var[i] = S.var[c]; L.cross[i] = S.cross[c]; L.value[i] = S.value[c]; L.tps_b[i] = S.tpsb[c];
+            }
+        }
+        if (tid == 0) S.cta_improving = 1;
+    }
+    __syncthreads();
+}
+
+// ctrl layout (unsigned ints): [0] barrier counter, [1] iterations executed (out), [2] cancelled (out),
+// [8 + it] per-iteration flags: bit0 = improving, bit1 = cancel requested.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 4 : (NW <= 16 ? 2 : 1)))
+k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, int flag, float max_iter,
+        unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SweepSmem &S = *reinterpret_cast<SweepSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 625; k += NW * 32) S.tps[k] = (&st->tps[0][0])[k];
+    if (tid < 25) S.iomask[tid] = st->iomask[tid];
+    __syncthreads();
+
+    const int gx = (L.w + OPT_BW * 2 + SPACING - 1) / (OPT_BW * 2 + SPACING);
+    const int gy = (L.h + OPT_BH * 2 + SPACING - 1) / (OPT_BH * 2 + SPACING);
+    const int ntiles = gx * gy;
+    unsigned int epoch = 0;
+    int iter = 0;
+    bool go;
+    do {
+        if (tid == 0) S.cta_improving = 0;
+        __syncthreads();
+#pragma unroll 1
+        for (int step = 0; step < 4; step++) {
+            const int offx = (step & 1) ? OPT_BW * 2 : 0, offy = (step & 2) ? OPT_BH * 2 : 0;   // morph.cu:1382-1385
+            const bool empty = offx >= L.w || offy >= L.h;   // no pixel of any tile inside the image: empty launch
+            if (!empty) {
+                for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                    int by = t / gx, bx = t - by * gx;
+                    int ox = bx * (OPT_BW * 2 + SPACING) + offx - 2, oy = by * (OPT_BH * 2 + SPACING) + offy - 2;
+                    if (ox + 2 >= L.w || oy + 2 >= L.h) continue;
+                    tile_step<NW>(S, L, P, st, page, flag != 0, ox, oy);
+                }
+            }
+            if (step == 3 && tid == 0) {                      // publish this CTA's vote before the iteration's last barrier
+                unsigned f = S.cta_improving ? 1u : 0u;
+                if (blockIdx.x == 0 && run_flag && *run_flag == 0) f |= 2u;
+                if (f) atomicOr(&ctrl[8 + iter], f);
+            }
+            if (!empty || step == 3) grid_barrier(&ctrl[0], epoch, gridDim.x);
+        }
+        unsigned f = __ldcg(&ctrl[8 + iter]);
+        iter++;
+        if (blockIdx.x == 0 && tid == 0 && progress) *progress = (seq << 12) | iter;
+        go = ((float)iter < max_iter) && (f & 1u) && !(f & 2u);          // morph.cu:1390
+        if (!go && blockIdx.x == 0 && tid == 0) { ctrl[1] = (unsigned)iter; ctrl[2] = (f & 2u) ? 1u : 0u; }
+    } while (go);
+}
+
+// ------------------------------------------------------------------ host launcher
+static int g_sweep_max_blocks[4] = {0, 0, 0, 0};
+
+template <int NW>
+static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag,
+                                  float max_iter, unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq,
+                                  int ntiles, int sm_count, cudaStream_t stream, int slot) {
+    size_t smem = sizeof(SweepSmem);
+    auto kern = k_sweep<NW>;
+    if (!g_sweep_max_blocks[slot]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        g_sweep_max_blocks[slot] = per_sm * sm_count;
+    }
+    int grid = ntiles < g_sweep_max_blocks[slot] ? ntiles : g_sweep_max_blocks[slot];
+    LevelView Lc = L; KParams Pc = P;
+    void *args[] = {&Lc, &Pc, (void *)&st, &page, &flag, &max_iter, &ctrl, (void *)&run_flag, (void *)&progress, &seq};
+    count_launch();
+    return cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(NW * 32), args, smem, stream);
+}
+
+cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
+                         unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, cudaStream_t stream) {
+    const int gx = (L.w + OPT_BW * 2 + SPACING - 1) / (OPT_BW * 2 + SPACING);
+    const int gy = (L.h + OPT_BH * 2 + SPACING - 1) / (OPT_BH * 2 + SPACING);
+    const int ntiles = gx * gy;
+    // few tiles: latency-bound chain -> widest CTA (32 warps, one pixel per warp in flight);
+    // many tiles: 8-warp CTAs, 4 per SM.
+    if (ntiles <= sm_count) return launch_sweep_t<32>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 0);
+    if (ntiles <= 2 * sm_count) return launch_sweep_t<16>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 1);
+    return launch_sweep_t<8>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 2);
+}
+
+size_t sweep_ctrl_words(int max_iter_ceil) { return 8 + (size_t)max_iter_ceil + 8; }
+
+}  // namespace vm
