@@ -1,0 +1,77 @@
+"""Full-size checks at BASELINE.json sizes through size-independent properties (the oracle is too slow there):
+determinism, incremental == direct state, energy monotonicity across the run, recovery of the synthetic warp."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vm():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from videomorphing_b200 import build
+    build.build()
+    import videomorphing_b200 as vm
+    return vm
+
+
+def _levels_from_oracle(vm, oracle_lib, rgb0, rgb1):
+    o = oracle_lib.Oracle()
+    n = o.build(rgb0, rgb1)
+    d, h, w, _ = rgb0.shape
+    pyr = vm.Pyramid(0)
+    assert pyr.alloc(w, h, d) == n
+    for l in range(1, n - 1):
+        pyr.set(l, "img0", o.get(l, "img0")); pyr.set(l, "img1", o.get(l, "img1"))
+    return pyr, n
+
+
+def test_cfg2_properties(vm, oracle_lib):
+    # BASELINE.json configs[1]: 512x512 pair, 20 UI point constraints, full pyramid
+    from videomorphing_b200 import synth
+    w, h, d, s1, s2, amp = synth.CONFIGS["cfg2"]
+    rgb0, rgb1, field = synth.image_pair(w, h, s1, s2, amp)
+    cons = synth.point_pairs(20, w, h, 2003, field)
+    pyr, n = _levels_from_oracle(vm, oracle_lib, rgb0, rgb1)
+    runs = []
+    for _ in range(2):
+        m = vm.Morph(vm.Parameters(), pyr)
+        m.set_constraints(*cons)
+        m.run()
+        runs.append((m.get_vectors(), m.iters_log().copy(), m.energy(1)[0]))
+    np.testing.assert_array_equal(runs[0][0], runs[1][0])            # deterministic (no float atomics anywhere)
+    np.testing.assert_array_equal(runs[0][1], runs[1][1])
+    log = runs[0][1]
+    assert list(log[:, 0]) == list(range(n - 2, 0, -1))
+    max_it = 1000.0
+    for l, _, it in log:
+        assert 1 <= it <= int(np.ceil(max_it))
+        max_it /= 2
+    # incremental state == direct re-initialisation from the final v (SURVEY section 4 cross-check 3)
+    inc = {k: pyr.get(1, k) for k in ("mean", "var", "cross", "value", "tps_b")}
+    e_inc = m.energy(1)[0]
+    m.initialize_level(1)
+    for k, a in inc.items():
+        np.testing.assert_allclose(a, pyr.get(1, k), rtol=3e-4, atol=0.5 if k in ("var", "cross") else 5e-3, err_msg=k)
+    assert abs(m.energy(1)[0] - e_inc) <= 1e-3 * abs(e_inc)
+    # the optimizer recovers the synthetic warp: halfway vector ~ warp / 2
+    err = np.abs(runs[0][0][0] - field / 2)
+    assert err.mean() < 0.5 and np.median(err) < 0.25
+
+
+def test_optimisation_lowers_energy_at_every_level(vm, oracle_lib):
+    from videomorphing_b200 import synth
+    rgb0, rgb1, _ = synth.image_pair(320, 200, 81, 82, 8.0)
+    pyr, n = _levels_from_oracle(vm, oracle_lib, rgb0, rgb1)
+    m = vm.Morph(vm.Parameters(max_iter=200), pyr)
+    m.cpu_optimize_level()
+    mi = 200.0
+    for l in range(n - 2, 0, -1):
+        m.upsample(l); m.initialize_level(l)
+        e0 = m.energy(l)[0]
+        m.optimize_frame(l, 0, False, mi)
+        e1 = m.energy(l)[0]
+        assert e1 <= e0 * (1 + 1e-6), (l, e0, e1)
+        mi /= 2

@@ -1,0 +1,202 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+The arithmetic contract (-fmad=false, IEEE div/sqrt, fixed summation orders) makes the two paths agree bit for bit on
+the optimizer state, so the hard gates of BASELINE.md section 4 (vectors <= 0.05 px, energy <= 0.1 %) are asserted
+together with exact equality; integer items (iteration counts, improving masks, strides) must always be equal."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+STATE = ["mean", "var", "luma", "cross", "value", "counter", "tps_axy", "tps_b", "ui_axy", "ui_b", "impmask"]
+TOL_VEC_PX = 0.05      # north_star: halfway vectors within 0.05 px
+TOL_ENERGY = 1e-3      # final energy within 0.1 %
+
+
+@pytest.fixture(scope="module")
+def vm():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from videomorphing_b200 import build
+    build.build()
+    import videomorphing_b200 as vm
+    assert vm._lib.load().vm_device_count() >= 1
+    return vm
+
+
+def _setup(vm, po, rgb0, rgb1, params, flows=None, cons=None, voxel_cap=14000000):
+    o = po.Oracle(params)
+    n = o.build(rgb0, rgb1, flows=flows, voxel_cap=voxel_cap)
+    d, h, w, _ = rgb0.shape
+    pyr = vm.Pyramid(0)
+    assert pyr.alloc(w, h, d, int(params.get("start_res", 8)), voxel_cap) == n
+    for l in range(n):
+        a, b = pyr.info(l), o.info(l)
+        for k in ("w", "h", "d", "rowstride", "pagestride", "impmask_rowstride", "impmask_pagestride", "has_images"):
+            assert a[k] == b[k], (l, k)
+        assert a["factor_d"] == b["factor_d"] and a["inv_wh"] == b["inv_wh"]
+    for l in range(1, n - 1):
+        for f in ("img0", "img1") + (("f0", "f1", "b0", "b1") if flows is not None else ()):
+            pyr.set(l, f, o.get(l, f))
+    m = vm.Morph(vm.Parameters(**params), pyr)
+    if cons is not None:
+        o.set_constraints(*cons)
+        m.set_constraints(*cons)
+    return o, pyr, m, n
+
+
+def _assert_vec(a, b, what):
+    err = float(np.abs(a.astype(np.float64) - b).max())
+    assert err <= TOL_VEC_PX, f"{what}: max |dv| = {err} px"
+    assert np.array_equal(a, b), f"{what}: within tolerance ({err} px) but not bit-exact"
+
+
+def test_stagewise_state_parity(vm, oracle_lib):
+    from videomorphing_b200 import synth
+    rgb0, rgb1, field = synth.image_pair(96, 72, 21, 22, 4.0)
+    cons = synth.point_pairs(8, 96, 72, 23, field, margin=8)
+    o, pyr, m, n = _setup(vm, oracle_lib, rgb0, rgb1, dict(max_iter=40), cons=cons)
+    o.coarse_solve(); m.cpu_optimize_level()
+    _assert_vec(pyr.get(n - 1, "v"), o.get(n - 1, "v"), "coarse solve")
+    mi = 40.0
+    for l in range(n - 2, 0, -1):
+        o.upsample(l); m.upsample(l)
+        _assert_vec(pyr.get(l, "v"), o.get(l, "v"), f"upsample level {l}")
+        o.initialize_level(l); m.initialize_level(l)
+        for f in STATE:
+            np.testing.assert_array_equal(pyr.get(l, f), o.get(l, f), err_msg=f"init {f} level {l}")
+        it_o = o.optimize_frame(l, 0, False, mi)
+        it_g = m.optimize_frame(l, 0, False, mi)
+        assert it_o == it_g
+        _assert_vec(pyr.get(l, "v"), o.get(l, "v"), f"optimize level {l}")
+        for f in STATE:
+            np.testing.assert_array_equal(pyr.get(l, f), o.get(l, f), err_msg=f"opt {f} level {l}")
+        eo, _ = o.energy(l); eg, _ = m.energy(l)
+        assert abs(eo - eg) <= TOL_ENERGY * abs(eo)
+        mi /= 2
+
+
+@pytest.mark.parametrize("w,h,bcond,npts,max_iter", [(80, 56, 0, 0, 60), (150, 70, 2, 0, 30), (64, 48, 1, 5, 40), (33, 27, 0, 3, 50), (200, 40, 0, 0, 16)])
+def test_full_run_parity(vm, oracle_lib, w, h, bcond, npts, max_iter):
+    from videomorphing_b200 import synth
+    rgb0, rgb1, field = synth.image_pair(w, h, 100 + w, 200 + h, 3.0)
+    cons = synth.point_pairs(npts, w, h, 7, field, margin=6) if npts else None
+    o, pyr, m, n = _setup(vm, oracle_lib, rgb0, rgb1, dict(max_iter=max_iter, bcond=bcond), cons=cons)
+    o.run(); m.run()
+    np.testing.assert_array_equal(m.iters_log(), o.iters_log())
+    assert m.executed_pixel_iters == o.executed_pixel_iters
+    _assert_vec(m.get_vectors(), o.extract_vectors(), "final vectors")
+    eo, _ = o.energy(1); eg, _ = m.energy(1)
+    assert abs(eo - eg) <= TOL_ENERGY * abs(eo)
+
+
+def test_cfg1_default_parameters(vm, oracle_lib):
+    # BASELINE.json configs[0]: single 256x256 pair, default parameters, no UI constraints
+    from videomorphing_b200 import synth
+    w, h, d, s1, s2, amp = synth.CONFIGS["cfg1"]
+    rgb0, rgb1, field = synth.image_pair(w, h, s1, s2, amp)
+    o, pyr, m, n = _setup(vm, oracle_lib, rgb0, rgb1, {})
+    o.run(); m.run()
+    np.testing.assert_array_equal(m.iters_log(), o.iters_log())
+    vg, vo = m.get_vectors(), o.extract_vectors()
+    _assert_vec(vg, vo, "cfg1 vectors")
+    eo, _ = o.energy(1); eg, _ = m.energy(1)
+    assert abs(eo - eg) <= TOL_ENERGY * abs(eo)
+    # the optimizer recovers the synthetic warp (halfway vector = warp / 2)
+    assert np.abs(vg[0] - field / 2).mean() < 0.3
+
+
+def test_cluster_and_cta_width_do_not_change_results(vm, oracle_lib):
+    # the tile schedule is fixed by the reference; how many SMs cooperate on a tile must not matter
+    from videomorphing_b200 import synth
+    rgb0, rgb1, _ = synth.image_pair(140, 90, 5, 6, 3.0)
+    res = []
+    try:
+        for env in ({"VMORPH_CLUSTER": "1", "VMORPH_WARPS": "8"}, {"VMORPH_CLUSTER": "2", "VMORPH_WARPS": "16"},
+                    {"VMORPH_CLUSTER": "4", "VMORPH_WARPS": "32"}, {"VMORPH_CLUSTER": "8", "VMORPH_WARPS": "32"}, {}):
+            for k in ("VMORPH_CLUSTER", "VMORPH_WARPS"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            o, pyr, m, n = _setup(vm, oracle_lib, rgb0, rgb1, dict(max_iter=24))
+            m.run()
+            res.append((m.get_vectors(), m.iters_log()))
+    finally:
+        for k in ("VMORPH_CLUSTER", "VMORPH_WARPS"):
+            os.environ.pop(k, None)
+    for v, it in res[1:]:
+        np.testing.assert_array_equal(v, res[0][0])
+        np.testing.assert_array_equal(it, res[0][1])
+    o.run()
+    np.testing.assert_array_equal(res[0][0], o.extract_vectors())
+
+
+def test_video_temporal_path_parity(vm, oracle_lib):
+    # 9 frames: temporal pyramid levels, flow-guided in-fill on upsample, initialize_temp + temporal energy term
+    from videomorphing_b200 import synth
+    v0, v1, flows, _ = synth.video_pair(56, 40, 9, 41, 42, 3.0)
+    o, pyr, m, n = _setup(vm, oracle_lib, v0, v1, dict(max_iter=20, start_res=4), flows=flows)
+    assert len({pyr.info(l)["d"] for l in range(n)}) > 1          # the schedule really has temporal levels
+    o.run(); m.run()
+    np.testing.assert_array_equal(m.iters_log(), o.iters_log())
+    _assert_vec(m.get_vectors(), o.extract_vectors(), "video vectors")
+    for f in ("temp_ref", "temp_mask", "value"):
+        np.testing.assert_array_equal(pyr.get(1, f), o.get(1, f), err_msg=f)
+    mid = pyr.info(1)["d"] // 2
+    for fr, flag in ((mid, False), (0, True), (pyr.info(1)["d"] - 1, True)):
+        eo, _ = o.energy(1, fr, flag); eg, _ = m.energy(1, fr, flag)
+        assert abs(eo - eg) <= TOL_ENERGY * abs(eo)
+
+
+def test_render_parity(vm, oracle_lib):
+    from videomorphing_b200 import synth
+    w, h = 150, 90
+    rgb0, rgb1, field = synth.image_pair(w, h, 61, 62, 5.0)
+    ex = int(max(w, h) * 0.1)
+    e0, e1 = synth.extended_rgba(rgb0[0], ex), synth.extended_rgba(rgb1[0], ex)
+    vec = (field / 2).astype(np.float32)
+    rng = np.random.Generator(np.random.PCG64(9))
+    qp = (rng.standard_normal((h, w, 2)) * 0.3).astype(np.float32)
+    for color_from in (0, 1, 2):
+        for t in (0.0, 0.3, 1.0):
+            fa = float(synth.smoothstep(t))
+            for q in (None, qp):
+                got = vm.render_halfway_image(w, h, ex, fa, fa, color_from, e0, e1, vec, q)
+                ref = oracle_lib.render_halfway(w, h, ex, fa, fa, color_from, e0, e1, vec, q)[:, :w]
+                mse = float(((got.astype(np.float64) - ref) ** 2).mean())
+                psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+                assert psnr >= 45.0, (color_from, t, psnr)          # north_star: rendered frames >= 45 dB
+                np.testing.assert_array_equal(got, ref)
+
+
+def test_error_paths(vm):
+    pyr = vm.Pyramid(0)
+    with pytest.raises(vm._lib.VmError):
+        pyr.alloc(4, 4, 1)                     # too small for start_res 8
+    pyr.alloc(64, 48, 1)
+    m = vm.Morph(vm.Parameters(max_iter=4), pyr)
+    with pytest.raises(vm._lib.VmError):
+        m.optimize_frame(1, 0, False, 4)       # level not initialised
+    with pytest.raises(vm._lib.VmError):
+        m.upsample(1)                          # no coarser solution yet
+    with pytest.raises(vm._lib.VmError):
+        vm.Morph(vm.Parameters(max_iter=0), pyr)
+
+
+def test_cancellation_and_progress(vm, oracle_lib):
+    import ctypes as C
+    from videomorphing_b200 import synth
+    rgb0, rgb1, _ = synth.image_pair(96, 64, 71, 72, 3.0)
+    o, pyr, m0, n = _setup(vm, oracle_lib, rgb0, rgb1, dict(max_iter=30))
+    flag = C.c_int(0)                          # cleared before the run: morph.cu:156 skips every level
+    m = vm.Morph(vm.Parameters(max_iter=30), pyr, run_flag=flag)
+    m.run()
+    assert m.executed_pixel_iters == 0
+    flag.value = 1
+    m.run()
+    pr = m.progress()
+    assert pr["total_l"] == n - 1 and pr["current_iter"] > 0 and pr["total_iter"] > 0
+    o.run()
+    np.testing.assert_array_equal(m.get_vectors(), o.extract_vectors())

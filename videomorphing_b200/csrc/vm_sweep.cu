@@ -11,11 +11,17 @@
 //     so the ~21 energy evaluations of gradient + golden-section search touch no shared memory at all;
 //   * commits are deterministic gathers (fixed row-major contributor order) instead of float atomics
 //     (morph.cu:982-984,1013), so the result is reproducible and equals the CPU oracle op for op;
-//   * tiles whose improving-mask words are all clear are skipped without touching their state.
+//   * tiles whose improving-mask words are all clear are skipped without touching their state;
+//   * coarse levels have only 1..100 tiles: there a thread-block CLUSTER of R = 2/4/8 CTAs (one per SM) works on one
+//     tile.  Every CTA keeps a replica of the tile in its own shared memory, takes every R-th queued pixel, and
+//     broadcasts accepted moves (step, SSIM deltas) into all replicas through distributed shared memory; one
+//     hardware cluster barrier per colour sub-phase replaces what would otherwise be a single-SM serial chain.
 // The schedule -- tile origins bx*69+off-2, offsets (0,0),(64,0),(0,16),(64,16), sub-phase order i outer / j inner,
 // stride-2 pixel lattice, improving-mask cell layout -- is the reference's, bit for bit.
 #include "vm_device.cuh"
 #include "vm_host.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace vm {
 
@@ -24,19 +30,23 @@ constexpr int TW = OPT_BW * 2 + 4, TH = OPT_BH * 2 + 4;    // 68 x 20 tile (morp
 constexpr int TCELLS = TW * TH;
 constexpr int NPIX = OPT_BW * OPT_BH;                      // pixels per colour sub-phase
 
+// accepted moves of one colour sub-phase; written by the owning warp into EVERY CTA of the cluster (DSMEM)
+struct SlotBuf {
+    float2 d[NPIX], dm[NPIX], dv[NPIX];
+    float dc[NPIX];
+    unsigned char acc[NPIX];
+};
+
 struct SweepSmem {
-    float2 mean[TCELLS], var[TCELLS], tpsb[TCELLS];
+    float2 mean[TCELLS], var[TCELLS], tpsb[TCELLS];     // this CTA's replica of the tile state
     float cross[TCELLS], value[TCELLS], cnt[TCELLS];
-    float2 s_d[NPIX], s_dm[NPIX], s_dv[NPIX];
-    float s_dc[NPIX];
-    unsigned char status[NPIX];      // 0 = no mask index, 1 = has index / not accepted, 2 = accepted
+    SlotBuf slot[2];                                     // double-buffered by sub-phase parity
+    unsigned char status[NPIX];      // 0 = no mask index, 1 = has a mask index
     unsigned char bcls[NPIX];        // By*5+Bx of the pixel
     unsigned short queue[NPIX];
+    int warp_cnt[NPIX / 32];
     float tps[25 * 25];
     unsigned int iomask[25];
-    int qcount;
-    int tile_flag;
-    int sub_flag;
     int cta_improving;
 };
 
@@ -198,28 +208,38 @@ __device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float ep
     return false;
 }
 
-// One tile of one offset step (one block of one launch of the reference, morph.cu:1281-1345).
+// One tile of one offset step (one block of one launch of the reference, morph.cu:1281-1345), executed by a
+// cluster of R CTAs (R == 1: a single CTA).  Everything that decides control flow is computed redundantly and
+// deterministically by every CTA of the cluster, so the cluster barriers are always reached by all of them.
 template <int NW>
 __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, const StencilTables *__restrict__ st,
-                          int page, bool flag, int ox, int oy) {
+                          int page, bool flag, int ox, int oy, int R, int rank, unsigned int &phase) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NT = NW * 32;
     const size_t poff = (size_t)page * L.ps;
     const float *I0 = L.img0 + (size_t)page * L.w * L.h, *I1 = L.img1 + (size_t)page * L.w * L.h;
+    cg::cluster_group cluster = cg::this_cluster();
 
-    // --- tile skip: no improving bit anywhere near the processed region => no pixel can be active (exact)
+    // --- tile skip: no improving bit of any pixel inside the tile extent => no pixel can be active (exact).
+    // Only bits of pixels inside this tile's extent are tested: those are never modified by another cluster during
+    // this step, so all CTAs of the cluster take the same decision.
     {
-        int cx0 = max(ox, 0) / 5, cx1 = min(ox + TW - 1, L.w - 1) / 5;
-        int cy0 = max(oy, 0) / 5, cy1 = min(oy + TH - 1, L.h - 1) / 5;
+        // (the extent is clipped to the mask's interior cells, NOT to the image: bits of the never-existing pixels in
+        //  partial right/bottom cells stay set forever and keep their neighbours active in the reference)
+        int ex0 = max(ox, 0), ex1 = min(ox + TW - 1, ((L.w + 4) / 5) * 5 - 1), ey0 = max(oy, 0), ey1 = min(oy + TH - 1, ((L.h + 4) / 5) * 5 - 1);
+        int cx0 = ex0 / 5, cx1 = ex1 / 5, cy0 = ey0 / 5, cy1 = ey1 / 5;
         int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1;
         int any = 0;
         for (int k = tid; k < ncx * ncy; k += NT) {
             int cy = cy0 + k / ncx, cx = cx0 + k % ncx;
-            any |= __ldcg(L.impmask + page * L.ips + (cy + 1) * L.irs + (cx + 1)) != 0u;
+            unsigned xm = 0, m = 0;
+            for (int r = 0; r < 5; r++) if (cx * 5 + r >= ex0 && cx * 5 + r <= ex1) xm |= 1u << r;
+            for (int r = 0; r < 5; r++) if (cy * 5 + r >= ey0 && cy * 5 + r <= ey1) m |= xm << (5 * r);
+            any |= (__ldcg(L.impmask + page * L.ips + (cy + 1) * L.irs + (cx + 1)) & m) != 0u;
         }
         if (!__syncthreads_or(any)) return;
     }
-    // --- LoadSSIM (morph.cu:1214-1234) + counter + tps.b
+    // --- LoadSSIM (morph.cu:1214-1234) + counter + tps.b into this CTA's replica
     for (int c = tid; c < TCELLS; c += NT) {
         int sy = c / TW, sx = c - sy * TW;
         int x = ox + sx, y = oy + sy;
@@ -232,35 +252,47 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             S.cross[c] = S.value[c] = S.cnt[c] = 0.f;
         }
     }
-    if (tid == 0) S.tile_flag = 0;
+    bool dirty = false;
     __syncthreads();
 
     for (int si = 0; si < 2; ++si)
         for (int sj = 0; sj < 2; ++sj) {
-            // ---- filter: which pixels of this colour have an improving neighbourhood (morph.cu:1041-1054)
-            if (tid == 0) { S.qcount = 0; S.sub_flag = 0; }
-            __syncthreads();
+            SlotBuf &SB = S.slot[phase & 1u];
+            // ---- filter: which pixels of this colour have an improving neighbourhood (morph.cu:1041-1054);
+            //      deterministic compaction (slot order) so every CTA of the cluster builds the same queue
+            bool act = false; unsigned bal = 0;
             if (tid < NPIX) {
                 int tx = tid & 31, ty = tid >> 5;
                 int px = ox + tx * 2 + sj + 2, py = oy + ty * 2 + si + 2;
                 unsigned char stt = 0;
-                bool act = false;
                 if (px >= 0 && px < L.w && py >= 0 && py < L.h) {
                     int idx = get_improve_mask_idx(L, st, page, px, py);
-                    if (idx >= 0) { stt = 1; act = !pixel_on_border(L, P.bcond, px, py); }
+                    if (idx >= 0) {
+                        stt = 1; act = !pixel_on_border(L, P.bcond, px, py);
+                        if (!act && (tid % R) == rank) {          // locked border pixel: ok == false (morph.cu:1328-1332)
+                            int bx = px / 5, by = py / 5;
+                            atomicAnd(L.impmask + page * L.ips + (by + 1) * L.irs + (bx + 1), ~(1u << ((px - bx * 5) + (py - by * 5) * 5)));
+                        }
+                    }
                     S.bcls[tid] = (unsigned char)(border_class(py, L.h) * 5 + border_class(px, L.w));
                 }
                 S.status[tid] = stt;
-                unsigned bal = __ballot_sync(0xffffffffu, act);
-                int base = 0;
-                if (lane == 0 && bal) base = atomicAdd(&S.qcount, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (act) S.queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)tid;
+                bal = __ballot_sync(0xffffffffu, act);
+                if (lane == 0) S.warp_cnt[warp] = __popc(bal);
             }
             __syncthreads();
-            // ---- compute: one warp per active pixel, all from the pre-sub-phase state
-            const int qn = S.qcount;
-            for (int q = warp; q < qn; q += NW) {
+            int qn = 0;
+#pragma unroll
+            for (int k = 0; k < NPIX / 32; k++) qn += S.warp_cnt[k];
+            if (tid < NPIX && act) {
+                int base = 0;
+                for (int k = 0; k < warp; k++) base += S.warp_cnt[k];
+                S.queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)tid;
+            }
+            __syncthreads();
+            // ---- compute: one warp per active pixel, all from the pre-sub-phase state; the owning warp commits the
+            //      pixel's own cells at once (nobody else reads them in this sub-phase) and broadcasts the deltas
+            for (int q = rank * NW + warp; q < qn; q += R * NW) {
                 int slot = S.queue[q];
                 int tx = slot & 31, ty = slot >> 5;
                 int lx = tx * 2 + sj + 2, ly = ty * 2 + si + 2;
@@ -300,46 +332,41 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                 }
                 float2 d;
                 bool ok = optimize_pixel_warp(E, P.eps, nb, inb, d);
-                if (ok && lane == 0) { S.status[slot] = 2; S.s_d[slot] = d; }
-            }
-            __syncthreads();
-            // ---- commit A: per accepted pixel own-cell updates (morph.cu:951-971,1017-1025,1320-1332)
-            if (tid < NPIX) {
-                int stt = S.status[tid];
-                if (stt) {
-                    int tx = tid & 31, ty = tid >> 5;
-                    int px = ox + tx * 2 + sj + 2, py = oy + ty * 2 + si + 2;
-                    int bx = px / 5, by = py / 5;
-                    unsigned bit = 1u << ((px - bx * 5) + (py - by * 5) * 5);
-                    unsigned *mw = L.impmask + page * L.ips + (by + 1) * L.irs + (bx + 1);
-                    if (stt == 2) {
-                        size_t idx = (size_t)py * L.rs + px + poff;
-                        float2 d = S.s_d[tid];
-                        float2 v = __ldcg(L.v + idx), old_luma = __ldcg(L.luma + idx);
-                        float2 newv = make_float2(v.x + d.x, v.y + d.y);
-                        float2 luma;
-                        luma.x = tex2d<true>(I0, L.w, L.h, (float)px - newv.x + 0.5f, (float)py - newv.y + 0.5f);
-                        luma.y = tex2d<true>(I1, L.w, L.h, (float)px + newv.x + 0.5f, (float)py + newv.y + 0.5f);
+                int bx = px / 5, by = py / 5;
+                unsigned bit = 1u << ((px - bx * 5) + (py - by * 5) * 5);
+                unsigned *mw = L.impmask + page * L.ips + (by + 1) * L.irs + (bx + 1);
+                if (ok) {
+                    // commit of the pixel's own cells (morph.cu:951-971,1017-1025,1320-1327)
+                    float2 newv = make_float2(E.v.x + d.x, E.v.y + d.y);
+                    float2 luma;
+                    luma.x = tex2d<true>(I0, L.w, L.h, (float)px - newv.x + 0.5f, (float)py - newv.y + 0.5f);
+                    luma.y = tex2d<true>(I1, L.w, L.h, (float)px + newv.x + 0.5f, (float)py + newv.y + 0.5f);
+                    float2 dm = make_float2(luma.x - E.old_luma.x, luma.y - E.old_luma.y);
+                    float2 dv = make_float2(luma.x * luma.x - E.old_luma.x * E.old_luma.x, luma.y * luma.y - E.old_luma.y * E.old_luma.y);
+                    float dc = luma.x * luma.y - E.old_luma.x * E.old_luma.y;
+                    if (lane == 0) {
                         L.luma[idx] = luma;
-                        S.s_dm[tid] = make_float2(luma.x - old_luma.x, luma.y - old_luma.y);
-                        S.s_dv[tid] = make_float2(luma.x * luma.x - old_luma.x * old_luma.x, luma.y * luma.y - old_luma.y * old_luma.y);
-                        S.s_dc[tid] = luma.x * luma.y - old_luma.x * old_luma.y;
-                        float axy = __ldcg(L.ui_axy + idx);
-                        float2 ub = __ldcg(L.ui_b + idx);
-                        ub.x += 2 * d.x * axy; ub.y += 2 * d.y * axy;
+                        float2 ub = E.ui_b;
+                        ub.x += 2 * d.x * E.ui_axy; ub.y += 2 * d.y * E.ui_axy;
                         L.ui_b[idx] = ub;
                         L.v[idx] = newv;
                         atomicOr(mw, bit);
-                        S.tile_flag = 1; S.sub_flag = 1;
-                    } else {
-                        atomicAnd(mw, ~bit);
                     }
+                    if (lane < R) {                                // broadcast into every replica's slot buffer
+                        SlotBuf *dst = (R > 1) ? cluster.map_shared_rank(&SB, lane) : &SB;
+                        dst->d[slot] = d; dst->dm[slot] = dm; dst->dv[slot] = dv; dst->dc[slot] = dc; dst->acc[slot] = 1;
+                    }
+                } else if (lane == 0) {
+                    atomicAnd(mw, ~bit);                            // morph.cu:1328-1332
                 }
             }
-            __syncthreads();
-            // ---- commit B: deterministic gather of the SSIM-sum and TPS deltas into the tile, then UpdateSSIM
+            // every mask / v / luma update of this sub-phase is ordered before the next filter by this barrier
+            if (R > 1) cluster.sync(); else __syncthreads();
+            // ---- commit B: deterministic gather of the SSIM-sum and TPS deltas into the replica, then UpdateSSIM
             //      (morph.cu:973-987,1006-1015,1258-1279).  Contributors in row-major order of the source pixel.
-            if (S.sub_flag) {
+            int any = (tid < NPIX) ? (int)SB.acc[tid] : 0;
+            if (__syncthreads_or(any)) {
+                dirty = true;
                 for (int c = tid; c < TCELLS; c += NT) {
                     int sy = c / TW, sx = c - sy * TW;
                     float2 m = S.mean[c], vr = S.var[c], tb = S.tpsb[c];
@@ -351,19 +378,19 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                         if (t < 0 || (t & 1) || (t >> 1) >= OPT_BH) continue;
 #pragma unroll
                         for (int dx = -2; dx <= 2; dx++) {
-                            int s = sx + dx - sj - 2;
-                            if (s < 0 || (s & 1) || (s >> 1) >= OPT_BW) continue;
-                            int slot = (t >> 1) * OPT_BW + (s >> 1);
-                            if (S.status[slot] != 2) continue;
+                            int s2 = sx + dx - sj - 2;
+                            if (s2 < 0 || (s2 & 1) || (s2 >> 1) >= OPT_BW) continue;
+                            int slot = (t >> 1) * OPT_BW + (s2 >> 1);
+                            if (!SB.acc[slot]) continue;
                             int B = S.bcls[slot];
                             int k = (2 - dy) * 5 + (2 - dx);
                             if ((S.iomask[B] >> k) & 1u) {
-                                float2 dm = S.s_dm[slot], dv = S.s_dv[slot];
-                                m.x += dm.x; m.y += dm.y; vr.x += dv.x; vr.y += dv.y; cr += S.s_dc[slot];
+                                float2 dm = SB.dm[slot], dv = SB.dv[slot];
+                                m.x += dm.x; m.y += dm.y; vr.x += dv.x; vr.y += dv.y; cr += SB.dc[slot];
                                 ch_s = true;
                             }
                             float T = S.tps[B * 25 + k];
-                            if (T != 0.0f) { float2 d = S.s_d[slot]; tb.x += d.x * T; tb.y += d.y * T; ch_t = true; }
+                            if (T != 0.0f) { float2 d = SB.d[slot]; tb.x += d.x * T; tb.y += d.y * T; ch_t = true; }
                         }
                     }
                     if (ch_s) {
@@ -372,19 +399,23 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                     }
                     if (ch_t) S.tpsb[c] = tb;
                 }
+                __syncthreads();
+                if (tid < NPIX) SB.acc[tid] = 0;       // next written two sub-phases from now, after the next barrier
             }
+            phase++;
             __syncthreads();
         }
-    // --- SaveSSIM (morph.cu:1236-1256) + tps.b, only when something was committed
-    if (S.tile_flag) {
-        for (int c = tid; c < TCELLS; c += NT) {
-            int sy = c / TW, sx = c - sy * TW;
-            int x = ox + sx, y = oy + sy;
-            if (x >= 0 && x < L.w && y >= 0 && y < L.h) {
-                size_t i = (size_t)y * L.rs + x + poff;
-                L.mean[i] = S.mean[c]; L.var[i] = S.var[c]; L.cross[i] = S.cross[c]; L.value[i] = S.value[c]; L.tps_b[i] = S.tpsb[c];
+    // --- SaveSSIM (morph.cu:1236-1256) + tps.b, only when something was committed; replicas are identical, rank 0 stores
+    if (dirty) {
+        if (rank == 0)
+            for (int c = tid; c < TCELLS; c += NT) {
+                int sy = c / TW, sx = c - sy * TW;
+                int x = ox + sx, y = oy + sy;
+                if (x >= 0 && x < L.w && y >= 0 && y < L.h) {
+                    size_t i = (size_t)y * L.rs + x + poff;
+                    L.mean[i] = S.mean[c]; L.var[i] = S.var[c]; L.cross[i] = S.cross[c]; L.value[i] = S.value[c]; L.tps_b[i] = S.tpsb[c];
+                }
             }
-        }
         if (tid == 0) S.cta_improving = 1;
     }
     __syncthreads();
@@ -399,14 +430,19 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SweepSmem &S = *reinterpret_cast<SweepSmem *>(smem_raw);
     const int tid = threadIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int R = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     for (int k = tid; k < 625; k += NW * 32) S.tps[k] = (&st->tps[0][0])[k];
     if (tid < 25) S.iomask[tid] = st->iomask[tid];
+    if (tid < NPIX) { S.slot[0].acc[tid] = 0; S.slot[1].acc[tid] = 0; }
     __syncthreads();
+    if (R > 1) cluster.sync();          // slot buffers of every CTA are initialised before any remote write
 
     const int gx = (L.w + OPT_BW * 2 + SPACING - 1) / (OPT_BW * 2 + SPACING);
     const int gy = (L.h + OPT_BH * 2 + SPACING - 1) / (OPT_BH * 2 + SPACING);
     const int ntiles = gx * gy;
-    unsigned int epoch = 0;
+    const int nclusters = gridDim.x / R, cid = blockIdx.x / R;
+    unsigned int epoch = 0, phase = 0;
     int iter = 0;
     bool go;
     do {
@@ -417,11 +453,11 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
             const int offx = (step & 1) ? OPT_BW * 2 : 0, offy = (step & 2) ? OPT_BH * 2 : 0;   // morph.cu:1382-1385
             const bool empty = offx >= L.w || offy >= L.h;   // no pixel of any tile inside the image: empty launch
             if (!empty) {
-                for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                for (int t = cid; t < ntiles; t += nclusters) {
                     int by = t / gx, bx = t - by * gx;
                     int ox = bx * (OPT_BW * 2 + SPACING) + offx - 2, oy = by * (OPT_BH * 2 + SPACING) + offy - 2;
                     if (ox + 2 >= L.w || oy + 2 >= L.h) continue;
-                    tile_step<NW>(S, L, P, st, page, flag != 0, ox, oy);
+                    tile_step<NW>(S, L, P, st, page, flag != 0, ox, oy, R, rank, phase);
                 }
             }
             if (step == 3 && tid == 0) {                      // publish this CTA's vote before the iteration's last barrier
@@ -437,43 +473,80 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
         go = ((float)iter < max_iter) && (f & 1u) && !(f & 2u);          // morph.cu:1390
         if (!go && blockIdx.x == 0 && tid == 0) { ctrl[1] = (unsigned)iter; ctrl[2] = (f & 2u) ? 1u : 0u; }
     } while (go);
+    if (R > 1) cluster.sync();          // no CTA exits while a peer may still address its shared memory
 }
 
 // ------------------------------------------------------------------ host launcher
-static int g_sweep_max_blocks[4] = {0, 0, 0, 0};
+struct SweepCfg { bool init = false; int max_clusters[4] = {0, 0, 0, 0}; };   // index = log2(R)
+static SweepCfg g_cfg[3];
 
 template <int NW>
 static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag,
                                   float max_iter, unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq,
-                                  int ntiles, int sm_count, cudaStream_t stream, int slot) {
+                                  int ntiles, int sm_count, cudaStream_t stream, int slot, int want_r) {
     size_t smem = sizeof(SweepSmem);
     auto kern = k_sweep<NW>;
-    if (!g_sweep_max_blocks[slot]) {
+    SweepCfg &cfg = g_cfg[slot];
+    if (!cfg.init) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        g_sweep_max_blocks[slot] = per_sm * sm_count;
+        cfg.max_clusters[0] = per_sm * sm_count;
+        for (int lg = 1; lg <= 3; lg++) {
+            cudaLaunchConfig_t qc = {};
+            qc.gridDim = dim3(1 << lg); qc.blockDim = dim3(NW * 32); qc.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1 << lg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            qc.attrs = at; qc.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, kern, &qc) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+            cfg.max_clusters[lg] = nc;
+        }
+        cfg.init = true;
     }
-    int grid = ntiles < g_sweep_max_blocks[slot] ? ntiles : g_sweep_max_blocks[slot];
+    // cluster size: the largest power of two <= want_r for which one cluster per tile is co-resident
+    int lg = 0;
+    for (int c = 3; c >= 1; c--) if ((1 << c) <= want_r && cfg.max_clusters[c] >= ntiles) { lg = c; break; }
+    int R = 1 << lg;
+    int nclusters = ntiles < cfg.max_clusters[lg] ? ntiles : cfg.max_clusters[lg];
     LevelView Lc = L; KParams Pc = P;
-    void *args[] = {&Lc, &Pc, (void *)&st, &page, &flag, &max_iter, &ctrl, (void *)&run_flag, (void *)&progress, &seq};
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(nclusters * R); lc.blockDim = dim3(NW * 32); lc.dynamicSmemBytes = smem; lc.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension; at[1].val.clusterDim.x = R; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = (R > 1) ? 2 : 1;
     count_launch();
-    return cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(NW * 32), args, smem, stream);
+    cudaError_t e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq);
+    if (e != cudaSuccess && R > 1) {
+        // cooperative + cluster attribute combination rejected: the grid is sized to be co-resident
+        // (<= cudaOccupancyMaxActiveClusters), launch it as a plain cluster grid.
+        cudaGetLastError();
+        lc.attrs = at + 1; lc.numAttrs = 1;
+        e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq);
+    }
+    return e;
 }
+
+// test hooks (read on every launch): VMORPH_CLUSTER=1/2/4/8 caps the cluster size, VMORPH_WARPS=8/16/32 pins the CTA width
 
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
                          unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, cudaStream_t stream) {
     const int gx = (L.w + OPT_BW * 2 + SPACING - 1) / (OPT_BW * 2 + SPACING);
     const int gy = (L.h + OPT_BH * 2 + SPACING - 1) / (OPT_BH * 2 + SPACING);
     const int ntiles = gx * gy;
-    // few tiles: latency-bound chain -> widest CTA (32 warps, one pixel per warp in flight);
-    // many tiles: 8-warp CTAs, 4 per SM.
-    if (ntiles <= sm_count) return launch_sweep_t<32>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 0);
-    if (ntiles <= 2 * sm_count) return launch_sweep_t<16>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 1);
-    return launch_sweep_t<8>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 2);
+    const char *ec = getenv("VMORPH_CLUSTER"), *ew = getenv("VMORPH_WARPS");
+    const int g_force_cluster = ec ? atoi(ec) : 0, g_force_warps = ew ? atoi(ew) : 0;
+    int want_r = g_force_cluster > 0 ? g_force_cluster : 8;
+    int nw = g_force_warps;
+    // few tiles: latency-bound chain -> widest CTA (32 warps) and a cluster per tile; many tiles: 8-warp CTAs, 4 per SM.
+    if (!nw) nw = (ntiles <= sm_count) ? 32 : (ntiles <= 2 * sm_count ? 16 : 8);
+    if (nw >= 32) return launch_sweep_t<32>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 0, want_r);
+    if (nw >= 16) return launch_sweep_t<16>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 1, want_r);
+    return launch_sweep_t<8>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 2, want_r);
 }
 
 size_t sweep_ctrl_words(int max_iter_ceil) { return 8 + (size_t)max_iter_ceil + 8; }
