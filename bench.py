@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one synthetic workload: Morph::calculate_halfway_parametrization
+(coarse solve + upsample / initialise / optimise every level) for the 512x512 image pair with 20 UI point constraints
+(BASELINE.json configs[1], the configuration the metric is quoted on that fits one GPU).
+
+  value      halfway-opt Mpixel-iters/s with the pyramid already resident in HBM (CUDA events on the launching stream)
+  e2e        the same metric through the reference-facing calls with HOST buffers: Pyramid::build (H2D of the RGB
+             frames from pinned memory + GPU resampling) -> Morph run -> update_result (D2H of the vector field)
+  roofline   dominant kernel (the optimizer sweep): 144 algorithmic B per pixel-iteration / live CUDA-event duration
+  cpu_baseline  the CPU restatement of the reference algorithm (oracle/, "port") on the box's host cores, N=1 rank 0 only
+  render     secondary figure of the metric: morphed 720p frames/s (device-resident and host-buffer variants)
+
+Image-pair configs do not shard ("replicas only"): with --gpus N every rank runs an independent replica
+(seeded by rank), no data-path collective, scaling "weak".  --impl reference times the oracle (the reference ships no
+CPU optimizer and its CUDA cannot be built with CUDA 12) on all host threads.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "halfway-opt Mpixel-iters/s"
+BYTES_PER_PIXEL_ITER = 144.0          # algorithmic bytes of one optimizer pixel-iteration
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_inputs(name, rank):
+    """Seeded synthetic inputs of SURVEY.md 8(d) (rank > 0: an independent replica with shifted seeds)."""
+    from videomorphing_b200 import synth
+    w, h, d, s1, s2, amp = synth.CONFIGS[name]
+    if d != 1:
+        raise SystemExit("bench.py times the image-pair workloads (cfg1/cfg2/cfg3); video configs: tools/video_bench.py")
+    rgb0, rgb1, field = synth.image_pair(w, h, s1 + 100 * rank, s2 + 100 * rank, amp)
+    cons = synth.point_pairs(20, w, h, 2003 + rank, field) if name == "cfg2" else None
+    return w, h, rgb0, rgb1, cons
+
+
+def describe(name):
+    return {"cfg1": "cfg1: 256x256 image pair, default parameters, no UI constraints",
+            "cfg2": "cfg2: 512x512 image pair, 20 UI point constraints, full pyramid (BASELINE.json configs[1])",
+            "cfg3": "cfg3: 1920x1080 image pair, full pyramid"}[name]
+
+
+# ------------------------------------------------------------------------------------------------ CPU (oracle) legs
+def oracle_run(name, rank, threads=None):
+    """One full coarse-to-fine run of the CPU oracle on the workload; returns (pixel_iters, seconds, threads)."""
+    from oracle import pyoracle as po
+    # -march=native: always rebuilt on the machine that runs it (a stale .so from another CPU must not be reused)
+    subprocess.run(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), "liboracle_native.so"], check=True, stdout=subprocess.DEVNULL)
+    L = po.lib(native=True)
+    L.vo_num_threads.restype = C.c_int
+    if threads:
+        L.vo_set_num_threads(int(threads))
+    nthreads = L.vo_num_threads()
+    w, h, rgb0, rgb1, cons = workload_inputs(name, rank)
+    o = po.Oracle(native=True)
+    o.build(rgb0, rgb1)                      # pyramid build is outside the metric
+    if cons is not None:
+        o.set_constraints(*cons)
+    return o, nthreads
+
+
+def cpu_sample(o, max_seconds):
+    """Runs Morph::calculate_halfway_parametrization on the oracle level by level (coarse to fine, full iteration
+    budget) and stops after the first level that ends past max_seconds.  Returns pixel-iters, seconds, description."""
+    n = o.num_levels
+    t0 = time.perf_counter()
+    o.coarse_solve()
+    mi = float(o.params["max_iter"])
+    px = 0.0
+    done = []
+    for l in range(n - 2, 0, -1):
+        o.upsample(l)
+        o.initialize_level(l)
+        it = o.optimize_frame(l, 0, False, mi)
+        i = o.info(l)
+        px += float(i["w"]) * i["h"] * it
+        done.append(l)
+        mi /= float(o.params["max_iter_drop_factor"])
+        if time.perf_counter() - t0 > max_seconds and l > 1:
+            break
+    dt = time.perf_counter() - t0
+    full = done[-1] == 1
+    desc = ("full coarse-to-fine run, all levels" if full else
+            f"levels {done[0]}..{done[-1]} of {n - 2}..1 (coarse to fine, full iteration budget; stopped after {max_seconds:.0f} s)")
+    return px, dt, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    o, nthreads = oracle_run(args.workload, 0)
+    total = args.steps + args.warmup
+    budget = max(4.0, 150.0 / max(1, total))          # whole run within a few minutes
+    times, pix, desc = [], [], ""
+    for s in range(total):
+        px, dt, desc = cpu_sample(o, budget)
+        if s >= args.warmup:
+            times.append(dt); pix.append(px)
+    T = sum(times)
+    val = sum(pix) / T / 1e6
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpixel-iters/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * T / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": describe(args.workload), "note": "CPU restatement of the reference algorithm (oracle/); the reference "
+                      "ships no CPU optimizer and its CUDA (texture references) cannot be built with CUDA 12"},
+           "cpu_baseline": {"value": val, "unit": "Mpixel-iters/s", "cores": nthreads, "kind": "port", "sample": desc},
+           "e2e": {"value": val, "unit": "Mpixel-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import videomorphing_b200 as vm
+    from videomorphing_b200 import _lib, synth
+    L = _lib.load()
+    w, h, rgb0, rgb1, cons = workload_inputs(args.workload, rank)
+    # pinned host buffers: inputs (RGB8 frames) and the result (level-0 vector field)
+    pin0 = torch.from_numpy(rgb0.copy()).pin_memory()
+    pin1 = torch.from_numpy(rgb1.copy()).pin_memory()
+    out_pin = torch.empty((1, h, w, 2), dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream()
+    sh = C.c_void_p(stream.cuda_stream)
+
+    pyr = vm.Pyramid(local)
+
+    def build():
+        _lib.check(L.vm_pyramid_build(pyr.h, C.c_void_p(pin0.data_ptr()), C.c_void_p(pin1.data_ptr()), None, None, None, None,
+                                      w, h, 1, 8, vm.REFERENCE_VOXEL_CAP, sh))
+    build()
+    m = vm.Morph(vm.Parameters(), pyr)
+    if cons is not None:
+        m.set_constraints(*cons)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident steps: value
+    def step():
+        _lib.check(L.vm_morph_run(m.h, sh))
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = L.vm_kernel_launch_count()
+    px0 = m.executed_pixel_iters
+    sw0, nl0 = m.sweep_time_ms()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                                                           # L2 flush between timed iterations
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = L.vm_kernel_launch_count() - launches0
+    px = m.executed_pixel_iters - px0
+    sw1, nl1 = m.sweep_time_ms()
+    sweep_ms, sweep_n = sw1 - sw0, nl1 - nl0
+
+    # ---------------- end-to-end steps through the host-buffer API: e2e
+    def e2e_step():
+        build()                                                                 # H2D of the RGB frames + GPU pyramid
+        _lib.check(L.vm_morph_run(m.h, sh))
+        _lib.check(L.vm_morph_get_vectors(m.h, C.c_void_p(out_pin.data_ptr()), sh))   # D2H of the result
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    px_e0 = m.executed_pixel_iters
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    px_e = m.executed_pixel_iters - px_e0
+    h2d = int(pin0.numel() + pin1.numel())
+    d2h = int(out_pin.numel() * 4)
+
+    # ---------------- secondary figure: morphed 720p frames/s (render.cu path)
+    render = render_bench(vm, L, local, sh, stream, barrier) if rank == 0 and not args.no_render else None
+
+    # ---------------- reduce over ranks (device time: max; work: sum)
+    t = torch.tensor([dev_ms, e2e_s, sweep_ms], dtype=torch.float64, device="cuda")
+    s = torch.tensor([px, px_e, float(launches), float(sweep_n)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_max, sweep_ms_max = [float(x) for x in t.tolist()]
+    px_all, px_e_all, launches_all, sweep_n_all = [float(x) for x in s.tolist()]
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        value = px_all / (dev_ms_max * 1e-3) / 1e6
+        # roofline of the dominant kernel, per launch on one GPU (this rank's launches)
+        a_bytes = BYTES_PER_PIXEL_ITER * px / max(1, sweep_n)
+        a_ms = sweep_ms / max(1, sweep_n)
+        achieved = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(args.workload)
+        out = {"metric": METRIC, "value": value, "unit": "Mpixel-iters/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": describe(args.workload), "parallelism": f"replicas x{world} (image pairs do not shard; no collective)",
+                          "l2": "256 MiB buffer written between timed steps", "pixel_iters_per_step": px / args.steps,
+                          "timing": "CUDA events on the launching stream, one pair per step, summed; max over ranks"},
+               "e2e": {"value": px_e_all / e2e_max / 1e6, "unit": "Mpixel-iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": 1e3 * e2e_max / args.steps,
+                       "path": "vm_pyramid_build(host RGB8, pinned) -> vm_morph_run -> vm_morph_get_vectors(host), wall clock"},
+               "gpu_launches": int(launches_all),
+               "clocks": clocks,
+               "roofline": {"bound": "hbm", "kernel": "k_sweep (optimizer sweep, one persistent launch per level x frame)",
+                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                            "peak_source": peak_src, "algorithmic_bytes_per_launch": a_bytes, "avg_launch_ms": a_ms,
+                            "launches_timed": int(sweep_n), "share_of_step": sweep_ms / dev_ms if dev_ms > 0 else None,
+                            "note": "the sweep is FP32-issue / dependent-latency bound while pixels are active (SURVEY.md R10), "
+                                    "not HBM bound; the HBM fraction is reported because north_star asks for it"},
+               "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps}
+        if render is not None:
+            out["render"] = render
+        if world == 1 and not args.no_cpu:
+            o, nthreads = oracle_run(args.workload, 0)
+            cpx, cdt, desc = cpu_sample(o, args.cpu_seconds)
+            out["cpu_baseline"] = {"value": cpx / cdt / 1e6, "unit": "Mpixel-iters/s", "cores": nthreads, "kind": "port",
+                                   "sample": desc, "seconds": cdt}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def render_bench(vm, L, device, sh, stream, barrier, nframes=60):
+    """render_halfway_image on a 1280x720 pair: frames/s with device-resident inputs and through host buffers."""
+    import torch
+    from videomorphing_b200 import _lib, synth
+    w, h = 1280, 720
+    ex = int(max(w, h) * 0.1)
+    rgb0, rgb1, field = synth.image_pair(w, h, 4001, 4002, 8.0)
+    e0 = torch.from_numpy(synth.extended_rgba(rgb0[0], ex)).pin_memory()
+    e1 = torch.from_numpy(synth.extended_rgba(rgb1[0], ex)).pin_memory()
+    vec = torch.from_numpy((field / 2).astype(np.float32)).pin_memory()
+    d_e0, d_e1, d_v = e0.cuda(), e1.cuda(), vec.cuda()
+    rs = (w + 31) // 32 * 32
+    d_out = torch.empty((h, rs, 3), dtype=torch.uint8, device="cuda")
+    out_pin = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory()
+    fa = [float(synth.smoothstep(k / (nframes - 1))) for k in range(nframes)]
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    for k in range(3):
+        _lib.check(L.vm_render_halfway_dev(vp(d_out), rs, w, h, ex, fa[k], fa[k], 1, vp(d_e0), vp(d_e1), vp(d_v), None, sh))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record(stream)
+    for k in range(nframes):
+        _lib.check(L.vm_render_halfway_dev(vp(d_out), rs, w, h, ex, fa[k], fa[k], 1, vp(d_e0), vp(d_e1), vp(d_v), None, sh))
+    b.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = a.elapsed_time(b)
+    t0 = time.perf_counter()
+    for k in range(nframes):
+        _lib.check(L.vm_render_halfway(device, vp(out_pin), w, h, ex, fa[k], fa[k], 1, vp(e0), vp(e1), vp(vec), None, sh))
+    host_s = time.perf_counter() - t0
+    px = float(w) * h
+    peak, _ = load_peaks()
+    gbs = 27.0 * px * nframes / (dev_ms * 1e-3) / 1e9                              # 27 algorithmic B / output px (u8 RGBA inputs)
+    return {"metric": "morphed 720p frames/s", "frames": nframes, "device_resident_fps": nframes / (dev_ms * 1e-3),
+            "host_buffers_fps": nframes / host_s, "algorithmic_GBps": gbs, "hbm_frac": gbs / peak,
+            "note": "render_halfway_image, 20-step fixed-point inversion + bilinear RGBA fetch + cross-dissolve, color_from=1"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--cpu-seconds", type=float, default=25.0, help="bound of the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                       # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

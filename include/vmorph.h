@@ -132,6 +132,10 @@ int vm_morph_run(vm_morph *m, void *stream);
 int vm_morph_progress(const vm_morph *m, int *total_l, int *current_l, double *total_iter, double *current_iter, float *max_iter);
 /* sum over levels/frames of width*height*iterations actually executed (BASELINE.md metric numerator) */
 double vm_morph_executed_pixel_iters(const vm_morph *m);
+/* accumulated device time (ms, CUDA events on the launching stream) of the optimizer sweep launches collected so far
+ * and their count: the live measurement behind bench.py's roofline (no reference counterpart; the reference only
+ * clocks the whole stage, MatchingThread.cpp:141-145) */
+double vm_morph_sweep_ms(const vm_morph *m, uint64_t *launches_out);
 /* (level, frame, iterations) triples logged by optimize_level; returns count */
 int vm_morph_iters_log(const vm_morph *m, int max_triples, int32_t *out);
 /* operator-level entry points (for unit parity with the reference operators) */

@@ -83,6 +83,9 @@ def lib(native=False):
     L.vo_render_halfway.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, _u8p, _u8p, _fp, _fp]
     L.vo_qpath_optimize.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _ip]
     L.vo_set_num_threads.argtypes = [C.c_int]
+    L.vo_set_pow_mode.argtypes = [C.c_int]
+    L.vo_det_powf.argtypes = [C.c_float, C.c_float]
+    L.vo_det_powf.restype = C.c_float
     if not native:
         _lib = L
     return L
@@ -240,6 +243,15 @@ class Oracle:
         out = np.zeros(3 * 65536, np.int32)
         n = self.L.vo_iters_log(self.h, 65536, _ptr(out, _ip))
         return out[: 3 * n].reshape(n, 3)
+
+
+def set_pow_mode(mode):
+    """0 = libm powf (as the compiled reference), 1 = deterministic pow shared with the CUDA path (default)."""
+    lib().vo_set_pow_mode(int(mode))
+
+
+def det_powf(x, y):
+    return lib().vo_det_powf(float(x), float(y))
 
 
 def resample_scale(planes, hout, wout):

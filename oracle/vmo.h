@@ -28,6 +28,10 @@
 //  D3  the 25-term SSIM change sum (morph.cu:695-725) is summed either
 //      sequentially (reference order, sum_mode=0) or as a 32-leaf pairwise
 //      butterfly tree (sum_mode=1, the order the sm_100a warp reduction uses).
+//  D5  powf in the sRGB curves of the resampler (color.h:9-38): evaluated by a fixed
+//      sequence of IEEE double operations (pow_mode=1, default) that the CUDA path
+//      reproduces exactly; pow_mode=0 calls libm powf like the compiled reference.
+//      The modes agree to ~1 float ulp.
 //  D4  cv::Mat::inv (OpenCV 3.0, not vendored) is restated as f64 Gaussian
 //      elimination with partial pivoting; singular => conjugate-gradient
 //      minimum-norm solution (the pseudo-inverse the reference falls back to).
@@ -112,6 +116,8 @@ struct Pyramid {
 // --- resampler (include/resample) + Pyramid::build (pyramid.cu:166-485) ---
 struct Rgba { int h = 0, w = 0; std::vector<float> r, g, b, a; };
 void resample_scale(int hout, int wout, const Rgba &in, Rgba &out);          // scale.cpp:225-272
+void set_pow_mode(int m);              // D5: 0 = libm powf (as the compiled reference), 1 = deterministic double-op pow (default)
+float det_powf(float x, float y);      // the deterministic pow of D5
 void pyramid_build(Pyramid &P, const uint8_t *rgb0, const uint8_t *rgb1,
                    const float *f0, const float *f1, const float *b0, const float *b1,
                    int w, int h, int d, int start_res, long long voxel_cap);

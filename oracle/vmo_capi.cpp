@@ -145,6 +145,9 @@ void vo_resample_scale(const float *in, int hin, int win, float *out, int hout, 
     memcpy(out, b.r.data(), m * 4); memcpy(out + m, b.g.data(), m * 4); memcpy(out + 2 * m, b.b.data(), m * 4); memcpy(out + 3 * m, b.a.data(), m * 4);
 }
 
+void vo_set_pow_mode(int m) { set_pow_mode(m); }
+float vo_det_powf(float x, float y) { return det_powf(x, y); }
+
 void vo_render_halfway(uint8_t *out, int rowstride, int w, int hh, int ex, float color_fa, float geo_fa, int color_from,
                        const uint8_t *ext0, const uint8_t *ext1, const float *vec, const float *qpath) {
     render_halfway(out, rowstride, w, hh, ex, color_fa, geo_fa, color_from, ext0, ext1, vec, qpath);

@@ -10,16 +10,56 @@
 namespace vmo {
 
 namespace {
+// D5 (vmo.h): powf.  color.h:9-38 calls libm powf, whose result differs by an ulp between libm builds and from the
+// GPU's powf.  pow_mode 1 (default) evaluates pow through a fixed sequence of IEEE double operations
+// (no FMA contraction: -ffp-contract=off) that the CUDA path reproduces operation for operation, so both give
+// the same bits; pow_mode 0 calls libm powf (what the compiled reference does; used to pin this file against it).
+// The two modes agree to ~1 float ulp (tests/test_oracle_resample.py).
+//   log(x): x = m*2^e, m in (sqrt(.5), sqrt(2)], s = (m-1)/(m+1), log m = 2 s (1 + s^2/3 + ... + s^22/23)
+//   exp(t): k = floor(t/ln2 + .5), r = t - k ln2, exp r = Taylor degree 13 (Horner), result * 2^k
+int g_pow_mode = 1;
+inline double det_log(double x) {
+    uint64_t bits; memcpy(&bits, &x, 8);
+    int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    bits = (bits & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
+    double m; memcpy(&m, &bits, 8);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double s = (m - 1.0) / (m + 1.0), s2 = s * s;
+    double p = 1.0 / 23.0;
+    p = p * s2 + 1.0 / 21.0; p = p * s2 + 1.0 / 19.0; p = p * s2 + 1.0 / 17.0; p = p * s2 + 1.0 / 15.0;
+    p = p * s2 + 1.0 / 13.0; p = p * s2 + 1.0 / 11.0; p = p * s2 + 1.0 / 9.0; p = p * s2 + 1.0 / 7.0;
+    p = p * s2 + 1.0 / 5.0; p = p * s2 + 1.0 / 3.0; p = p * s2 + 1.0;
+    return 2.0 * s * p + (double)e * 0.6931471805599453;
+}
+inline double det_exp(double t) {
+    double k = std::floor(t * 1.4426950408889634 + 0.5);
+    double r = t - k * 0.6931471805599453;
+    double q = 1.0 / 6227020800.0;
+    q = q * r + 1.0 / 479001600.0; q = q * r + 1.0 / 39916800.0; q = q * r + 1.0 / 3628800.0; q = q * r + 1.0 / 362880.0;
+    q = q * r + 1.0 / 40320.0; q = q * r + 1.0 / 5040.0; q = q * r + 1.0 / 720.0; q = q * r + 1.0 / 120.0;
+    q = q * r + 1.0 / 24.0; q = q * r + 1.0 / 6.0; q = q * r + 0.5; q = q * r + 1.0; q = q * r + 1.0;
+    int ki = (int)k;
+    if (ki < -1000) return 0.0;
+    if (ki > 1000) ki = 1000;
+    uint64_t sb = (uint64_t)(ki + 1023) << 52;
+    double sc; memcpy(&sc, &sb, 8);
+    return q * sc;
+}
+inline float pow_f(float x, float y) {
+    if (g_pow_mode == 0) return powf(x, y);
+    if (!(x > 0.0f)) return 0.0f;          // never reached by the curves below (both call pow on positive arguments)
+    return (float)det_exp((double)y * det_log((double)x));
+}
 // color.h:9-18, 29-38
 inline float srgbcurve(float f) {
     const float a = 0.055f;
     if (f <= 0.0031308f) return 12.92f * f;
-    return (1.f + a) * powf(f, 1.f / 2.4f) - a;
+    return (1.f + a) * pow_f(f, 1.f / 2.4f) - a;
 }
 inline float srgbuncurve(float f) {
     const float a = 0.055f;
     if (f <= 0.04045f) return f / 12.92f;
-    return powf((f + a) / (1.f + a), 2.4f);
+    return pow_f((f + a) / (1.f + a), 2.4f);
 }
 inline float clamp01(float t) { return t < 0.f ? 0.f : (t > 1.f ? 1.f : t); }   // extension.h:30-34
 
@@ -255,6 +295,9 @@ f2 bilinear_flow(const f2 *img, int cols, int rows, float px, float py) {
     return r;
 }
 }  // namespace
+
+void set_pow_mode(int m) { g_pow_mode = m; }
+float det_powf(float x, float y) { int k = g_pow_mode; g_pow_mode = 1; float r = pow_f(x, y); g_pow_mode = k; return r; }
 
 void resample_scale(int hout, int wout, const Rgba &in, Rgba &out) {
     Planes p; p.h = in.h; p.w = in.w; p.nc = 4;

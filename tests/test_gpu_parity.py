@@ -200,3 +200,52 @@ def test_cancellation_and_progress(vm, oracle_lib):
     assert pr["total_l"] == n - 1 and pr["current_iter"] > 0 and pr["total_iter"] > 0
     o.run()
     np.testing.assert_array_equal(m.get_vectors(), o.extract_vectors())
+
+
+@pytest.mark.parametrize("w,h,d,start_res,cap", [(96, 72, 1, 8, 14000000), (150, 91, 1, 8, 14000000), (130, 100, 1, 8, 4000),
+                                                 (56, 40, 9, 4, 14000000), (64, 48, 12, 4, 60000)])
+def test_pyramid_build_parity(vm, oracle_lib, w, h, d, start_res, cap):
+    # Pyramid::build on the GPU (vm_pyramid_build) against the oracle's restatement of pyramid.cu:166-485 +
+    # include/resample, from the same RGB8 frames / flows: every level's gray images and flows, bit for bit
+    # (cap < w*h*d exercises the first-level down-sampling of pyramid.cu:223-226; d > 1 the temporal flow composition)
+    from videomorphing_b200 import synth
+    if d == 1:
+        v0, v1, _ = synth.image_pair(w, h, 300 + w, 400 + h, 3.0)
+        flows = None
+    else:
+        v0, v1, flows, _ = synth.video_pair(w, h, d, 51, 52, 3.0)
+    o = oracle_lib.Oracle(dict(start_res=start_res))
+    n = o.build(v0, v1, flows=flows, voxel_cap=cap)
+    pyr = vm.Pyramid(0)
+    assert pyr.build(v0, v1, flows, start_res=start_res, voxel_cap=cap) == n
+    if cap < w * h * d:
+        assert pyr.info(1)["w"] < w
+    for l in range(n):
+        a, b = pyr.info(l), o.info(l)
+        for k in ("w", "h", "d", "rowstride", "pagestride", "has_images"):
+            assert a[k] == b[k], (l, k)
+    for l in range(1, n - 1):
+        for f in ("img0", "img1") + (("f0", "f1", "b0", "b1") if flows is not None else ()):
+            got, ref = pyr.get(l, f), o.get(l, f)
+            err = float(np.abs(got.astype(np.float64) - ref).max())
+            assert err <= 2e-3, f"level {l} {f}: max abs err {err}"          # stated float tolerance (gray levels / px)
+            np.testing.assert_array_equal(got, ref, err_msg=f"level {l} {f} (max err {err})")
+    # building twice into the same handle reuses every buffer and gives the same result
+    assert pyr.build(v0, v1, flows, start_res=start_res, voxel_cap=cap) == n
+    np.testing.assert_array_equal(pyr.get(1, "img1"), o.get(1, "img1"))
+
+
+def test_end_to_end_from_rgb(vm, oracle_lib):
+    # the reference-facing call sequence: Pyramid::build -> Morph::calculate_halfway_parametrization -> update_result
+    from videomorphing_b200 import synth
+    rgb0, rgb1, field = synth.image_pair(120, 88, 91, 92, 4.0)
+    cons = synth.point_pairs(6, 120, 88, 93, field, margin=8)
+    o = oracle_lib.Oracle(dict(max_iter=40))
+    o.build(rgb0, rgb1); o.set_constraints(*cons); o.run()
+    pyr = vm.Pyramid(0)
+    pyr.build(rgb0, rgb1)
+    m = vm.Morph(vm.Parameters(max_iter=40), pyr)
+    m.set_constraints(*cons)
+    m.run()
+    np.testing.assert_array_equal(m.iters_log(), o.iters_log())
+    _assert_vec(m.get_vectors(), o.extract_vectors(), "end-to-end vectors")

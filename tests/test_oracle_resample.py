@@ -77,3 +77,28 @@ def test_scale_live_against_compiled_reference(oracle_lib):
         got = oracle_lib.resample_scale(planes, hout, wout)
         ref = oracle_lib.ref_scale_planar(planes, hout, wout)
         np.testing.assert_allclose(got[:3], ref[:3], rtol=0, atol=3e-6)
+
+
+def test_deterministic_pow_matches_libm_to_an_ulp(oracle_lib):
+    # oracle deviation D5: the sRGB curves use a fixed-operation-sequence pow shared with the CUDA path
+    rng = np.random.Generator(np.random.PCG64(12))
+    xs = np.concatenate([rng.random(20000, dtype=np.float32) * 1.5 + np.float32(0.003), np.float32([0.0031309, 0.04046, 1.0, 0.5, 2.0])])
+    for y in (np.float32(2.4), np.float32(1.0) / np.float32(2.4)):
+        ref = np.power(xs.astype(np.float64), np.float64(y)).astype(np.float32)
+        got = np.array([oracle_lib.det_powf(x, y) for x in xs], np.float32)
+        ulp = np.abs(got.astype(np.float64) - ref) / np.spacing(ref)
+        assert ulp.max() <= 1.0
+
+
+def test_pow_modes_agree_and_libm_mode_equals_compiled_reference(oracle_lib):
+    rng = np.random.Generator(np.random.PCG64(6))
+    planes = rng.random((4, 40, 40), dtype=np.float32)
+    try:
+        oracle_lib.set_pow_mode(0)
+        a = oracle_lib.resample_scale(planes, 40, 40)          # same-size = "upsample" path: 4 pow passes
+        if oracle_lib.ref_lib() is not None:
+            np.testing.assert_array_equal(a[:3], oracle_lib.ref_scale_planar(planes, 40, 40)[:3])   # libm mode: bit-equal
+    finally:
+        oracle_lib.set_pow_mode(1)
+    b = oracle_lib.resample_scale(planes, 40, 40)
+    np.testing.assert_allclose(a[:3], b[:3], rtol=0, atol=2e-6)

@@ -203,6 +203,12 @@ class Morph:
     def executed_pixel_iters(self):
         return self.L.vm_morph_executed_pixel_iters(self.h)
 
+    def sweep_time_ms(self):
+        """(accumulated device ms of the sweep launches, number of launches) -- CUDA events inside the library."""
+        n = C.c_uint64(0)
+        ms = self.L.vm_morph_sweep_ms(self.h, C.byref(n))
+        return ms, n.value
+
     def iters_log(self):
         out = np.zeros(3 * 65536, np.int32)
         n = check(self.L.vm_morph_iters_log(self.h, 65536, _vp(out)))

@@ -10,7 +10,7 @@ OUT = os.path.join(HERE, "libvmorph.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false",            # parity contract: no FMA contraction, IEEE div/sqrt (nvcc defaults)
-         "-shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+         "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
 
 
 def sources():

@@ -187,15 +187,25 @@ int vm_pyramid_create(int device, vm_pyramid **out) {
     *out = p;
     return VM_OK;
 }
-void vm_pyramid_destroy(vm_pyramid *p) { if (p) { cudaSetDevice(p->device); delete p; } }
+void vm_pyramid_destroy(vm_pyramid *p) { if (p) { cudaSetDevice(p->device); cudaDeviceSynchronize(); free_resample_cache(p); delete p; } }
 
 int vm_pyramid_alloc(vm_pyramid *p, int w, int h, int d, int start_res, int64_t voxel_cap) {
     if (!p || w <= 0 || h <= 0 || d <= 0 || start_res <= 0 || voxel_cap <= 0) { set_error("bad pyramid_alloc arguments"); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
     auto s = level_schedule(w, h, d, start_res, voxel_cap);
     if (s.size() < 3) { set_error("input %dx%dx%d too small for start_res %d (need >= 2 pyramid levels)", w, h, d, start_res); return VM_ERR_ARG; }
+    if (p->lv.size() == s.size() && p->w0 == w && p->h0 == h && p->d0 == d && p->a_start_res == start_res && p->a_cap == voxel_cap) {
+        // same shape as the current allocation: keep every buffer, reset the state a fresh allocation would have
+        for (size_t i = 1; i < p->lv.size(); i++) {
+            Level &L = p->lv[i];
+            VM_CUDA(cudaMemset(L.v.p, 0, sizeof(float2) * (size_t)L.ps * L.d));
+            L.v_valid = false; L.flows_valid = false;
+        }
+        p->state_level = -1;
+        return (int)s.size();
+    }
     p->lv.clear(); p->lv.resize(s.size());
-    p->w0 = w; p->h0 = h; p->d0 = d; p->state_level = -1;
+    p->w0 = w; p->h0 = h; p->d0 = d; p->state_level = -1; p->a_start_res = start_res; p->a_cap = voxel_cap;
     size_t max_state = 0, max_ps = 0, max_imp = 0;
     for (size_t i = 0; i < s.size(); i++) {
         Level &L = p->lv[i];
@@ -325,6 +335,7 @@ void vm_morph_destroy(vm_morph *m) {
     cudaDeviceSynchronize();
     if (m->run_flag_registered) cudaHostUnregister((void *)m->run_flag);
     if (m->progress_host) cudaFreeHost(m->progress_host);
+    for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
     delete m;
 }
 
@@ -463,8 +474,11 @@ static int enqueue_frame(vm_morph *m, int level, int frame, int flag, float max_
     VM_CUDA(m->ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(iters_cap)));
     VM_CUDA(cudaMemsetAsync(m->ctrl.p, 0, sizeof(unsigned) * sweep_ctrl_words(iters_cap), s));
     m->seqs.push_back({level, frame, (double)L.w * L.h, max_iter});
+    while (m->ev.size() < 2 * (size_t)(seq + 1)) { cudaEvent_t e; VM_CUDA(cudaEventCreate(&e)); m->ev.push_back(e); }
+    VM_CUDA(cudaEventRecord(m->ev[2 * seq], s));
     VM_CUDA(launch_sweep(make_view(p, level), kparams(m->prm), p->stencils.as<StencilTables>(), frame, flag, max_iter,
                          m->ctrl.as<unsigned>(), m->run_flag_dev, m->progress_dev, seq, p->sm_count, s));
+    VM_CUDA(cudaEventRecord(m->ev[2 * seq + 1], s));
     VM_CUDA(cudaMemcpyAsync(m->log_dev.as<unsigned>() + seq, m->ctrl.as<unsigned>() + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
     if (seq_out) *seq_out = seq;
     return VM_OK;
@@ -478,6 +492,8 @@ static int collect_log(vm_morph *m, size_t from, cudaStream_t s) {
     VM_CUDA(cudaStreamSynchronize(s));
     VM_CUDA(cudaMemcpy(it.data(), m->log_dev.as<unsigned>() + from, sizeof(unsigned) * (n - from), cudaMemcpyDeviceToHost));
     for (size_t k = from; k < n; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, m->ev[2 * k], m->ev[2 * k + 1]) == cudaSuccess) { m->sweep_ms += ms; m->sweep_launches++; } else cudaGetLastError();
         m->executed_pixel_iters += m->seqs[k].wh * it[k - from];
         m->iters_log.push_back(m->seqs[k].level); m->iters_log.push_back(m->seqs[k].frame); m->iters_log.push_back((int)it[k - from]);
     }
@@ -565,6 +581,11 @@ int vm_morph_progress(const vm_morph *m, int *total_l, int *current_l, double *t
     return VM_OK;
 }
 double vm_morph_executed_pixel_iters(const vm_morph *m) { return m ? m->executed_pixel_iters : 0.0; }
+double vm_morph_sweep_ms(const vm_morph *m, uint64_t *launches_out) {
+    if (!m) return 0.0;
+    if (launches_out) *launches_out = m->sweep_launches;
+    return m->sweep_ms;
+}
 int vm_morph_iters_log(const vm_morph *m, int max_triples, int32_t *out) {
     if (!m) return VM_ERR_ARG;
     int n = (int)m->iters_log.size() / 3;

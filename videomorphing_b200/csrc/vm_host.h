@@ -75,6 +75,8 @@ struct vm_pyramid {
     vm::DevBuf stencils;                  // StencilTables on the device
     vm::DevBuf tmp_a, tmp_b, tmp_c;       // transient scratch (splat accumulators, coarse solve, resampler planes)
     vm::HostStencils hst;
+    int a_start_res = 0; int64_t a_cap = 0;   // arguments of the last vm_pyramid_alloc (identical re-allocations are no-ops)
+    void *resample_cache = nullptr;       // vm::ResampleCache (vm_resample.cu): filter tables, prefilter factors, transient planes
 };
 
 struct vm_morph {
@@ -99,11 +101,16 @@ struct vm_morph {
     double executed_pixel_iters = 0;
     std::vector<int32_t> iters_log;
     bool cancelled = false;
+    // device time of the sweep launches (CUDA events on the launching stream around every k_sweep launch)
+    std::vector<cudaEvent_t> ev;          // 2 per launch: ev[2*seq], ev[2*seq+1]
+    double sweep_ms = 0;                  // accumulated by collect_log
+    uint64_t sweep_launches = 0;
 };
 
 namespace vm {
 
 LevelView make_view(vm_pyramid *p, int level);
+void free_resample_cache(vm_pyramid *p);
 
 // kernels (launchers) -- vm_kernels.cu / vm_sweep.cu / vm_render.cu / vm_resample.cu
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,

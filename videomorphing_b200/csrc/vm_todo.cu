@@ -3,8 +3,6 @@
 #include "vm_host.h"
 using namespace vm;
 extern "C" {
-int vm_pyramid_build(vm_pyramid *, const uint8_t *, const uint8_t *, const float *, const float *, const float *, const float *, int, int, int, int, int64_t, void *) {
-    set_error("vm_pyramid_build: GPU resampler not built in this revision"); return VM_ERR_STATE; }
 int vm_qpath_optimize(int, const float *, float *, int, int, int, float, int *, void *) {
     set_error("vm_qpath_optimize: not built in this revision"); return VM_ERR_STATE; }
 int vm_params_parse_xml(const char *, vm_params *, vm_tracks *) { set_error("vm_params_parse_xml: not built in this revision"); return VM_ERR_STATE; }
