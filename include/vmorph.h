@@ -169,6 +169,12 @@ int vm_render_halfway(int device, uint8_t *out, int w, int h, int ex, float colo
 /* one frame: vector (w*h float2, host) -> qpath (w*h float2, host). max_iter=10000, tol=1e-12 reproduce the reference */
 int vm_qpath_optimize(int device, const float *vector, float *qpath, int w, int h, int max_iter, float tol, int *iters_out, void *stream);
 
+/* Diagnostics (no reference counterpart): the sweep kernel evaluates SSIM with branch-free division / square root
+ * sequences that must equal IEEE round-to-nearest bit for bit.  Compares them with the compiler's div.rn / sqrt.rn on
+ * the device: mismatches3[0] = sqrt over every float in [2^-100, FLT_MAX] and +0, [1] = n_div pseudo-random quotients,
+ * [2] = every float in [2^-60, 2^40] (both signs) divided by each window count 4..25.  All three must be 0. */
+int vm_selftest_exact_arith(int device, uint64_t n_div, uint64_t *mismatches3);
+
 /* device memory helpers for callers that keep inputs resident (bench, multi-frame render) */
 int vm_dev_alloc(int device, size_t nbytes, void **out_dev);
 int vm_dev_free(int device, void *dev);

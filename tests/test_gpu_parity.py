@@ -115,16 +115,17 @@ def test_cluster_and_cta_width_do_not_change_results(vm, oracle_lib):
     rgb0, rgb1, _ = synth.image_pair(140, 90, 5, 6, 3.0)
     res = []
     try:
-        for env in ({"VMORPH_CLUSTER": "1", "VMORPH_WARPS": "8"}, {"VMORPH_CLUSTER": "2", "VMORPH_WARPS": "16"},
-                    {"VMORPH_CLUSTER": "4", "VMORPH_WARPS": "32"}, {"VMORPH_CLUSTER": "8", "VMORPH_WARPS": "32"}, {}):
-            for k in ("VMORPH_CLUSTER", "VMORPH_WARPS"):
+        for env in ({"VMORPH_CLUSTER": "1", "VMORPH_VARIANT": "thr8"}, {"VMORPH_CLUSTER": "2", "VMORPH_VARIANT": "thr16"},
+                    {"VMORPH_CLUSTER": "1", "VMORPH_VARIANT": "lat"}, {"VMORPH_CLUSTER": "4", "VMORPH_VARIANT": "lat"},
+                    {"VMORPH_CLUSTER": "8", "VMORPH_VARIANT": "lat"}, {"VMORPH_CLUSTER": "16", "VMORPH_VARIANT": "lat"}, {}):
+            for k in ("VMORPH_CLUSTER", "VMORPH_VARIANT"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             o, pyr, m, n = _setup(vm, oracle_lib, rgb0, rgb1, dict(max_iter=24))
             m.run()
             res.append((m.get_vectors(), m.iters_log()))
     finally:
-        for k in ("VMORPH_CLUSTER", "VMORPH_WARPS"):
+        for k in ("VMORPH_CLUSTER", "VMORPH_VARIANT"):
             os.environ.pop(k, None)
     for v, it in res[1:]:
         np.testing.assert_array_equal(v, res[0][0])
@@ -169,6 +170,14 @@ def test_render_parity(vm, oracle_lib):
                 psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
                 assert psnr >= 45.0, (color_from, t, psnr)          # north_star: rendered frames >= 45 dB
                 np.testing.assert_array_equal(got, ref)
+
+
+def test_exact_arith(vm):
+    # the branch-free division / square root of the sweep kernel (vm_device.cuh) == IEEE div.rn / sqrt.rn, bit for bit
+    import ctypes as C
+    out = (C.c_uint64 * 3)()
+    vm._lib.check(vm._lib.load().vm_selftest_exact_arith(0, 1 << 31, out))
+    assert list(out) == [0, 0, 0], f"sqrt / random-division / count-division mismatches: {list(out)}"
 
 
 def test_error_paths(vm):

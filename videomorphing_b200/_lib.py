@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvmorph.so")
+LIB_PATH = os.environ.get("VMORPH_LIB") or os.path.join(_HERE, "libvmorph.so")   # VMORPH_LIB: development builds (e.g. libvmorph_trace.so)
 
 
 class VmParams(C.Structure):
@@ -44,7 +44,7 @@ EXPORTS = [
     "vm_morph_sweep_ms", "vm_morph_iters_log", "vm_level_cpu_solve", "vm_level_upsample", "vm_level_initialize", "vm_level_init_temp",
     "vm_level_optimize_frame", "vm_level_optimize", "vm_level_energy", "vm_morph_get_vectors", "vm_stencils_get",
     "vm_render_halfway_dev", "vm_render_halfway", "vm_qpath_optimize", "vm_dev_alloc", "vm_dev_free", "vm_dev_upload",
-    "vm_dev_download", "vm_stream_sync", "vm_kernel_launch_count",
+    "vm_dev_download", "vm_stream_sync", "vm_kernel_launch_count", "vm_selftest_exact_arith",
 ]
 
 _lib = None
@@ -103,6 +103,7 @@ def load():
     L.vm_dev_upload.argtypes = [i32, vp, vp, C.c_size_t, vp]
     L.vm_dev_download.argtypes = [i32, vp, vp, C.c_size_t, vp]
     L.vm_stream_sync.argtypes = [i32, vp]
+    L.vm_selftest_exact_arith.argtypes = [i32, C.c_uint64, C.POINTER(C.c_uint64)]
     _lib = L
     return L
 

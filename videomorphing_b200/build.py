@@ -38,6 +38,19 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_trace():
+    """Development aid: libvmorph_trace.so = the same sources with -DVM_TRACE (per-phase cycle counters in the sweep)."""
+    out = os.path.join(HERE, "libvmorph_trace.so")
+    r = subprocess.run([NVCC] + FLAGS + ["-DVM_TRACE", "-o", out] + sources(), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("nvcc failed building libvmorph_trace.so")
+    return out
+
+
 if __name__ == "__main__":
-    build(force=True, verbose="-v" in sys.argv)
-    print(OUT)
+    if "--trace" in sys.argv:
+        print(build_trace())
+    else:
+        build(force=True, verbose="-v" in sys.argv)
+        print(OUT)

@@ -657,6 +657,18 @@ int vm_render_halfway(int device, uint8_t *out, int w, int h, int ex, float colo
     return VM_OK;
 }
 
+// ---------------------------------------------------------------- diagnostics
+int vm_selftest_exact_arith(int device, uint64_t n_div, uint64_t *mismatches3) {
+    if (!mismatches3) { set_error("null out"); return VM_ERR_ARG; }
+    int rc = use_device(device); if (rc) return rc;
+    DevBuf out; VM_CUDA(out.ensure(3 * sizeof(unsigned long long)));
+    VM_CUDA(launch_selftest_arith((unsigned long long)n_div, out.as<unsigned long long>(), 0));
+    unsigned long long h[3];
+    VM_CUDA(cudaMemcpy(h, out.p, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; k++) mismatches3[k] = h[k];
+    return VM_OK;
+}
+
 // ---------------------------------------------------------------- device memory helpers
 int vm_dev_alloc(int device, size_t nbytes, void **out_dev) {
     if (!out_dev || nbytes == 0) { set_error("bad alloc"); return VM_ERR_ARG; }

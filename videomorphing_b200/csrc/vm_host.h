@@ -126,6 +126,7 @@ cudaError_t launch_coarse_solve(const LevelView &L, const KParams &P, const Conn
                                 float *Af, double *Ad, double *rhs, int *status, cudaStream_t s);
 cudaError_t launch_energy(const LevelView &L, const KParams &P, int frame, int flag, double *out4_dev, cudaStream_t s);
 cudaError_t launch_extract(const LevelView &L1, float2 *out, int w0, int h0, int d0, int factor, cudaStream_t s);
+cudaError_t launch_selftest_arith(unsigned long long n_div, unsigned long long *out3_dev, cudaStream_t s);
 cudaError_t launch_render(uint8_t *out, int rowstride, int w, int h, int ex, float color_fa, float geo_fa, int color_from,
                           const uint8_t *ext0, const uint8_t *ext1, const float2 *vec, const float2 *qpath, cudaStream_t s);
 

@@ -500,4 +500,58 @@ cudaError_t launch_extract(const LevelView &L1, float2 *out, int w0, int h0, int
     return cudaGetLastError();
 }
 
+// =====================================================================================================
+// Self-test of div_fast / sqrt_fast (vm_device.cuh) against the compiler's IEEE div.rn / sqrt.rn on the device.
+// out[0]: sqrt mismatches over EVERY float in [2^-100, FLT_MAX] plus +0; out[1]: division mismatches over n_div
+// pseudo-random pairs (x sign-random with exponent in [2^-100, 2^40], y in [1, 2^30]); out[2]: division mismatches
+// over every float x in [2^-60, 2^40] divided by each of the SSIM window counts 4..25.
+// =====================================================================================================
+__device__ __forceinline__ unsigned int hash32(unsigned int x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+
+__global__ void k_selftest_sqrt(unsigned long long *out) {
+    unsigned long long bad = 0;
+    const unsigned lo = 0x0d800000u, hi = 0x7f7fffffu;
+    for (unsigned long long b = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= hi; b += (unsigned long long)gridDim.x * blockDim.x) {
+        float x = __uint_as_float((unsigned)b);
+        if (__float_as_uint(sqrt_fast(x)) != __float_as_uint(sqrtf(x))) bad++;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && __float_as_uint(sqrt_fast(0.0f)) != 0u) bad++;
+    if (bad) atomicAdd(out, bad);
+}
+__global__ void k_selftest_div(unsigned long long n, unsigned long long *out) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned h1 = hash32((unsigned)i * 2u + 1u), h2 = hash32((unsigned)(i >> 3) * 2654435761u + (unsigned)i + 77u), h3 = hash32(h1 ^ (h2 << 1));
+        unsigned ex = 27u + h3 % 141u;                      // biased exponent 27..167  -> 2^-100 .. 2^40
+        unsigned ey = 127u + (h3 >> 8) % 31u;               // 2^0 .. 2^30
+        float x = __uint_as_float((h1 & 0x807fffffu) | (ex << 23));
+        float y = __uint_as_float((h2 & 0x007fffffu) | (ey << 23));
+        if (__float_as_uint(div_fast(x, y)) != __float_as_uint(x / y)) bad++;
+    }
+    if (bad) atomicAdd(out + 1, bad);
+}
+__global__ void k_selftest_div_counts(unsigned long long *out) {
+    unsigned long long bad = 0;
+    const unsigned lo = (127u - 60u) << 23, hi = ((127u + 40u) << 23) | 0x7fffffu;
+    for (unsigned long long b = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= hi; b += (unsigned long long)gridDim.x * blockDim.x) {
+        float x = __uint_as_float((unsigned)b);
+#pragma unroll 1
+        for (int c = 4; c <= 25; c++) {
+            float y = (float)c;
+            if (__float_as_uint(div_fast(x, y)) != __float_as_uint(x / y)) bad++;
+            if (__float_as_uint(div_fast(-x, y)) != __float_as_uint(-x / y)) bad++;
+        }
+    }
+    if (bad) atomicAdd(out + 2, bad);
+}
+cudaError_t launch_selftest_arith(unsigned long long n_div, unsigned long long *out3_dev, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(out3_dev, 0, 3 * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    k_selftest_sqrt<<<148 * 8, 256, 0, s>>>(out3_dev);
+    k_selftest_div<<<148 * 8, 256, 0, s>>>(n_div, out3_dev);
+    k_selftest_div_counts<<<148 * 8, 256, 0, s>>>(out3_dev);
+    count_launch(3);
+    return cudaGetLastError();
+}
+
 }  // namespace vm

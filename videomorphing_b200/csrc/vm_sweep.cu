@@ -21,9 +21,22 @@
 #include "vm_device.cuh"
 #include "vm_host.h"
 #include <cooperative_groups.h>
+#include <cstring>
+#include <cstdlib>
 namespace cg = cooperative_groups;
 
 namespace vm {
+
+// Development-only phase timing (built into libvmorph_trace.so with -DVM_TRACE; never in libvmorph.so):
+// cycle counts of CTA 0 / warp 0 accumulated per phase of tile_step.
+#ifdef VM_TRACE
+__device__ unsigned long long g_trace[32];
+#define TR_DECL long long tr_t0 = clock64()
+#define TR(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t1 = clock64(); atomicAdd(&g_trace[k], (unsigned long long)(t1 - tr_t0)); atomicAdd(&g_trace[16 + (k)], 1ull); tr_t0 = t1; } else tr_t0 = clock64(); } while (0)
+#else
+#define TR_DECL
+#define TR(k)
+#endif
 
 constexpr int OPT_BW = 32, OPT_BH = 8, SPACING = 5;        // morph.cu:594-598
 constexpr int TW = OPT_BW * 2 + 4, TH = OPT_BH * 2 + 4;    // 68 x 20 tile (morph.cu:600-609)
@@ -100,7 +113,7 @@ __device__ __forceinline__ float warp_sum_tree(float t) {
 // Per-warp state for one pixel; scalar members are identical on all lanes, w_* are per-lane (window k = lane).
 struct PixelEval {
     const float *I0, *I1;
-    int W, H, px, py;
+    int W, H, px, py, lane;
     float2 v, old_luma;
     float tps_axy, ui_axy, tmask;
     float2 tps_b, ui_b, tref;
@@ -109,99 +122,211 @@ struct PixelEval {
     bool w_valid, flag;
     float w_ui, w_tps, w_ssim, w_temp, ssim_clamp, inv_wh, factor_d;
 
-    // morph.cu:672-761 (ssim_change + energy_change)
-    __device__ __forceinline__ float energy(float2 d) const {
-        float2 nv = make_float2(v.x + d.x, v.y + d.y);
-        float2 luma;
-        luma.x = tex2d<true>(I0, W, H, (float)px - nv.x + 0.5f, (float)py - nv.y + 0.5f);
-        luma.y = tex2d<true>(I1, W, H, (float)px + nv.x + 0.5f, (float)py + nv.y + 0.5f);
-        float term = 0.0f;
-        if (w_valid) {
+    // morph.cu:672-761 (ssim_change + energy_change) for N displacements at once.  The N evaluations are independent
+    // straight-line instruction streams (no branch anywhere: exact div / sqrt without the range-check branch, selects
+    // instead of early returns), so the compiler interleaves them: N results for roughly the latency of one.
+    template <int N>
+    __device__ __forceinline__ void energy_n(const float2 (&d)[N], float (&out)[N]) const {
+        float term[N];
+        // The 2N bilinear samples (image 0 at p - v - d_k, image 1 at p + v + d_k) are the same on every lane of the
+        // warp.  Instead of all 32 lanes computing all of them, lane f (mod 2N) computes sample f and the results are
+        // broadcast with one shuffle each: the same arithmetic on another lane, 2N times fewer instructions.
+        constexpr int NF = 2 * N;
+        float fetched;
+        {
+            const int fid = lane % NF, fk = fid >> 1, img = fid & 1;
+            float2 dk = d[0];
+#pragma unroll
+            for (int k = 1; k < N; k++) if (fk == k) dk = d[k];
+            float2 nv = make_float2(v.x + dk.x, v.y + dk.y);
+            // image 0: (float)px - nv.x + 0.5f ; image 1: (float)px + nv.x + 0.5f  (a - b == a + (-b) exactly)
+            float ox = img ? nv.x : -nv.x, oy = img ? nv.y : -nv.y;
+            fetched = tex2d<true>(img ? I1 : I0, W, H, (float)px + ox + 0.5f, (float)py + oy + 0.5f);
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            float2 luma;
+            luma.x = __shfl_sync(0xffffffffu, fetched, 2 * k);
+            luma.y = __shfl_sync(0xffffffffu, fetched, 2 * k + 1);
             float2 dmean = make_float2(luma.x - old_luma.x, luma.y - old_luma.y);
             float2 dvar = make_float2(luma.x * luma.x - old_luma.x * old_luma.x, luma.y * luma.y - old_luma.y * old_luma.y);
             float dcross = luma.x * luma.y - old_luma.x * old_luma.y;
             float2 m = make_float2(w_mean.x + dmean.x, w_mean.y + dmean.y);
             float2 vr = make_float2(w_var.x + dvar.x, w_var.y + dvar.y);
             float cr = w_cross + dcross;
-            term = w_value - ssim_value(m, vr, cr, w_cnt, ssim_clamp);
+            float sv = ssim_value_fast(m, vr, cr, w_cnt, ssim_clamp);
+            term[k] = w_valid ? (w_value - sv) : 0.0f;
         }
-        float v_ssim = warp_sum_tree(term);
-        float dd = d.x * d.x + d.y * d.y;
-        float v_tps = tps_axy * dd;
-        v_tps += tps_b.x * d.x;
-        v_tps += tps_b.y * d.y;
-        float v_ui = ui_axy * dd;
-        v_ui += ui_b.x * d.x;
-        v_ui += ui_b.y * d.y;
-        float v_temp = 0.0f;
-        if (flag) {
-            v_temp += fabsf(v.x + d.x - tref.x) - fabsf(v.x - tref.x);
-            v_temp += fabsf(v.y + d.y - tref.y) - fabsf(v.y - tref.y);
+        // 32-leaf butterfly per evaluation: lane k ends with ((t_k + t_{k^16}) + ...) -- identical on every lane
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int k = 0; k < N; k++) term[k] = term[k] + __shfl_xor_sync(0xffffffffu, term[k], off);
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            float dd = d[k].x * d[k].x + d[k].y * d[k].y;
+            float v_tps = tps_axy * dd;
+            v_tps += tps_b.x * d[k].x;
+            v_tps += tps_b.y * d[k].y;
+            float v_ui = ui_axy * dd;
+            v_ui += ui_b.x * d[k].x;
+            v_ui += ui_b.y * d[k].y;
+            float v_temp = 0.0f;
+            if (flag) {
+                v_temp += fabsf(v.x + d[k].x - tref.x) - fabsf(v.x - tref.x);
+                v_temp += fabsf(v.y + d[k].y - tref.y) - fabsf(v.y - tref.y);
+            }
+            out[k] = (w_ui * v_ui + w_ssim * term[k] + w_temp * v_temp * tmask * factor_d) * inv_wh + w_tps * v_tps;
         }
-        return (w_ui * v_ui + w_ssim * v_ssim + w_temp * v_temp * tmask * factor_d) * inv_wh + w_tps * v_tps;
+    }
+    __device__ __forceinline__ float energy(float2 d) const {
+        const float2 dd[1] = {d}; float o[1];
+        energy_n<1>(dd, o);
+        return o[0];
     }
 };
 
-// morph.cu:794-831
-__device__ __forceinline__ void fover_update_isec_min(float2 c, float2 grad, float2 e0, float2 e1, float &t_min) {
+// morph.cu:794-831, split in two: the geometry of one ring segment (branch-free, all 16 segments overlap) ...
+struct Isec { float ud, d, td; };
+__device__ __forceinline__ Isec fover_isec(float2 c, float2 grad, float2 e0, float2 e1) {
     float2 de = make_float2(e1.x - e0.x, e1.y - e0.y), dce = make_float2(c.x - e0.x, c.y - e0.y);
-    float d = de.y * grad.x - de.x * grad.y;
-    float td = -1;
-    float ud = grad.x * dce.y - grad.y * dce.x;
-    int sign = (__float_as_int(d) < 0) ? 1 : 0;      // signbit(d), true for -0.0 too
-    if (sign) { ud = -ud; d = -d; }
-    if (ud >= 0 && ud <= d) {
-        td = de.x * dce.y - de.y * dce.x;
-        td *= (float)(-sign * 2 + 1);
-        if (td >= 0 && td < t_min * d) t_min = td / d;
-    }
+    Isec r;
+    r.d = de.y * grad.x - de.x * grad.y;
+    r.ud = grad.x * dce.y - grad.y * dce.x;
+    int sign = (__float_as_int(r.d) < 0) ? 1 : 0;      // signbit(d), true for -0.0 too
+    if (sign) { r.ud = -r.ud; r.d = -r.d; }
+    r.td = de.x * dce.y - de.y * dce.x;
+    r.td *= (float)(-sign * 2 + 1);
+    return r;
+}
+// ... and the sequential minimum update (the division only runs when a fold-over constraint really binds)
+__device__ __forceinline__ void fover_update(const Isec &s, float &t_min) {
+    if (s.ud >= 0 && s.ud <= s.d)
+        if (s.td >= 0 && s.td < t_min * s.d) t_min = s.td / s.d;
 }
 
 // morph.cu:782-792 + 833-870.  nb[8] = v of the 8 neighbours in the order (-1,-1),(0,-1),(1,-1),(1,0),(1,1),(0,1),(-1,1),(-1,0),
 // inb bit k = neighbour k inside the image.  Quirk kept: vertex position is p-off with the vector of p+off.
-__device__ __forceinline__ void fover_calc_isec_min(int SIGN, int px, int py, const float2 *nb, unsigned inb, float2 v, float2 grad, float &t_min) {
+__device__ __forceinline__ void fover_ring(int SIGN, int px, int py, const float2 *nb, unsigned inb, float2 v, float2 grad, Isec (&out)[8]) {
     const int OX[8] = {-1, 0, 1, 1, 1, 0, -1, -1}, OY[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
     float2 c = make_float2((float)px + v.x, (float)py + v.y);
-    float2 first, prev;
+    float2 e[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         float2 vv = v;
         if ((inb >> k) & 1) vv = make_float2((float)SIGN * nb[k].x, (float)SIGN * nb[k].y);
-        float2 e = make_float2(vv.x + (float)(px - OX[k]), vv.y + (float)(py - OY[k]));
-        if (k == 0) first = e; else fover_update_isec_min(c, grad, prev, e, t_min);
-        prev = e;
+        e[k] = make_float2(vv.x + (float)(px - OX[k]), vv.y + (float)(py - OY[k]));
     }
-    fover_update_isec_min(c, grad, prev, first, t_min);
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[k] = fover_isec(c, grad, e[k], e[(k + 1) & 7]);    // segments (0,1) ... (6,7), (7,0)
 }
 
 // One warp optimises one pixel (morph.cu:1030-1083: compute_gradient, prevent_foldover, golden_section_search).
 // Returns true (uniformly) if the move is accepted; d_out = step.
-__device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float eps, const float2 *nb, unsigned inb, float2 &d_out) {
+// LAT (latency mode, coarse levels where only a few warps per SM have work): the four gradient evaluations run as
+// one batch, and the golden-section search evaluates, together with the point of step k, BOTH candidate points of
+// step k+1 (which of the two is used depends on the comparison that step k's value decides).  Two steps per batch
+// of three evaluations; every accepted value is computed by the same expression as in the sequential search, the
+// unused speculative value is dropped.  Results are identical by construction.
+#ifdef VM_TRACE
+#define TR_ARG , long long &tr_t0
+#define TR_PASS , tr_t0
+#else
+#define TR_ARG
+#define TR_PASS
+#endif
+template <bool LAT>
+__device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float eps, const float2 *nb, unsigned inb, bool spec, float2 &d_out TR_ARG) {
     float2 g;
-    g.x = E.energy(make_float2(eps, 0.0f)) - E.energy(make_float2(-eps, 0.0f));
-    g.y = E.energy(make_float2(0.0f, eps)) - E.energy(make_float2(0.0f, -eps));
+    if (LAT) {
+        const float2 dd[4] = {make_float2(eps, 0.0f), make_float2(-eps, 0.0f), make_float2(0.0f, eps), make_float2(0.0f, -eps)};
+        float o[4];
+        E.energy_n<4>(dd, o);
+        g.x = o[0] - o[1]; g.y = o[2] - o[3];
+    } else {
+        g.x = E.energy(make_float2(eps, 0.0f)) - E.energy(make_float2(-eps, 0.0f));
+        g.y = E.energy(make_float2(0.0f, eps)) - E.energy(make_float2(0.0f, -eps));
+    }
     float2 grad = make_float2(-g.x, -g.y);
     float ng = sqrtf(grad.x * grad.x + grad.y * grad.y);
     if (ng == 0.0f) return false;
     grad.x = grad.x / ng; grad.y = grad.y / ng;
+    TR(9);
     // prevent_foldover, morph.cu:872-883
     float t_min = 10.0f;
-    fover_calc_isec_min(-1, E.px, E.py, nb, inb, make_float2(-E.v.x, -E.v.y), make_float2(-grad.x, -grad.y), t_min);
-    fover_calc_isec_min(1, E.px, E.py, nb, inb, E.v, grad, t_min);
+    if (LAT) {
+        Isec sa[8], sb[8];
+        fover_ring(-1, E.px, E.py, nb, inb, make_float2(-E.v.x, -E.v.y), make_float2(-grad.x, -grad.y), sa);
+        fover_ring(1, E.px, E.py, nb, inb, E.v, grad, sb);
+#pragma unroll
+        for (int k = 0; k < 8; k++) fover_update(sa[k], t_min);
+#pragma unroll
+        for (int k = 0; k < 8; k++) fover_update(sb[k], t_min);
+    } else {
+#pragma unroll 1
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+            Isec sa[8];
+            fover_ring(sgn, E.px, E.py, nb, inb, make_float2((float)sgn * E.v.x, (float)sgn * E.v.y), make_float2((float)sgn * grad.x, (float)sgn * grad.y), sa);
+#pragma unroll
+            for (int k = 0; k < 8; k++) fover_update(sa[k], t_min);
+        }
+    }
     float c = maxf_std(t_min - eps, 0.0f);
+    TR(10);
     // golden_section_search, morph.cu:885-947
     const float R = 0.618033989f, C = 1.0f - R;
     float a = 0.0f;
     float b = a * R + c * C, x = b * R + c * C;
-    float fb = E.energy(make_float2(grad.x * b, grad.y * b)), fx = E.energy(make_float2(grad.x * x, grad.y * x));
-    while (c - a > eps) {
-        bool lt = fx < fb;
-        if (lt) { a = b; b = x; x = b * R + c * C; }
-        else { c = x; x = b * R + a * C; }
-        float f = E.energy(make_float2(grad.x * x, grad.y * x));
-        if (lt) { fb = fx; fx = f; }
-        else { float t = b; b = x; x = t; fx = fb; fb = f; }
+    float fb, fx;
+    if (!LAT || !spec) {
+        fb = E.energy(make_float2(grad.x * b, grad.y * b));
+        fx = E.energy(make_float2(grad.x * x, grad.y * x));
+        while (c - a > eps) {
+            bool lt = fx < fb;
+            if (lt) { a = b; b = x; x = b * R + c * C; }
+            else { c = x; x = b * R + a * C; }
+            float f = E.energy(make_float2(grad.x * x, grad.y * x));
+            if (lt) { fb = fx; fx = f; }
+            else { float t = b; b = x; x = t; fx = fb; fb = f; }
+        }
+    } else {
+        float fT, fF;              // values at the two candidate points of the NEXT step from the current state
+        bool have = false;
+        {
+            float pT = x * R + c * C;          // next step if fx < fb : a = b; b = x; x = b*R + c*C
+            float pF = b * R + a * C;          // otherwise           : c = x; x = b*R + a*C
+            const float2 dd[4] = {make_float2(grad.x * b, grad.y * b), make_float2(grad.x * x, grad.y * x),
+                                  make_float2(grad.x * pT, grad.y * pT), make_float2(grad.x * pF, grad.y * pF)};
+            float o[4];
+            E.energy_n<4>(dd, o);
+            fb = o[0]; fx = o[1]; fT = o[2]; fF = o[3]; have = true;
+        }
+        while (c - a > eps) {
+            bool lt = fx < fb;
+            float f;
+            if (have) {
+                f = lt ? fT : fF;
+                have = false;
+                if (lt) { a = b; b = x; x = b * R + c * C; }
+                else { c = x; x = b * R + a * C; }
+            } else {
+                if (lt) { a = b; b = x; x = b * R + c * C; }
+                else { c = x; x = b * R + a * C; }
+                // state after this step (positions only): (a1, b1, x1, c1)
+                float a1 = a, c1 = c, b1 = lt ? b : x, x1 = lt ? x : b;
+                if (c1 - a1 > eps) {
+                    float pT = x1 * R + c1 * C, pF = b1 * R + a1 * C;
+                    const float2 dd[3] = {make_float2(grad.x * x, grad.y * x), make_float2(grad.x * pT, grad.y * pT), make_float2(grad.x * pF, grad.y * pF)};
+                    float o[3];
+                    E.energy_n<3>(dd, o);
+                    f = o[0]; fT = o[1]; fF = o[2]; have = true;
+                } else f = E.energy(make_float2(grad.x * x, grad.y * x));
+            }
+            if (lt) { fb = fx; fx = f; }
+            else { float t = b; b = x; x = t; fx = fb; fb = f; }
+        }
     }
+    TR(11);
     float tmin, fmin;
     if (fx < fb) { tmin = x; fmin = fx; } else { tmin = b; fmin = fb; }
     if (fmin < 0.0f) { d_out = make_float2(grad.x * tmin, grad.y * tmin); return true; }
@@ -211,7 +336,7 @@ __device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float ep
 // One tile of one offset step (one block of one launch of the reference, morph.cu:1281-1345), executed by a
 // cluster of R CTAs (R == 1: a single CTA).  Everything that decides control flow is computed redundantly and
 // deterministically by every CTA of the cluster, so the cluster barriers are always reached by all of them.
-template <int NW>
+template <int NW, bool LAT>
 __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, const StencilTables *__restrict__ st,
                           int page, bool flag, int ox, int oy, int R, int rank, unsigned int &phase) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -219,6 +344,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
     const size_t poff = (size_t)page * L.ps;
     const float *I0 = L.img0 + (size_t)page * L.w * L.h, *I1 = L.img1 + (size_t)page * L.w * L.h;
     cg::cluster_group cluster = cg::this_cluster();
+    TR_DECL;
 
     // --- tile skip: no improving bit of any pixel inside the tile extent => no pixel can be active (exact).
     // Only bits of pixels inside this tile's extent are tested: those are never modified by another cluster during
@@ -239,6 +365,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
         }
         if (!__syncthreads_or(any)) return;
     }
+    TR(0);
     // --- LoadSSIM (morph.cu:1214-1234) + counter + tps.b into this CTA's replica
     for (int c = tid; c < TCELLS; c += NT) {
         int sy = c / TW, sx = c - sy * TW;
@@ -254,6 +381,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
     }
     bool dirty = false;
     __syncthreads();
+    TR(1);
 
     for (int si = 0; si < 2; ++si)
         for (int sj = 0; sj < 2; ++sj) {
@@ -290,16 +418,21 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                 S.queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)tid;
             }
             __syncthreads();
+            TR(2);
+            // speculative line search only while the SM has issue slots to spare (at most ~1.5 busy warps per scheduler);
+            // qn, R are the same in every CTA of the cluster, so the choice is uniform (and does not change results)
+            const bool spec = LAT && qn <= 6 * R;
             // ---- compute: one warp per active pixel, all from the pre-sub-phase state; the owning warp commits the
             //      pixel's own cells at once (nobody else reads them in this sub-phase) and broadcasts the deltas
-            for (int q = rank * NW + warp; q < qn; q += R * NW) {
+            //      (queue entry q goes to CTA q % R, warp q / R: the active pixels spread over all SMs of the cluster)
+            for (int q = warp * R + rank; q < qn; q += R * NW) {
                 int slot = S.queue[q];
                 int tx = slot & 31, ty = slot >> 5;
                 int lx = tx * 2 + sj + 2, ly = ty * 2 + si + 2;
                 int px = ox + lx, py = oy + ly;
                 size_t idx = (size_t)py * L.rs + px + poff;
                 PixelEval E;
-                E.I0 = I0; E.I1 = I1; E.W = L.w; E.H = L.h; E.px = px; E.py = py;
+                E.I0 = I0; E.I1 = I1; E.W = L.w; E.H = L.h; E.px = px; E.py = py; E.lane = lane;
                 E.v = __ldcg(L.v + idx); E.old_luma = __ldcg(L.luma + idx);
                 E.tps_axy = __ldcg(L.tps_axy + idx); E.ui_axy = __ldcg(L.ui_axy + idx);
                 E.ui_b = __ldcg(L.ui_b + idx);
@@ -331,7 +464,8 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                     }
                 }
                 float2 d;
-                bool ok = optimize_pixel_warp(E, P.eps, nb, inb, d);
+                TR(8);
+                bool ok = optimize_pixel_warp<LAT>(E, P.eps, nb, inb, spec, d TR_PASS);
                 int bx = px / 5, by = py / 5;
                 unsigned bit = 1u << ((px - bx * 5) + (py - by * 5) * 5);
                 unsigned *mw = L.impmask + page * L.ips + (by + 1) * L.irs + (bx + 1);
@@ -359,9 +493,12 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                 } else if (lane == 0) {
                     atomicAnd(mw, ~bit);                            // morph.cu:1328-1332
                 }
+                TR(12);
             }
+            TR(3);
             // every mask / v / luma update of this sub-phase is ordered before the next filter by this barrier
             if (R > 1) cluster.sync(); else __syncthreads();
+            TR(4);
             // ---- commit B: deterministic gather of the SSIM-sum and TPS deltas into the replica, then UpdateSSIM
             //      (morph.cu:973-987,1006-1015,1258-1279).  Contributors in row-major order of the source pixel.
             int any = (tid < NPIX) ? (int)SB.acc[tid] : 0;
@@ -372,14 +509,20 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                     float2 m = S.mean[c], vr = S.var[c], tb = S.tpsb[c];
                     float cr = S.cross[c];
                     bool ch_s = false, ch_t = false;
+                    // contributors sit on the stride-2 lattice of this colour: at most 3 x 3 of them reach a cell.
+                    // Visited in row-major order of the source pixel (dy, dx ascending), like the oracle.
+                    const int ty0 = sy - si - 4, tx0 = sx - sj - 4;          // t = sy + dy - si - 2 with dy = -2
+                    const int dyb = (ty0 & 1) ? -1 : -2, dxb = (tx0 & 1) ? -1 : -2;
 #pragma unroll
-                    for (int dy = -2; dy <= 2; dy++) {
+                    for (int ky = 0; ky < 3; ky++) {
+                        int dy = dyb + 2 * ky;
                         int t = sy + dy - si - 2;
-                        if (t < 0 || (t & 1) || (t >> 1) >= OPT_BH) continue;
+                        if (dy > 2 || t < 0 || (t >> 1) >= OPT_BH) continue;
 #pragma unroll
-                        for (int dx = -2; dx <= 2; dx++) {
+                        for (int kx = 0; kx < 3; kx++) {
+                            int dx = dxb + 2 * kx;
                             int s2 = sx + dx - sj - 2;
-                            if (s2 < 0 || (s2 & 1) || (s2 >> 1) >= OPT_BW) continue;
+                            if (dx > 2 || s2 < 0 || (s2 >> 1) >= OPT_BW) continue;
                             int slot = (t >> 1) * OPT_BW + (s2 >> 1);
                             if (!SB.acc[slot]) continue;
                             int B = S.bcls[slot];
@@ -395,7 +538,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                     }
                     if (ch_s) {
                         S.mean[c] = m; S.var[c] = vr; S.cross[c] = cr;
-                        S.value[c] = ssim_value(m, vr, cr, S.cnt[c], P.ssim_clamp);
+                        S.value[c] = ssim_value_fast(m, vr, cr, S.cnt[c], P.ssim_clamp);
                     }
                     if (ch_t) S.tpsb[c] = tb;
                 }
@@ -404,6 +547,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             }
             phase++;
             __syncthreads();
+            TR(5);
         }
     // --- SaveSSIM (morph.cu:1236-1256) + tps.b, only when something was committed; replicas are identical, rank 0 stores
     if (dirty) {
@@ -419,12 +563,13 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
         if (tid == 0) S.cta_improving = 1;
     }
     __syncthreads();
+    TR(6);
 }
 
 // ctrl layout (unsigned ints): [0] barrier counter, [1] iterations executed (out), [2] cancelled (out),
 // [8 + it] per-iteration flags: bit0 = improving, bit1 = cancel requested.
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, (NW <= 8 ? 4 : (NW <= 16 ? 2 : 1)))
+template <int NW, bool LAT>
+__global__ void __launch_bounds__(NW * 32, (LAT ? 1 : (NW <= 8 ? 3 : 2)))
 k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, int flag, float max_iter,
         unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -457,7 +602,7 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
                     int by = t / gx, bx = t - by * gx;
                     int ox = bx * (OPT_BW * 2 + SPACING) + offx - 2, oy = by * (OPT_BH * 2 + SPACING) + offy - 2;
                     if (ox + 2 >= L.w || oy + 2 >= L.h) continue;
-                    tile_step<NW>(S, L, P, st, page, flag != 0, ox, oy, R, rank, phase);
+                    tile_step<NW, LAT>(S, L, P, st, page, flag != 0, ox, oy, R, rank, phase);
                 }
             }
             if (step == 3 && tid == 0) {                      // publish this CTA's vote before the iteration's last barrier
@@ -465,7 +610,11 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
                 if (blockIdx.x == 0 && run_flag && *run_flag == 0) f |= 2u;
                 if (f) atomicOr(&ctrl[8 + iter], f);
             }
+#ifdef VM_TRACE
+            long long tr_t0 = clock64();
+#endif
             if (!empty || step == 3) grid_barrier(&ctrl[0], epoch, gridDim.x);
+            TR(7);
         }
         unsigned f = __ldcg(&ctrl[8 + iter]);
         iter++;
@@ -477,15 +626,15 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
 }
 
 // ------------------------------------------------------------------ host launcher
-struct SweepCfg { bool init = false; int max_clusters[4] = {0, 0, 0, 0}; };   // index = log2(R)
+struct SweepCfg { bool init = false; int max_clusters[5] = {0, 0, 0, 0, 0}; };   // index = log2(R)
 static SweepCfg g_cfg[3];
 
-template <int NW>
+template <int NW, bool LAT>
 static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag,
                                   float max_iter, unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq,
                                   int ntiles, int sm_count, cudaStream_t stream, int slot, int want_r) {
     size_t smem = sizeof(SweepSmem);
-    auto kern = k_sweep<NW>;
+    auto kern = k_sweep<NW, LAT>;
     SweepCfg &cfg = g_cfg[slot];
     if (!cfg.init) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -495,7 +644,9 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         cfg.max_clusters[0] = per_sm * sm_count;
-        for (int lg = 1; lg <= 3; lg++) {
+        if (LAT) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);      // clusters of 16 CTAs
+        cudaGetLastError();
+        for (int lg = 1; lg <= (LAT ? 4 : 3); lg++) {
             cudaLaunchConfig_t qc = {};
             qc.gridDim = dim3(1 << lg); qc.blockDim = dim3(NW * 32); qc.dynamicSmemBytes = smem;
             cudaLaunchAttribute at[1];
@@ -509,7 +660,7 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
     }
     // cluster size: the largest power of two <= want_r for which one cluster per tile is co-resident
     int lg = 0;
-    for (int c = 3; c >= 1; c--) if ((1 << c) <= want_r && cfg.max_clusters[c] >= ntiles) { lg = c; break; }
+    for (int c = 4; c >= 1; c--) if ((1 << c) <= want_r && cfg.max_clusters[c] >= ntiles) { lg = c; break; }
     int R = 1 << lg;
     int nclusters = ntiles < cfg.max_clusters[lg] ? ntiles : cfg.max_clusters[lg];
     LevelView Lc = L; KParams Pc = P;
@@ -531,24 +682,35 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
     return e;
 }
 
-// test hooks (read on every launch): VMORPH_CLUSTER=1/2/4/8 caps the cluster size, VMORPH_WARPS=8/16/32 pins the CTA width
-
+// Kernel variants:
+//   lat   16 warps, 1 CTA / SM (up to 128 registers): batched + speculative energy evaluations; a cluster of up to 16
+//         CTAs per tile.  For levels with at most one tile per SM, where the dependent chain of one pixel's line
+//         search, not throughput, bounds the step.
+//   thr16 16 warps, 2 CTAs / SM;  thr8  8 warps, 3 CTAs / SM: sequential line search, for levels with many tiles.
+// Test hooks (read on every launch): VMORPH_CLUSTER=1/2/4/8 caps the cluster size, VMORPH_VARIANT=lat|thr16|thr8.
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
                          unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, cudaStream_t stream) {
     const int gx = (L.w + OPT_BW * 2 + SPACING - 1) / (OPT_BW * 2 + SPACING);
     const int gy = (L.h + OPT_BH * 2 + SPACING - 1) / (OPT_BH * 2 + SPACING);
     const int ntiles = gx * gy;
-    const char *ec = getenv("VMORPH_CLUSTER"), *ew = getenv("VMORPH_WARPS");
-    const int g_force_cluster = ec ? atoi(ec) : 0, g_force_warps = ew ? atoi(ew) : 0;
-    int want_r = g_force_cluster > 0 ? g_force_cluster : 8;
-    int nw = g_force_warps;
-    // few tiles: latency-bound chain -> widest CTA (32 warps) and a cluster per tile; many tiles: 8-warp CTAs, 4 per SM.
-    if (!nw) nw = (ntiles <= sm_count) ? 32 : (ntiles <= 2 * sm_count ? 16 : 8);
-    if (nw >= 32) return launch_sweep_t<32>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 0, want_r);
-    if (nw >= 16) return launch_sweep_t<16>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 1, want_r);
-    return launch_sweep_t<8>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 2, want_r);
+    const char *ec = getenv("VMORPH_CLUSTER"), *ev = getenv("VMORPH_VARIANT");
+    int want_r = (ec && atoi(ec) > 0) ? atoi(ec) : 16;
+    int variant = (ntiles <= sm_count) ? 0 : (ntiles <= 2 * sm_count ? 1 : 2);
+    if (ev) variant = !strcmp(ev, "lat") ? 0 : (!strcmp(ev, "thr16") ? 1 : (!strcmp(ev, "thr8") ? 2 : variant));
+    if (variant == 0) return launch_sweep_t<16, true>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 0, want_r);
+    if (variant == 1) return launch_sweep_t<16, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 1, want_r);
+    return launch_sweep_t<8, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 2, want_r);
 }
 
 size_t sweep_ctrl_words(int max_iter_ceil) { return 8 + (size_t)max_iter_ceil + 8; }
+
+#ifdef VM_TRACE
+extern "C" int vm_debug_trace(unsigned long long *out32, int reset) {
+    cudaDeviceSynchronize();
+    if (out32) cudaMemcpyFromSymbol(out32, g_trace, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_trace, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 }  // namespace vm
