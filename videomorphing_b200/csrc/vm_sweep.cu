@@ -42,6 +42,7 @@ constexpr int OPT_BW = 32, OPT_BH = 8, SPACING = 5;        // morph.cu:594-598
 constexpr int TW = OPT_BW * 2 + 4, TH = OPT_BH * 2 + 4;    // 68 x 20 tile (morph.cu:600-609)
 constexpr int TCELLS = TW * TH;
 constexpr int NPIX = OPT_BW * OPT_BH;                      // pixels per colour sub-phase
+constexpr int MASK_W = 16, MASK_H = 6;                     // improving-mask cells covering a tile's own pixels +- 1 cell
 
 // accepted moves of one colour sub-phase; written by the owning warp into EVERY CTA of the cluster (DSMEM)
 struct SlotBuf {
@@ -58,6 +59,9 @@ struct SweepSmem {
     unsigned char bcls[NPIX];        // By*5+Bx of the pixel
     unsigned short queue[NPIX];
     int warp_cnt[NPIX / 32];
+    unsigned int stat_any[NPIX / 32];    // per filter warp: ballot of pixels that have a mask index
+    unsigned int accrow[OPT_BH];         // accepted slots of the sub-phase, one 32-bit row per lattice row
+    unsigned int mask[MASK_W * MASK_H];  // improving-mask words around the tile (see tile_step)
     float tps[25 * 25];
     unsigned int iomask[25];
     int cta_improving;
@@ -77,22 +81,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
         }
         __syncthreads();
     }
-}
-
-// morph.cu:621-646
-__device__ __forceinline__ int get_improve_mask_idx(const LevelView &L, const StencilTables *__restrict__ st, int page, int px, int py) {
-    int bx = px / 5, by = py / 5, ox = px - bx * 5, oy = py - by * 5;
-    int begi = oy >= 2 ? 1 : 0, begj = ox >= 2 ? 1 : 0;
-    int impmask_idx = page * L.ips + (by + 1) * L.irs + (bx + 1);
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            int ii = begi + i, jj = begj + j;
-            int d = impmask_idx + (ii - 1) * L.irs + (jj - 1);
-            if (__ldcg(L.impmask + d) & __ldg(&st->improv[oy * 5 + ox][ii * 3 + jj])) return impmask_idx;
-        }
-    return -1;
 }
 
 // morph.cu:648-667 (the BCOND_CORNER '&&' typo is kept: only the two x==0 corners lock, unless h==1)
@@ -336,6 +324,15 @@ __device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float ep
 // One tile of one offset step (one block of one launch of the reference, morph.cu:1281-1345), executed by a
 // cluster of R CTAs (R == 1: a single CTA).  Everything that decides control flow is computed redundantly and
 // deterministically by every CTA of the cluster, so the cluster barriers are always reached by all of them.
+// One tile of one offset step (one block of one launch of the reference, morph.cu:1281-1345), executed by a
+// cluster of R CTAs (R == 1: a single CTA).  Everything that decides control flow is computed redundantly and
+// deterministically by every CTA of the cluster, so the cluster barriers are always reached by all of them.
+//
+// Improving mask: the words around the tile are replicated in shared memory for the duration of the step.  Only bits
+// of pixels inside the tile extent are ever looked at (5-pixel tile spacing: the 5x5 window of an own pixel reaches
+// own and gap pixels only), and only the tile's own pixels' bits change, so concurrent tiles never depend on each
+// other's words; the own words are stored back at the end of the step.  All optimize_pixel decisions of a sub-phase see
+// the mask as it was before the sub-phase; set / clear (morph.cu:1320-1332) happen at commit, like the reference.
 template <int NW, bool LAT>
 __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, const StencilTables *__restrict__ st,
                           int page, bool flag, int ox, int oy, int R, int rank, unsigned int &phase) {
@@ -346,27 +343,35 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
     cg::cluster_group cluster = cg::this_cluster();
     TR_DECL;
 
-    // --- tile skip: no improving bit of any pixel inside the tile extent => no pixel can be active (exact).
-    // Only bits of pixels inside this tile's extent are tested: those are never modified by another cluster during
-    // this step, so all CTAs of the cluster take the same decision.
+    // --- mask replica: mask-array cells [mcx0, mcx0+MASK_W) x [mcy0, mcy0+MASK_H) (array coordinates, i.e. pixel cell + 1)
+    const int mcx0 = (ox + 2) / 5, mcy0 = (oy + 2) / 5;
+    const int irows = L.ips / L.irs;
+    unsigned int *gmask = L.impmask + (size_t)page * L.ips;
     {
+        // tile skip: no improving bit of any pixel inside the tile extent => no pixel can be active (exact).
         // (the extent is clipped to the mask's interior cells, NOT to the image: bits of the never-existing pixels in
         //  partial right/bottom cells stay set forever and keep their neighbours active in the reference)
         int ex0 = max(ox, 0), ex1 = min(ox + TW - 1, ((L.w + 4) / 5) * 5 - 1), ey0 = max(oy, 0), ey1 = min(oy + TH - 1, ((L.h + 4) / 5) * 5 - 1);
-        int cx0 = ex0 / 5, cx1 = ex1 / 5, cy0 = ey0 / 5, cy1 = ey1 / 5;
-        int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1;
         int any = 0;
-        for (int k = tid; k < ncx * ncy; k += NT) {
-            int cy = cy0 + k / ncx, cx = cx0 + k % ncx;
+        if (tid < MASK_W * MASK_H) {
+            int my = tid / MASK_W, mx = tid - my * MASK_W;
+            int cx = mcx0 + mx, cy = mcy0 + my;                 // array coordinates
+            unsigned word = 0;
+            if (cx < L.irs && cy < irows) word = __ldcg(gmask + cy * L.irs + cx);
+            S.mask[tid] = word;
+            int pcx = cx - 1, pcy = cy - 1;                     // pixel-cell coordinates
             unsigned xm = 0, m = 0;
-            for (int r = 0; r < 5; r++) if (cx * 5 + r >= ex0 && cx * 5 + r <= ex1) xm |= 1u << r;
-            for (int r = 0; r < 5; r++) if (cy * 5 + r >= ey0 && cy * 5 + r <= ey1) m |= xm << (5 * r);
-            any |= (__ldcg(L.impmask + page * L.ips + (cy + 1) * L.irs + (cx + 1)) & m) != 0u;
+            for (int r = 0; r < 5; r++) if (pcx * 5 + r >= ex0 && pcx * 5 + r <= ex1) xm |= 1u << r;
+            for (int r = 0; r < 5; r++) if (pcy * 5 + r >= ey0 && pcy * 5 + r <= ey1) m |= xm << (5 * r);
+            any = (pcx >= 0 && pcy >= 0 && (word & m) != 0u);
         }
         if (!__syncthreads_or(any)) return;
     }
     TR(0);
-    // --- LoadSSIM (morph.cu:1214-1234) + counter + tps.b into this CTA's replica
+    // --- LoadSSIM (morph.cu:1214-1234) + counter + tps.b into this CTA's replica; cells outside the image are zero
+    // tile-local rectangle of cells that lie inside the image
+    const int rx0 = max(0, -ox), rx1 = min(TW, L.w - ox), ry0 = max(0, -oy), ry1 = min(TH, L.h - oy);
+    const int rw = rx1 - rx0, rh = ry1 - ry0, rcells = rw * rh;
     for (int c = tid; c < TCELLS; c += NT) {
         int sy = c / TW, sx = c - sy * TW;
         int x = ox + sx, y = oy + sy;
@@ -379,14 +384,14 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             S.cross[c] = S.value[c] = S.cnt[c] = 0.f;
         }
     }
-    bool dirty = false;
+    bool dirty = false, mdirty = false;
     __syncthreads();
     TR(1);
 
     for (int si = 0; si < 2; ++si)
         for (int sj = 0; sj < 2; ++sj) {
             SlotBuf &SB = S.slot[phase & 1u];
-            // ---- filter: which pixels of this colour have an improving neighbourhood (morph.cu:1041-1054);
+            // ---- filter: which pixels of this colour have an improving neighbourhood (morph.cu:1041-1054, 621-646);
             //      deterministic compaction (slot order) so every CTA of the cluster builds the same queue
             bool act = false; unsigned bal = 0;
             if (tid < NPIX) {
@@ -394,30 +399,36 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                 int px = ox + tx * 2 + sj + 2, py = oy + ty * 2 + si + 2;
                 unsigned char stt = 0;
                 if (px >= 0 && px < L.w && py >= 0 && py < L.h) {
-                    int idx = get_improve_mask_idx(L, st, page, px, py);
-                    if (idx >= 0) {
-                        stt = 1; act = !pixel_on_border(L, P.bcond, px, py);
-                        if (!act && (tid % R) == rank) {          // locked border pixel: ok == false (morph.cu:1328-1332)
-                            int bx = px / 5, by = py / 5;
-                            atomicAnd(L.impmask + page * L.ips + (by + 1) * L.irs + (bx + 1), ~(1u << ((px - bx * 5) + (py - by * 5) * 5)));
+                    int bx = px / 5, by = py / 5, oxx = px - bx * 5, oyy = py - by * 5;
+                    int begi = oyy >= 2 ? 1 : 0, begj = oxx >= 2 ? 1 : 0;
+                    const unsigned *imp = st->improv[oyy * 5 + oxx];
+                    int lx = bx + 1 - mcx0, ly = by + 1 - mcy0;           // this pixel's cell inside the replica
+                    bool hit = false;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            int ii = begi + i, jj = begj + j;
+                            hit |= (S.mask[(ly + ii - 1) * MASK_W + (lx + jj - 1)] & __ldg(imp + ii * 3 + jj)) != 0u;
                         }
-                    }
+                    if (hit) { stt = 1; act = !pixel_on_border(L, P.bcond, px, py); }
                     S.bcls[tid] = (unsigned char)(border_class(py, L.h) * 5 + border_class(px, L.w));
                 }
                 S.status[tid] = stt;
                 bal = __ballot_sync(0xffffffffu, act);
-                if (lane == 0) S.warp_cnt[warp] = __popc(bal);
+                unsigned sbal = __ballot_sync(0xffffffffu, stt != 0);
+                if (lane == 0) { S.warp_cnt[warp] = __popc(bal); S.stat_any[warp] = sbal; }
             }
             __syncthreads();
-            int qn = 0;
+            int qn = 0; unsigned stat_any = 0;
 #pragma unroll
-            for (int k = 0; k < NPIX / 32; k++) qn += S.warp_cnt[k];
+            for (int k = 0; k < NPIX / 32; k++) { qn += S.warp_cnt[k]; stat_any |= S.stat_any[k]; }
             if (tid < NPIX && act) {
                 int base = 0;
                 for (int k = 0; k < warp; k++) base += S.warp_cnt[k];
                 S.queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)tid;
             }
-            __syncthreads();
+            if (qn > 0) __syncthreads();
             TR(2);
             // speculative line search only while the SM has issue slots to spare (at most ~1.5 busy warps per scheduler);
             // qn, R are the same in every CTA of the cluster, so the choice is uniform (and does not change results)
@@ -466,9 +477,6 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                 float2 d;
                 TR(8);
                 bool ok = optimize_pixel_warp<LAT>(E, P.eps, nb, inb, spec, d TR_PASS);
-                int bx = px / 5, by = py / 5;
-                unsigned bit = 1u << ((px - bx * 5) + (py - by * 5) * 5);
-                unsigned *mw = L.impmask + page * L.ips + (by + 1) * L.irs + (bx + 1);
                 if (ok) {
                     // commit of the pixel's own cells (morph.cu:951-971,1017-1025,1320-1327)
                     float2 newv = make_float2(E.v.x + d.x, E.v.y + d.y);
@@ -484,47 +492,74 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                         ub.x += 2 * d.x * E.ui_axy; ub.y += 2 * d.y * E.ui_axy;
                         L.ui_b[idx] = ub;
                         L.v[idx] = newv;
-                        atomicOr(mw, bit);
                     }
                     if (lane < R) {                                // broadcast into every replica's slot buffer
                         SlotBuf *dst = (R > 1) ? cluster.map_shared_rank(&SB, lane) : &SB;
                         dst->d[slot] = d; dst->dm[slot] = dm; dst->dv[slot] = dv; dst->dc[slot] = dc; dst->acc[slot] = 1;
                     }
-                } else if (lane == 0) {
-                    atomicAnd(mw, ~bit);                            // morph.cu:1328-1332
                 }
                 TR(12);
             }
             TR(3);
-            // every mask / v / luma update of this sub-phase is ordered before the next filter by this barrier
+            // every v / luma / slot update of this sub-phase is ordered before the commit by this barrier
+            // Nothing to commit and no mask bit to clear (uniform).  A cluster still needs its barrier: the slot buffers
+            // are double-buffered by sub-phase parity and the barrier is what orders their reuse.
+            if (stat_any == 0 && R == 1) { phase++; __syncthreads(); continue; }
             if (R > 1) cluster.sync(); else __syncthreads();
             TR(4);
+            // ---- commit A: improving-mask bits of every pixel that had a mask index: set if accepted, cleared otherwise
+            //      (morph.cu:1320-1332); accepted-slot bitmask rows for the gather below
+            mdirty = true;
+            int any = 0;
+            if (tid < NPIX) {
+                int tx = tid & 31, ty = tid >> 5;
+                int acc = SB.acc[tid];
+                any = acc;
+                unsigned abal = __ballot_sync(0xffffffffu, acc != 0);
+                if (lane == 0) S.accrow[ty] = abal;
+                if (S.status[tid]) {
+                    int px = ox + tx * 2 + sj + 2, py = oy + ty * 2 + si + 2;
+                    int bx = px / 5, by = py / 5;
+                    unsigned bit = 1u << ((px - bx * 5) + (py - by * 5) * 5);
+                    unsigned *mw = &S.mask[(by + 1 - mcy0) * MASK_W + (bx + 1 - mcx0)];
+                    if (acc) atomicOr(mw, bit); else atomicAnd(mw, ~bit);
+                }
+            }
             // ---- commit B: deterministic gather of the SSIM-sum and TPS deltas into the replica, then UpdateSSIM
             //      (morph.cu:973-987,1006-1015,1258-1279).  Contributors in row-major order of the source pixel.
-            int any = (tid < NPIX) ? (int)SB.acc[tid] : 0;
             if (__syncthreads_or(any)) {
                 dirty = true;
-                for (int c = tid; c < TCELLS; c += NT) {
-                    int sy = c / TW, sx = c - sy * TW;
-                    float2 m = S.mean[c], vr = S.var[c], tb = S.tpsb[c];
-                    float cr = S.cross[c];
-                    bool ch_s = false, ch_t = false;
+                for (int cc = tid; cc < rcells; cc += NT) {
+                    int ry = cc / rw, sy = ry0 + ry, sx = rx0 + (cc - ry * rw);
+                    int c = sy * TW + sx;
                     // contributors sit on the stride-2 lattice of this colour: at most 3 x 3 of them reach a cell.
                     // Visited in row-major order of the source pixel (dy, dx ascending), like the oracle.
                     const int ty0 = sy - si - 4, tx0 = sx - sj - 4;          // t = sy + dy - si - 2 with dy = -2
                     const int dyb = (ty0 & 1) ? -1 : -2, dxb = (tx0 & 1) ? -1 : -2;
+                    const int tyb = (sy + dyb - si - 2) >> 1, txb = (sx + dxb - sj - 2) >> 1;   // lattice coords of the first candidate (may be < 0)
+                    // accepted candidates as a 3x3 bit pattern without touching the slot data
+                    unsigned cand = 0;
 #pragma unroll
                     for (int ky = 0; ky < 3; ky++) {
-                        int dy = dyb + 2 * ky;
-                        int t = sy + dy - si - 2;
-                        if (dy > 2 || t < 0 || (t >> 1) >= OPT_BH) continue;
+                        int ty = tyb + ky;
+                        unsigned row = (ty >= 0 && ty < OPT_BH && dyb + 2 * ky <= 2) ? S.accrow[ty] : 0u;
 #pragma unroll
                         for (int kx = 0; kx < 3; kx++) {
-                            int dx = dxb + 2 * kx;
-                            int s2 = sx + dx - sj - 2;
-                            if (dx > 2 || s2 < 0 || (s2 >> 1) >= OPT_BW) continue;
-                            int slot = (t >> 1) * OPT_BW + (s2 >> 1);
-                            if (!SB.acc[slot]) continue;
+                            int tx = txb + kx;
+                            if (tx >= 0 && tx < OPT_BW && dxb + 2 * kx <= 2 && ((row >> tx) & 1u)) cand |= 1u << (ky * 3 + kx);
+                        }
+                    }
+                    if (!cand) continue;
+                    float2 m = S.mean[c], vr = S.var[c], tb = S.tpsb[c];
+                    float cr = S.cross[c];
+                    bool ch_s = false, ch_t = false;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                        for (int kx = 0; kx < 3; kx++) {
+                            if (!((cand >> (ky * 3 + kx)) & 1u)) continue;
+                            int dy = dyb + 2 * ky, dx = dxb + 2 * kx;
+                            int slot = (tyb + ky) * OPT_BW + (txb + kx);
                             int B = S.bcls[slot];
                             int k = (2 - dy) * 5 + (2 - dx);
                             if ((S.iomask[B] >> k) & 1u) {
@@ -535,7 +570,6 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                             float T = S.tps[B * 25 + k];
                             if (T != 0.0f) { float2 d = SB.d[slot]; tb.x += d.x * T; tb.y += d.y * T; ch_t = true; }
                         }
-                    }
                     if (ch_s) {
                         S.mean[c] = m; S.var[c] = vr; S.cross[c] = cr;
                         S.value[c] = ssim_value_fast(m, vr, cr, S.cnt[c], P.ssim_clamp);
@@ -550,18 +584,24 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             TR(5);
         }
     // --- SaveSSIM (morph.cu:1236-1256) + tps.b, only when something was committed; replicas are identical, rank 0 stores
-    if (dirty) {
-        if (rank == 0)
-            for (int c = tid; c < TCELLS; c += NT) {
-                int sy = c / TW, sx = c - sy * TW;
-                int x = ox + sx, y = oy + sy;
-                if (x >= 0 && x < L.w && y >= 0 && y < L.h) {
-                    size_t i = (size_t)y * L.rs + x + poff;
-                    L.mean[i] = S.mean[c]; L.var[i] = S.var[c]; L.cross[i] = S.cross[c]; L.value[i] = S.value[c]; L.tps_b[i] = S.tpsb[c];
-                }
+    if (rank == 0) {
+        if (dirty)
+            for (int cc = tid; cc < rcells; cc += NT) {
+                int ry = cc / rw, sy = ry0 + ry, sx = rx0 + (cc - ry * rw);
+                int c = sy * TW + sx;
+                size_t i = (size_t)(oy + sy) * L.rs + (ox + sx) + poff;
+                L.mean[i] = S.mean[c]; L.var[i] = S.var[c]; L.cross[i] = S.cross[c]; L.value[i] = S.value[c]; L.tps_b[i] = S.tpsb[c];
             }
-        if (tid == 0) S.cta_improving = 1;
+        // own mask words (cells that contain a pixel of this tile's lattice); the apron words are read-only
+        if (mdirty && tid < MASK_W * MASK_H) {
+            int my = tid / MASK_W, mx = tid - my * MASK_W;
+            int cx = mcx0 + mx, cy = mcy0 + my;
+            int ocx0 = (ox + 2) / 5 + 1, ocx1 = min(ox + 2 * OPT_BW + 1, L.w - 1) / 5 + 1;
+            int ocy0 = (oy + 2) / 5 + 1, ocy1 = min(oy + 2 * OPT_BH + 1, L.h - 1) / 5 + 1;
+            if (cx >= ocx0 && cx <= ocx1 && cy >= ocy0 && cy <= ocy1) gmask[cy * L.irs + cx] = S.mask[tid];
+        }
     }
+    if (dirty && tid == 0) S.cta_improving = 1;
     __syncthreads();
     TR(6);
 }
