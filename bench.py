@@ -249,13 +249,21 @@ def run_ours(args):
     sweep_ms, sweep_n = sw1 - sw0, nl1 - nl0
 
     # ---------------- end-to-end steps through the host-buffer API: e2e
+    e2e_parts = [0.0, 0.0, 0.0]
+
     def e2e_step():
+        t0 = time.perf_counter()
         build()                                                                 # H2D of the RGB frames + GPU pyramid
+        t1 = time.perf_counter()
         _lib.check(L.vm_morph_run(m.h, sh))
+        t2 = time.perf_counter()
         _lib.check(L.vm_morph_get_vectors(m.h, C.c_void_p(out_pin.data_ptr()), sh))   # D2H of the result
+        t3 = time.perf_counter()
+        e2e_parts[0] += t1 - t0; e2e_parts[1] += t2 - t1; e2e_parts[2] += t3 - t2
     for _ in range(min(args.warmup, 3)):
         e2e_step()
     px_e0 = m.executed_pixel_iters
+    e2e_parts[:] = [0.0, 0.0, 0.0]
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -298,6 +306,7 @@ def run_ours(args):
                           "timing": "CUDA events on the launching stream, one pair per step, summed; max over ranks"},
                "e2e": {"value": px_e_all / e2e_max / 1e6, "unit": "Mpixel-iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": 1e3 * e2e_max / args.steps,
+                       "ms_build_run_extract": [1e3 * v / args.steps for v in e2e_parts],
                        "path": "vm_pyramid_build(host RGB8, pinned) -> vm_morph_run -> vm_morph_get_vectors(host), wall clock"},
                "gpu_launches": int(launches_all),
                "clocks": clocks,

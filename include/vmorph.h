@@ -168,6 +168,9 @@ int vm_render_halfway(int device, uint8_t *out, int w, int h, int ex, float colo
 /* ---- QuadraticPath (QuadraticPath.h:10-14, QuadraticPath.cpp:24-318) ---- */
 /* one frame: vector (w*h float2, host) -> qpath (w*h float2, host). max_iter=10000, tol=1e-12 reproduce the reference */
 int vm_qpath_optimize(int device, const float *vector, float *qpath, int w, int h, int max_iter, float tol, int *iters_out, void *stream);
+/* CQuadraticPath::optimize over all d frames (the z loop of QuadraticPath.cpp:27): vectors / qpaths = d*h*w float2 (host),
+ * iters_out = 2 ints per frame (CG iterations of the x and y systems).  Frames are independent and run concurrently. */
+int vm_qpath_optimize_frames(int device, const float *vectors, float *qpaths, int w, int h, int d, int max_iter, float tol, int *iters_out, void *stream);
 
 /* Diagnostics (no reference counterpart): the sweep kernel evaluates SSIM with branch-free division / square root
  * sequences that must equal IEEE round-to-nearest bit for bit.  Compares them with the compiler's div.rn / sqrt.rn on

@@ -32,6 +32,9 @@
 //      sequence of IEEE double operations (pow_mode=1, default) that the CUDA path
 //      reproduces exactly; pow_mode=0 calls libm powf like the compiled reference.
 //      The modes agree to ~1 float ulp.
+//  D6  cublasSdot (QuadraticPath.cpp:282-306) has no specified summation order; the
+//      conjugate-gradient dots use a fixed lane / tree order (vmo_render.cpp qp_dot) that the
+//      CUDA path reproduces exactly.
 //  D4  cv::Mat::inv (OpenCV 3.0, not vendored) is restated as f64 Gaussian
 //      elimination with partial pivoting; singular => conjugate-gradient
 //      minimum-norm solution (the pseudo-inverse the reference falls back to).

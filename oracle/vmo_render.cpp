@@ -71,12 +71,32 @@ void render_halfway(uint8_t *out, int rowstride, int w, int h, int ex, float col
 }
 
 // QuadraticPath.cpp:225-318 restated matrix-free on the 5-point operator assembled at 134-202.
-// Dots are accumulated in f64 and rounded to f32 (cublasSdot's internal order is unspecified).
+// D6 (vmo.h): cublasSdot's internal summation order is unspecified.  Here a dot product is DEFINED as: QP_LANES = 32768
+// lanes, lane t sums the exact products a[i]*b[i] of the elements i = t, t+QP_LANES, ... sequentially in f64; each group
+// of 256 consecutive lanes is reduced by a binary tree (stride 128, 64, ..., 1); the 128 group sums are added
+// sequentially; the result is rounded to f32.  The CUDA path uses the same order, so both are bit-identical.
+static const int QP_LANES = 32768, QP_GROUP = 256;
+static float qp_dot(const float *a, const float *b, int N) {
+    std::vector<double> lane(QP_LANES, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < QP_LANES; t++) {
+        double s = 0;
+        for (int i = t; i < N; i += QP_LANES) s += (double)a[i] * (double)b[i];
+        lane[t] = s;
+    }
+    double total = 0;
+    for (int g = 0; g < QP_LANES / QP_GROUP; g++) {
+        double *sh = lane.data() + (size_t)g * QP_GROUP;
+        for (int off = QP_GROUP / 2; off > 0; off >>= 1)
+            for (int t = 0; t < off; t++) sh[t] += sh[t + off];
+        total += sh[0];
+    }
+    return (float)total;
+}
 static int cg_solve(int cols, int rows, const std::vector<float> &B, std::vector<float> &X, int max_iter, float tol) {
     int N = cols * rows;
     std::vector<float> r(B), p(N, 0.0f), om(N, 0.0f);
-    auto dot = [&](const std::vector<float> &a, const std::vector<float> &b) {
-        double s = 0; for (int i = 0; i < N; i++) s += (double)a[i] * b[i]; return (float)s; };
+    auto dot = [&](const std::vector<float> &a, const std::vector<float> &b) { return qp_dot(a.data(), b.data(), N); };
     auto spmv = [&](const std::vector<float> &in, std::vector<float> &out) {
 #pragma omp parallel for schedule(static)
         for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) {

@@ -258,3 +258,25 @@ def test_end_to_end_from_rgb(vm, oracle_lib):
     m.run()
     np.testing.assert_array_equal(m.iters_log(), o.iters_log())
     _assert_vec(m.get_vectors(), o.extract_vectors(), "end-to-end vectors")
+
+
+@pytest.mark.parametrize("w,h,max_iter", [(31, 24, 300), (150, 91, 500), (64, 64, 10000)])
+def test_qpath_parity(vm, oracle_lib, w, h, max_iter):
+    # CQuadraticPath::optimize: Jacobian blend + two CG solves; fixed dot-product order (oracle D6) -> bit-equal, same iteration counts
+    from videomorphing_b200 import api
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    rng = np.random.Generator(np.random.PCG64(w * 7 + h))
+    v = np.stack([2 * np.sin(xx / 7) * np.cos(yy / 5), 1.5 * np.cos(xx / 6 + yy / 9)], -1).astype(np.float32)
+    v += (rng.standard_normal(v.shape) * 0.01).astype(np.float32)
+    qo, ito = oracle_lib.qpath_optimize(v, max_iter, 1e-12)
+    qg, itg = api.quadratic_path(v, max_iter, 1e-12)
+    assert list(itg) == list(ito)
+    assert float(np.abs(qg - qo).max()) <= 1e-3                       # stated float tolerance (px)
+    np.testing.assert_array_equal(qg, qo)
+    # batched frames == frame by frame
+    vs = np.stack([v, v[::-1].copy(), v * np.float32(0.5)])
+    qb, itb = api.quadratic_path_frames(vs, min(max_iter, 300), 1e-12)
+    for z in range(3):
+        q1, it1 = api.quadratic_path(vs[z], min(max_iter, 300), 1e-12)
+        np.testing.assert_array_equal(qb[z], q1)
+        assert list(itb[z]) == list(it1)

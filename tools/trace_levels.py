@@ -31,6 +31,7 @@ for rep in range(2):
         if rep == 1:
             tot = sum(buf[k] for k in (0, 1, 2, 3, 4, 5, 6, 7))
             print(f"level {l} {i['w']}x{i['h']} iters={it}: CTA0/thread0 cycles total {tot/1e6:.1f} M")
+            print(f"   tile steps executed {buf[13]} skipped {buf[14]}; active pixels per executed sub-phase {buf[15] / max(1, buf[31]):.1f}")
             for k in range(13):
                 if buf[16 + k]:
                     print(f"   {NAMES[k]:32s} {buf[k]/1e6:9.2f} Mcyc  n={buf[16+k]:8d}  avg={buf[k]/buf[16+k]:9.0f}")

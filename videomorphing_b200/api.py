@@ -160,6 +160,26 @@ class Morph:
         self._keep = (a, b)
         check(self.L.vm_morph_set_constraints(self.h, len(a), a, b))
 
+    def set_tracks(self, lp, rp, cnt):
+        """Parameters::lp / rp / cnt (parameters.h:45-47) in the reference's ragged layout (see parse_config_xml)."""
+        from ._lib import VmConnect
+        def flat(tracks):
+            lens = (C.c_int32 * max(1, len(tracks)))(*[len(t) for t in tracks])
+            pts = [p for t in tracks for p in t]
+            arr = (VmConp * max(1, len(pts)))()
+            for k, p in enumerate(pts):
+                arr[k] = VmConp(int(p[0]), int(p[1]), int(p[2]), int(p[3]), float(p[4]))
+            return lens, arr
+        ll, la = flat(lp)
+        rl, ra = flat(rp)
+        gl = (C.c_int32 * max(1, len(cnt)))(*[len(g) for g in cnt])
+        cs = [c for g in cnt for c in g]
+        ca = (VmConnect * max(1, len(cs)))()
+        for k, c in enumerate(cs):
+            ca[k] = VmConnect(int(c[0]), int(c[1]), int(c[2]), int(c[3]))
+        self._keep_tracks = (ll, la, rl, ra, gl, ca)
+        check(self.L.vm_morph_set_tracks(self.h, len(lp), ll, la, len(rp), rl, ra, len(cnt), gl, ca))
+
     def calculate_halfway_parametrization(self, stream=None):
         check(self.L.vm_morph_run(self.h, stream))
         return True
@@ -231,6 +251,43 @@ def render_halfway_image(w, h, ex, color_fa, geo_fa, color_from, ext0, ext1, vec
     check(_lib.load().vm_render_halfway(device, _vp(out), w, h, ex, float(color_fa), float(geo_fa), int(color_from),
                                         _vp(ext0), _vp(ext1), _vp(vector), _vp(qp), stream))
     return out
+
+
+def parse_config_xml(path):
+    """parse_config_xml (param_io.h:8) for the live settings.xml schema (UI/MdiEditor.cpp:566-749): returns Parameters with
+    lp / rp as lists of tracks of (x, y, frame, keyflag, weight) and cnt as lists of groups of (li_track, li_idx, ri_track, ri_idx)."""
+    from ._lib import VmTracks
+    L = _lib.load()
+    prm = Parameters()
+    tr = VmTracks()
+    check(L.vm_params_parse_xml(str(path).encode(), C.byref(prm._p), C.byref(tr)))
+    try:
+        def tracks(n, lens, pts):
+            out, o = [], 0
+            for i in range(n):
+                out.append([(pts[o + j].x, pts[o + j].y, pts[o + j].z, pts[o + j].w, pts[o + j].weight) for j in range(lens[i])])
+                o += lens[i]
+            return out
+        prm.lp = tracks(tr.n_left, tr.left_len, tr.left)
+        prm.rp = tracks(tr.n_right, tr.right_len, tr.right)
+        prm.cnt, o = [], 0
+        for i in range(tr.n_groups):
+            prm.cnt.append([(tr.connects[o + j].li_track, tr.connects[o + j].li_idx, tr.connects[o + j].ri_track, tr.connects[o + j].ri_idx)
+                            for j in range(tr.group_len[i])])
+            o += tr.group_len[i]
+    finally:
+        L.vm_tracks_free(C.byref(tr))
+    return prm
+
+
+def quadratic_path_frames(vectors, max_iter=10000, tol=1e-12, device=0, stream=None):
+    """CQuadraticPath::optimize over all frames: vectors (d,h,w,2) -> qpath (d,h,w,2), iterations (d,2)."""
+    vectors = np.ascontiguousarray(vectors, np.float32)
+    d, h, w, _ = vectors.shape
+    out = np.zeros_like(vectors)
+    it = np.zeros((d, 2), np.int32)
+    check(_lib.load().vm_qpath_optimize_frames(device, _vp(vectors), _vp(out), w, h, d, max_iter, tol, _vp(it), stream))
+    return out, it
 
 
 def quadratic_path(vector, max_iter=10000, tol=1e-12, device=0, stream=None):

@@ -365,8 +365,16 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             for (int r = 0; r < 5; r++) if (pcy * 5 + r >= ey0 && pcy * 5 + r <= ey1) m |= xm << (5 * r);
             any = (pcx >= 0 && pcy >= 0 && (word & m) != 0u);
         }
-        if (!__syncthreads_or(any)) return;
+        if (!__syncthreads_or(any)) {
+#ifdef VM_TRACE
+            if (threadIdx.x == 0 && rank == 0) atomicAdd(&g_trace[14], 1ull);      // tile steps skipped
+#endif
+            return;
+        }
     }
+#ifdef VM_TRACE
+    if (threadIdx.x == 0 && rank == 0) atomicAdd(&g_trace[13], 1ull);              // tile steps executed
+#endif
     TR(0);
     // --- LoadSSIM (morph.cu:1214-1234) + counter + tps.b into this CTA's replica; cells outside the image are zero
     // tile-local rectangle of cells that lie inside the image
@@ -430,6 +438,9 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             }
             if (qn > 0) __syncthreads();
             TR(2);
+#ifdef VM_TRACE
+            if (threadIdx.x == 0 && rank == 0) { atomicAdd(&g_trace[15], (unsigned long long)qn); atomicAdd(&g_trace[31], 1ull); }   // active pixels / sub-phases
+#endif
             // speculative line search only while the SM has issue slots to spare (at most ~1.5 busy warps per scheduler);
             // qn, R are the same in every CTA of the cluster, so the choice is uniform (and does not change results)
             const bool spec = LAT && qn <= 6 * R;
