@@ -182,14 +182,12 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from videomorphing_b200 import dist as vd
+    rank, local, world = vd.env_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    vd.init("nccl", device_id=local)                      # one process per GPU; no-op for a single rank
 
     import videomorphing_b200 as vm
     from videomorphing_b200 import _lib, synth

@@ -1,0 +1,60 @@
+"""Headless video morph on one GPU: Pyramid::build -> Morph -> QuadraticPath (optional) -> render of every frame.
+BASELINE.json configs[3]-style workload (synthetic video pair with analytic flows); prints one JSON line.
+
+    python tools/video_bench.py [--w 1280 --h 720 --d 120] [--cap 14000000|0 (0 = lifted)] [--qpath] [--cpu-frames N]
+"""
+import argparse, json, os, sys, time, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--w", type=int, default=1280); ap.add_argument("--h", type=int, default=720); ap.add_argument("--d", type=int, default=120)
+    ap.add_argument("--cap", type=int, default=0, help="voxel cap (pyramid.cu:8 uses 14000000); 0 = lifted")
+    ap.add_argument("--max-iter", type=int, default=1000)
+    ap.add_argument("--qpath", action="store_true"); ap.add_argument("--qpath-iter", type=int, default=10000)
+    ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--device", type=int, default=0)
+    args = ap.parse_args()
+    import videomorphing_b200 as vm
+    from videomorphing_b200 import synth, api
+    cap = args.cap if args.cap > 0 else (1 << 62)
+    t = time.time()
+    v0, v1, flows, field = synth.video_pair(args.w, args.h, args.d, 4001, 4002, 8.0)
+    t_synth = time.time() - t
+    L = vm._lib.load()
+    pyr = vm.Pyramid(args.device)
+    out = {}
+    for rep in range(args.reps):
+        t = time.perf_counter(); n = pyr.build(v0, v1, flows, voxel_cap=cap); t_build = time.perf_counter() - t
+        m = vm.Morph(vm.Parameters(max_iter=args.max_iter), pyr)
+        px0 = m.executed_pixel_iters
+        t = time.perf_counter(); m.run(); t_run = time.perf_counter() - t
+        px = m.executed_pixel_iters - px0
+        t = time.perf_counter(); vec = m.get_vectors(); t_extract = time.perf_counter() - t
+        sw_ms, sw_n = m.sweep_time_ms()
+        levels = [(pyr.info(l)["w"], pyr.info(l)["h"], pyr.info(l)["d"]) for l in range(n)]
+        qp = None; t_qpath = None; qit = None
+        if args.qpath:
+            t = time.perf_counter(); qp, qit = api.quadratic_path_frames(vec, args.qpath_iter, 1e-12, device=args.device); t_qpath = time.perf_counter() - t
+        ex = int(max(args.w, args.h) * 0.1)
+        t = time.perf_counter()
+        for z in range(args.d):
+            fa = float(synth.smoothstep(z / max(1, args.d - 1)))
+            e0, e1 = synth.extended_rgba(v0[z], ex), synth.extended_rgba(v1[z], ex)
+            img = vm.render_halfway_image(args.w, args.h, ex, fa, fa, 1, e0, e1, vec[z], None if qp is None else qp[z], device=args.device)
+        t_render = time.perf_counter() - t
+        err = np.abs(vec - field[None] / 2)
+        out = {"workload": f"{args.w}x{args.h}x{args.d} video pair, voxel cap {'lifted' if args.cap <= 0 else args.cap}", "levels": levels,
+               "chains": os.environ.get("VMORPH_CHAINS", "2"), "synth_s": t_synth, "build_s": t_build, "optimize_s": t_run, "extract_s": t_extract,
+               "qpath_s": t_qpath, "render_host_buffers_s": t_render, "pixel_iters": px, "mpixel_iters_per_s": px / t_run / 1e6,
+               "frames_per_s_optimize_plus_render": args.d / (t_run + t_render), "sweep_launches": sw_n, "sweep_ms_sum": sw_ms,
+               "mean_abs_err_vs_true_halfway_px": float(err.mean()), "qpath_iters_first": None if qit is None else qit[0].tolist(),
+               "launches": int(L.vm_kernel_launch_count())}
+        print(json.dumps(out), flush=True)
+        m.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -233,6 +233,7 @@ int vm_pyramid_alloc(vm_pyramid *p, int w, int h, int d, int start_res, int64_t 
     VM_CUDA(p->tps_axy.ensure(4 * max_state)); VM_CUDA(p->ui_axy.ensure(4 * max_state)); VM_CUDA(p->temp_mask.ensure(4 * max_state));
     VM_CUDA(p->impmask.ensure(4 * max_imp));
     VM_CUDA(p->tmp_a.ensure(sizeof(long long) * 3 * max_ps)); VM_CUDA(p->tmp_b.ensure(sizeof(float2) * max_ps)); VM_CUDA(p->tmp_c.ensure(sizeof(float) * max_ps));
+    if (d > 2) VM_CUDA(p->tmp_a2.ensure(sizeof(long long) * 3 * max_ps));
     return (int)s.size();
 }
 
@@ -318,6 +319,9 @@ int vm_morph_create(const vm_params *prm, vm_pyramid *pyr, volatile int *run_fla
     cudaError_t e = cudaHostAlloc((void **)&m->progress_host, 64, cudaHostAllocMapped);
     if (e == cudaSuccess) { m->progress_host[0] = 0; e = cudaHostGetDevicePointer((void **)&m->progress_dev, m->progress_host, 0); }
     if (e == cudaSuccess) e = m->ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(prm->max_iter + 1));
+    if (e == cudaSuccess) e = m->ctrl2.ensure(sizeof(unsigned) * sweep_ctrl_words(prm->max_iter + 1));
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaStreamCreateWithFlags(&m->chain_stream[k], cudaStreamNonBlocking);
+    for (int k = 0; k < 3 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&m->chain_ev[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { vm_morph_destroy(m); return cuda_fail(e, "morph_create"); }
     // morph.cu:128-140
     m->total_l = (int)pyr->lv.size() - 1;
@@ -336,6 +340,8 @@ void vm_morph_destroy(vm_morph *m) {
     if (m->run_flag_registered) cudaHostUnregister((void *)m->run_flag);
     if (m->progress_host) cudaFreeHost(m->progress_host);
     for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
+    for (int k = 0; k < 2; k++) if (m->chain_stream[k]) cudaStreamDestroy(m->chain_stream[k]);
+    for (int k = 0; k < 3; k++) if (m->chain_ev[k]) cudaEventDestroy(m->chain_ev[k]);
     delete m;
 }
 
@@ -443,7 +449,9 @@ int vm_level_initialize(vm_morph *m, int level, void *stream) {
     return VM_OK;
 }
 
-int vm_level_init_temp(vm_morph *m, int level, int frame, int dir, void *stream) {
+static int init_temp_chain(vm_morph *m, int level, int frame, int dir, cudaStream_t s, int chain);
+int vm_level_init_temp(vm_morph *m, int level, int frame, int dir, void *stream) { return init_temp_chain(m, level, frame, dir, (cudaStream_t)stream, 0); }
+static int init_temp_chain(vm_morph *m, int level, int frame, int dir, cudaStream_t stream, int chain) {
     if (!m) { set_error("null morph"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
     if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
@@ -451,13 +459,14 @@ int vm_level_init_temp(vm_morph *m, int level, int frame, int dir, void *stream)
     if ((dir != 1 && dir != -1) || frame < 0 || frame >= L.d || frame + dir < 0 || frame + dir >= L.d) { set_error("bad frame/dir %d/%d", frame, dir); return VM_ERR_ARG; }
     if (!L.f0.p) { set_error("level %d has no optical flows", level); return VM_ERR_STATE; }
     int rc = use_device(p->device); if (rc) return rc;
-    VM_CUDA(p->tmp_a.ensure(sizeof(long long) * 3 * (size_t)L.ps));
-    VM_CUDA(launch_initialize_temp(make_view(p, level), frame, dir, p->tmp_a.as<long long>(), s));
+    DevBuf &acc = chain ? p->tmp_a2 : p->tmp_a;
+    if (acc.bytes < sizeof(long long) * 3 * (size_t)L.ps) { VM_CUDA(cudaDeviceSynchronize()); VM_CUDA(acc.ensure(sizeof(long long) * 3 * (size_t)L.ps)); }
+    VM_CUDA(launch_initialize_temp(make_view(p, level), frame, dir, acc.as<long long>(), s));
     return VM_OK;
 }
 
 // enqueue one frame's optimisation; iterations land in log_dev[seq]
-static int enqueue_frame(vm_morph *m, int level, int frame, int flag, float max_iter, cudaStream_t s, int *seq_out) {
+static int enqueue_frame(vm_morph *m, int level, int frame, int flag, float max_iter, cudaStream_t s, int *seq_out, int chain = 0, int sm_budget = 0) {
     vm_pyramid *p = m->pyr;
     Level &L = p->lv[level];
     int seq = (int)m->seqs.size();
@@ -465,21 +474,22 @@ static int enqueue_frame(vm_morph *m, int level, int frame, int flag, float max_
     size_t need = sizeof(unsigned) * (size_t)(seq + 1024);
     if (m->log_dev.bytes < need) {
         DevBuf nb; VM_CUDA(nb.ensure(need * 2));
-        VM_CUDA(cudaStreamSynchronize(s));
+        VM_CUDA(cudaDeviceSynchronize());
         if (m->log_dev.p) VM_CUDA(cudaMemcpy(nb.p, m->log_dev.p, m->log_dev.bytes, cudaMemcpyDeviceToDevice));
         std::swap(nb.p, m->log_dev.p); std::swap(nb.bytes, m->log_dev.bytes);
     }
     int iters_cap = (int)ceilf(max_iter) + 1;
     if (iters_cap < 1) iters_cap = 1;
-    VM_CUDA(m->ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(iters_cap)));
-    VM_CUDA(cudaMemsetAsync(m->ctrl.p, 0, sizeof(unsigned) * sweep_ctrl_words(iters_cap), s));
+    DevBuf &ctrl = chain ? m->ctrl2 : m->ctrl;
+    if (ctrl.bytes < sizeof(unsigned) * sweep_ctrl_words(iters_cap)) { VM_CUDA(cudaDeviceSynchronize()); VM_CUDA(ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(iters_cap))); }
+    VM_CUDA(cudaMemsetAsync(ctrl.p, 0, sizeof(unsigned) * sweep_ctrl_words(iters_cap), s));
     m->seqs.push_back({level, frame, (double)L.w * L.h, max_iter});
     while (m->ev.size() < 2 * (size_t)(seq + 1)) { cudaEvent_t e; VM_CUDA(cudaEventCreate(&e)); m->ev.push_back(e); }
     VM_CUDA(cudaEventRecord(m->ev[2 * seq], s));
     VM_CUDA(launch_sweep(make_view(p, level), kparams(m->prm), p->stencils.as<StencilTables>(), frame, flag, max_iter,
-                         m->ctrl.as<unsigned>(), m->run_flag_dev, m->progress_dev, seq, p->sm_count, s));
+                         ctrl.as<unsigned>(), m->run_flag_dev, m->progress_dev, seq, p->sm_count, sm_budget, s));
     VM_CUDA(cudaEventRecord(m->ev[2 * seq + 1], s));
-    VM_CUDA(cudaMemcpyAsync(m->log_dev.as<unsigned>() + seq, m->ctrl.as<unsigned>() + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
+    VM_CUDA(cudaMemcpyAsync(m->log_dev.as<unsigned>() + seq, ctrl.as<unsigned>() + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
     if (seq_out) *seq_out = seq;
     return VM_OK;
 }
@@ -513,20 +523,48 @@ int vm_level_optimize_frame(vm_morph *m, int level, int frame, int flag, float m
     return VM_OK;
 }
 
-// Morph::optimize_level (morph.cu:1353-1441): middle frame, then forward chain, then backward chain.
+// Morph::optimize_level (morph.cu:1353-1441): middle frame, then forward chain (frames mid+1 .. d-1, each seeded from
+// frame i-1), then backward chain (mid-1 .. 0, each seeded from frame i+1).  The two chains only share the middle
+// frame's result, so they are enqueued on two streams and run CONCURRENTLY, each with half of the SMs as its budget
+// (coarse levels occupy a fraction of the GPU anyway).  Same arithmetic, same results as the sequential order; the
+// iteration log keeps the reference's order.  VMORPH_CHAINS=1 forces the sequential schedule (test hook).
 static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s) {
     vm_pyramid *p = m->pyr; Level &L = p->lv[level];
     int mid = L.d / 2, rc;
     rc = enqueue_frame(m, level, mid, 0, max_iter, s, nullptr); if (rc) return rc;
+    const char *ec = getenv("VMORPH_CHAINS");
+    const bool two = L.d > 2 && !(ec && atoi(ec) == 1);
+    cudaStream_t sf = s, sb = s;
+    int budget = 0;
+    if (two) {
+        sf = m->chain_stream[0]; sb = m->chain_stream[1]; budget = p->sm_count / 2;
+        // reserve the launch log up front: growing it needs a device-wide synchronisation
+        size_t need = sizeof(unsigned) * (m->seqs.size() + (size_t)L.d + 1024);
+        if (m->log_dev.bytes < need) {
+            DevBuf nb; VM_CUDA(nb.ensure(need * 2));
+            VM_CUDA(cudaDeviceSynchronize());
+            if (m->log_dev.p) VM_CUDA(cudaMemcpy(nb.p, m->log_dev.p, m->log_dev.bytes, cudaMemcpyDeviceToDevice));
+            std::swap(nb.p, m->log_dev.p); std::swap(nb.bytes, m->log_dev.bytes);
+        }
+        VM_CUDA(cudaEventRecord(m->chain_ev[0], s));
+        VM_CUDA(cudaStreamWaitEvent(sf, m->chain_ev[0], 0));
+        VM_CUDA(cudaStreamWaitEvent(sb, m->chain_ev[0], 0));
+    }
     for (int i = mid + 1; i < L.d; i++) {
         if (!keep_running(m)) break;
-        rc = vm_level_init_temp(m, level, i, -1, s); if (rc) return rc;
-        rc = enqueue_frame(m, level, i, 1, max_iter, s, nullptr); if (rc) return rc;
+        rc = init_temp_chain(m, level, i, -1, sf, 0); if (rc) return rc;
+        rc = enqueue_frame(m, level, i, 1, max_iter, sf, nullptr, 0, budget); if (rc) return rc;
     }
     for (int i = mid - 1; i >= 0; i--) {
         if (!keep_running(m)) break;
-        rc = vm_level_init_temp(m, level, i, 1, s); if (rc) return rc;
-        rc = enqueue_frame(m, level, i, 1, max_iter, s, nullptr); if (rc) return rc;
+        rc = init_temp_chain(m, level, i, 1, sb, two ? 1 : 0); if (rc) return rc;
+        rc = enqueue_frame(m, level, i, 1, max_iter, sb, nullptr, two ? 1 : 0, budget); if (rc) return rc;
+    }
+    if (two) {
+        VM_CUDA(cudaEventRecord(m->chain_ev[1], sf));
+        VM_CUDA(cudaEventRecord(m->chain_ev[2], sb));
+        VM_CUDA(cudaStreamWaitEvent(s, m->chain_ev[1], 0));
+        VM_CUDA(cudaStreamWaitEvent(s, m->chain_ev[2], 0));
     }
     return VM_OK;
 }
@@ -618,7 +656,7 @@ int vm_morph_get_vectors(vm_morph *m, float *host_out, void *stream) {
     int factor = (int)(L0.factor_d / L1.factor_d);
     if (factor != 1) { set_error("level 1 is temporally subsampled (factor %d): unsupported", factor); return VM_ERR_STATE; }
     size_t bytes = sizeof(float2) * (size_t)L0.w * L0.h * L0.d;
-    DevBuf out; VM_CUDA(out.ensure(bytes));
+    DevBuf &out = m->extract_buf; VM_CUDA(out.ensure(bytes));
     VM_CUDA(launch_extract(make_view(p, 1), out.as<float2>(), L0.w, L0.h, L0.d, factor, s));
     VM_CUDA(cudaMemcpyAsync(host_out, out.p, bytes, cudaMemcpyDeviceToHost, s));
     VM_CUDA(cudaStreamSynchronize(s));
@@ -636,23 +674,30 @@ int vm_render_halfway_dev(uint8_t *out_dev, int rowstride, int w, int h, int ex,
     return VM_OK;
 }
 
+// Device staging of the host-buffer renderer, kept per device between calls (the reference allocates and frees four
+// cudaArrays per rendered frame, UI/RenderWidget.cpp:239-264).
+namespace { struct RenderScratch { DevBuf e0, e1, v, q, o; }; RenderScratch g_render[16]; std::mutex g_render_mu; }
+
 int vm_render_halfway(int device, uint8_t *out, int w, int h, int ex, float color_fa, float geo_fa, int color_from,
                       const uint8_t *ext0, const uint8_t *ext1, const float *vector, const float *qpath, void *stream) {
     if (!out || !ext0 || !ext1 || !vector || w <= 0 || h <= 0 || ex < 0) { set_error("bad render arguments"); return VM_ERR_ARG; }
     int rc = use_device(device); if (rc) return rc;
+    if (device >= 16) { set_error("device %d: at most 16 devices", device); return VM_ERR_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     int rowstride = (w + 31) / 32 * 32;                                          // UI/RenderWidget.cpp:235
     size_t eb = (size_t)(w + 2 * ex) * (h + 2 * ex) * 4, vb = sizeof(float2) * (size_t)w * h, ob = (size_t)rowstride * h * 3;
-    DevBuf d_e0, d_e1, d_v, d_q, d_o;
-    VM_CUDA(d_e0.ensure(eb)); VM_CUDA(d_e1.ensure(eb)); VM_CUDA(d_v.ensure(vb)); VM_CUDA(d_o.ensure(ob));
-    VM_CUDA(cudaMemcpyAsync(d_e0.p, ext0, eb, cudaMemcpyHostToDevice, s));
-    VM_CUDA(cudaMemcpyAsync(d_e1.p, ext1, eb, cudaMemcpyHostToDevice, s));
-    VM_CUDA(cudaMemcpyAsync(d_v.p, vector, vb, cudaMemcpyHostToDevice, s));
-    if (qpath) { VM_CUDA(d_q.ensure(vb)); VM_CUDA(cudaMemcpyAsync(d_q.p, qpath, vb, cudaMemcpyHostToDevice, s)); }
-    rc = vm_render_halfway_dev(d_o.as<uint8_t>(), rowstride, w, h, ex, color_fa, geo_fa, color_from, d_e0.as<uint8_t>(), d_e1.as<uint8_t>(),
-                               d_v.as<float>(), qpath ? d_q.as<float>() : nullptr, stream);
+    std::lock_guard<std::mutex> lock(g_render_mu);
+    RenderScratch &R = g_render[device];
+    if (R.e0.bytes < eb || R.e1.bytes < eb || R.v.bytes < vb || R.o.bytes < ob || (qpath && R.q.bytes < vb)) VM_CUDA(cudaDeviceSynchronize());
+    VM_CUDA(R.e0.ensure(eb)); VM_CUDA(R.e1.ensure(eb)); VM_CUDA(R.v.ensure(vb)); VM_CUDA(R.o.ensure(ob));
+    VM_CUDA(cudaMemcpyAsync(R.e0.p, ext0, eb, cudaMemcpyHostToDevice, s));
+    VM_CUDA(cudaMemcpyAsync(R.e1.p, ext1, eb, cudaMemcpyHostToDevice, s));
+    VM_CUDA(cudaMemcpyAsync(R.v.p, vector, vb, cudaMemcpyHostToDevice, s));
+    if (qpath) { VM_CUDA(R.q.ensure(vb)); VM_CUDA(cudaMemcpyAsync(R.q.p, qpath, vb, cudaMemcpyHostToDevice, s)); }
+    rc = vm_render_halfway_dev(R.o.as<uint8_t>(), rowstride, w, h, ex, color_fa, geo_fa, color_from, R.e0.as<uint8_t>(), R.e1.as<uint8_t>(),
+                               R.v.as<float>(), qpath ? R.q.as<float>() : nullptr, stream);
     if (rc) return rc;
-    VM_CUDA(cudaMemcpy2DAsync(out, (size_t)w * 3, d_o.p, (size_t)rowstride * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s));   // RenderWidget.cpp:258
+    VM_CUDA(cudaMemcpy2DAsync(out, (size_t)w * 3, R.o.p, (size_t)rowstride * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s));   // RenderWidget.cpp:258
     VM_CUDA(cudaStreamSynchronize(s));
     return VM_OK;
 }

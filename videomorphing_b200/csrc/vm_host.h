@@ -74,6 +74,7 @@ struct vm_pyramid {
     int state_level = -1;                 // which level the arena currently describes
     vm::DevBuf stencils;                  // StencilTables on the device
     vm::DevBuf tmp_a, tmp_b, tmp_c;       // transient scratch (splat accumulators, coarse solve, resampler planes)
+    vm::DevBuf tmp_a2;                    // splat accumulators of the second (backward) frame chain
     vm::HostStencils hst;
     int a_start_res = 0; int64_t a_cap = 0;   // arguments of the last vm_pyramid_alloc (identical re-allocations are no-ops)
     void *resample_cache = nullptr;       // vm::ResampleCache (vm_resample.cu): filter tables, prefilter factors, transient planes
@@ -90,6 +91,9 @@ struct vm_morph {
     std::vector<vm::Conn> cons;
     vm::DevBuf cons_dev;
     vm::DevBuf ctrl;                      // sweep control block
+    vm::DevBuf ctrl2;                     // control block of the backward frame chain (runs concurrently with the forward chain)
+    cudaStream_t chain_stream[2] = {nullptr, nullptr};
+    cudaEvent_t chain_ev[3] = {nullptr, nullptr, nullptr};
     vm::DevBuf log_dev;                   // iterations executed per sweep launch (one word per launch)
     // launch table for progress reporting: seq -> (level, frame, w*h, max_iter)
     struct Seq { int level, frame; double wh; float max_iter; };
@@ -103,6 +107,7 @@ struct vm_morph {
     bool cancelled = false;
     // device time of the sweep launches (CUDA events on the launching stream around every k_sweep launch)
     std::vector<cudaEvent_t> ev;          // 2 per launch: ev[2*seq], ev[2*seq+1]
+    vm::DevBuf extract_buf;               // level-0 sized vector field staged for vm_morph_get_vectors (kept between calls)
     double sweep_ms = 0;                  // accumulated by collect_log
     uint64_t sweep_launches = 0;
 };
@@ -114,7 +119,7 @@ void free_resample_cache(vm_pyramid *p);
 
 // kernels (launchers) -- vm_kernels.cu / vm_sweep.cu / vm_render.cu / vm_resample.cu
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
-                         unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, cudaStream_t stream);
+                         unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, int sm_budget, cudaStream_t stream);
 size_t sweep_ctrl_words(int max_iter_ceil);
 
 cudaError_t launch_initialize_level(const LevelView &L, const StencilTables *st, float ssim_clamp, cudaStream_t s);

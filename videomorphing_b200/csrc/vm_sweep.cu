@@ -683,7 +683,7 @@ static SweepCfg g_cfg[3];
 template <int NW, bool LAT>
 static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag,
                                   float max_iter, unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq,
-                                  int ntiles, int sm_count, cudaStream_t stream, int slot, int want_r) {
+                                  int ntiles, int sm_count, int sm_budget, cudaStream_t stream, int slot, int want_r) {
     size_t smem = sizeof(SweepSmem);
     auto kern = k_sweep<NW, LAT>;
     SweepCfg &cfg = g_cfg[slot];
@@ -709,11 +709,14 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
         }
         cfg.init = true;
     }
-    // cluster size: the largest power of two <= want_r for which one cluster per tile is co-resident
+    // cluster size: the largest power of two <= want_r for which one cluster per tile is co-resident within the SM
+    // budget of this launch (sm_budget < sm_count when two frame chains share the GPU)
+    auto cap = [&](int c) { int by_budget = (cfg.max_clusters[0] / sm_count) * sm_budget >> c; return cfg.max_clusters[c] < by_budget ? cfg.max_clusters[c] : by_budget; };
     int lg = 0;
-    for (int c = 4; c >= 1; c--) if ((1 << c) <= want_r && cfg.max_clusters[c] >= ntiles) { lg = c; break; }
+    for (int c = 4; c >= 1; c--) if ((1 << c) <= want_r && cap(c) >= ntiles) { lg = c; break; }
     int R = 1 << lg;
-    int nclusters = ntiles < cfg.max_clusters[lg] ? ntiles : cfg.max_clusters[lg];
+    int nclusters = ntiles < cap(lg) ? ntiles : cap(lg);
+    if (nclusters < 1) nclusters = 1;
     LevelView Lc = L; KParams Pc = P;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(nclusters * R); lc.blockDim = dim3(NW * 32); lc.dynamicSmemBytes = smem; lc.stream = stream;
@@ -740,17 +743,18 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
 //   thr16 16 warps, 2 CTAs / SM;  thr8  8 warps, 3 CTAs / SM: sequential line search, for levels with many tiles.
 // Test hooks (read on every launch): VMORPH_CLUSTER=1/2/4/8 caps the cluster size, VMORPH_VARIANT=lat|thr16|thr8.
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
-                         unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, cudaStream_t stream) {
+                         unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, int sm_budget, cudaStream_t stream) {
     const int gx = (L.w + OPT_BW * 2 + SPACING - 1) / (OPT_BW * 2 + SPACING);
     const int gy = (L.h + OPT_BH * 2 + SPACING - 1) / (OPT_BH * 2 + SPACING);
     const int ntiles = gx * gy;
     const char *ec = getenv("VMORPH_CLUSTER"), *ev = getenv("VMORPH_VARIANT");
     int want_r = (ec && atoi(ec) > 0) ? atoi(ec) : 16;
-    int variant = (ntiles <= sm_count) ? 0 : (ntiles <= 2 * sm_count ? 1 : 2);
+    if (sm_budget <= 0 || sm_budget > sm_count) sm_budget = sm_count;
+    int variant = (ntiles <= sm_budget) ? 0 : (ntiles <= 2 * sm_budget ? 1 : 2);
     if (ev) variant = !strcmp(ev, "lat") ? 0 : (!strcmp(ev, "thr16") ? 1 : (!strcmp(ev, "thr8") ? 2 : variant));
-    if (variant == 0) return launch_sweep_t<16, true>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 0, want_r);
-    if (variant == 1) return launch_sweep_t<16, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 1, want_r);
-    return launch_sweep_t<8, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, stream, 2, want_r);
+    if (variant == 0) return launch_sweep_t<16, true>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 0, want_r);
+    if (variant == 1) return launch_sweep_t<16, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 1, want_r);
+    return launch_sweep_t<8, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 2, want_r);
 }
 
 size_t sweep_ctrl_words(int max_iter_ceil) { return 8 + (size_t)max_iter_ceil + 8; }

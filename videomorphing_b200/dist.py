@@ -1,0 +1,98 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+
+What shards on this path:
+  * image pairs (configs 1-3) do not shard: N GPUs = N independent replicas, no data-path collective;
+  * the frame-parallel stages of a video (pyramid image levels, render, QuadraticPath) split into contiguous frame
+    blocks, no exchange; results are gathered only when one host wants all frames;
+  * the optimizer is two sequential frame chains per level (forward / backward from the middle frame,
+    morph.cu:1374-1439): at most two ranks can own a chain each; they exchange their halves of `v` once per level.
+No collective is used unless a stage really exchanges data; timing reductions are scalar (MAX of seconds, SUM of units).
+"""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def init(backend=None, device_id=None):
+    """init_process_group from the torchrun environment (RANK, WORLD_SIZE, MASTER_ADDR, MASTER_PORT). No-op for world 1."""
+    rank, local, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl" and device_id is not None:
+            kw["device_id"] = torch.device("cuda", device_id)
+        dist.init_process_group(backend, **kw)
+    return rank, local, world
+
+
+def frame_blocks(d, world):
+    """Contiguous frame blocks [(begin, end), ...] per rank for the frame-parallel stages; sizes differ by at most one."""
+    base, rem = divmod(d, world)
+    out, b = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((b, b + n))
+        b += n
+    return out
+
+
+def chain_plan(d, world):
+    """Exact-mode optimizer plan for a level of depth d: {"mid": frame, "forward": (rank, [frames]), "backward": (rank, [frames])}.
+    The middle frame is optimised by every chain owner (deterministic => identical), each owner then walks its chain;
+    afterwards the owners exchange the `v` pages of their frames.  Ranks >= 2 own no chain (the chain is sequential)."""
+    mid = d // 2
+    fwd = list(range(mid + 1, d))
+    bwd = list(range(mid - 1, -1, -1))
+    return {"mid": mid, "forward": (0, fwd), "backward": (min(1, world - 1), bwd)}
+
+
+def reduce_throughput(units, seconds, device=None):
+    """Whole-job throughput: SUM of the units all ranks processed / MAX over ranks of the time.  Returns (units, seconds)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(units), float(seconds)
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    u = torch.tensor([float(units)], dtype=torch.float64, device=dev)
+    t = torch.tensor([float(seconds)], dtype=torch.float64, device=dev)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(u.item()), float(t.item())
+
+
+def gather_frames(local, d, device=None):
+    """All ranks contribute their frame block (frame_blocks order) of a (n_local, ...) array; every rank gets the (d, ...) whole."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return np.ascontiguousarray(local)
+    world = dist.get_world_size()
+    blocks = frame_blocks(d, world)
+    nmax = max(e - b for b, e in blocks)
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    loc = np.ascontiguousarray(local)
+    pad = np.zeros((nmax,) + loc.shape[1:], loc.dtype)
+    pad[: loc.shape[0]] = loc
+    t = torch.from_numpy(pad).to(dev)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    return np.concatenate([o.cpu().numpy()[: e - b] for o, (b, e) in zip(outs, blocks)], 0)
+
+
+def render_frames_sharded(w, h, ex, ext0, ext1, vectors, qpaths=None, color_from=1, device=0, gather=True):
+    """RenderWidget-style pass over all d frames (geo_fa = color_fa = smoothstep(frame / (d-1)), UI/RenderWidget.cpp:93-96),
+    each rank rendering its frame block on its own GPU.  ext0/ext1: (d, h+2ex, w+2ex, 4) u8; vectors: (d,h,w,2)."""
+    from . import api, synth
+    d = vectors.shape[0]
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    b, e = frame_blocks(d, world)[rank]
+    out = np.zeros((e - b, h, w, 3), np.uint8)
+    for z in range(b, e):
+        fa = float(synth.smoothstep(z / max(1, d - 1)))
+        out[z - b] = api.render_halfway_image(w, h, ex, fa, fa, color_from, ext0[z], ext1[z], vectors[z],
+                                              None if qpaths is None else qpaths[z], device=device)
+    return gather_frames(out, d) if gather else out
