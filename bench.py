@@ -273,7 +273,8 @@ def run_ours(args):
     d2h = int(out_pin.numel() * 4)
 
     # ---------------- secondary figure: morphed 720p frames/s (render.cu path)
-    render = render_bench(vm, L, local, sh, stream, barrier) if rank == 0 and not args.no_render else None
+    # rank 0 only: must not contain a collective (local synchronisation only)
+    render = render_bench(vm, L, local, sh, stream, torch.cuda.synchronize) if rank == 0 and not args.no_render else None
 
     # ---------------- reduce over ranks (device time: max; work: sum)
     t = torch.tensor([dev_ms, e2e_s, sweep_ms], dtype=torch.float64, device="cuda")

@@ -117,15 +117,17 @@ def test_cluster_and_cta_width_do_not_change_results(vm, oracle_lib):
     try:
         for env in ({"VMORPH_CLUSTER": "1", "VMORPH_VARIANT": "thr8"}, {"VMORPH_CLUSTER": "2", "VMORPH_VARIANT": "thr16"},
                     {"VMORPH_CLUSTER": "1", "VMORPH_VARIANT": "lat"}, {"VMORPH_CLUSTER": "4", "VMORPH_VARIANT": "lat"},
-                    {"VMORPH_CLUSTER": "8", "VMORPH_VARIANT": "lat"}, {"VMORPH_CLUSTER": "16", "VMORPH_VARIANT": "lat"}, {}):
-            for k in ("VMORPH_CLUSTER", "VMORPH_VARIANT"):
+                    {"VMORPH_CLUSTER": "8", "VMORPH_VARIANT": "lat"}, {"VMORPH_CLUSTER": "16", "VMORPH_VARIANT": "lat"},
+                    {"VMORPH_CLUSTER": "1", "VMORPH_VARIANT": "lat", "VMORPH_DYNAMIC": "1"},      # active-tile list, tiles pulled dynamically
+                    {"VMORPH_CLUSTER": "1", "VMORPH_VARIANT": "thr8", "VMORPH_DYNAMIC": "1"}, {}):
+            for k in ("VMORPH_CLUSTER", "VMORPH_VARIANT", "VMORPH_DYNAMIC"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             o, pyr, m, n = _setup(vm, oracle_lib, rgb0, rgb1, dict(max_iter=24))
             m.run()
             res.append((m.get_vectors(), m.iters_log()))
     finally:
-        for k in ("VMORPH_CLUSTER", "VMORPH_VARIANT"):
+        for k in ("VMORPH_CLUSTER", "VMORPH_VARIANT", "VMORPH_DYNAMIC"):
             os.environ.pop(k, None)
     for v, it in res[1:]:
         np.testing.assert_array_equal(v, res[0][0])

@@ -318,8 +318,8 @@ int vm_morph_create(const vm_params *prm, vm_pyramid *pyr, volatile int *run_fla
     }
     cudaError_t e = cudaHostAlloc((void **)&m->progress_host, 64, cudaHostAllocMapped);
     if (e == cudaSuccess) { m->progress_host[0] = 0; e = cudaHostGetDevicePointer((void **)&m->progress_dev, m->progress_host, 0); }
-    if (e == cudaSuccess) e = m->ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(prm->max_iter + 1));
-    if (e == cudaSuccess) e = m->ctrl2.ensure(sizeof(unsigned) * sweep_ctrl_words(prm->max_iter + 1));
+    if (e == cudaSuccess) e = m->ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(prm->max_iter + 1, 8192));
+    if (e == cudaSuccess) e = m->ctrl2.ensure(sizeof(unsigned) * sweep_ctrl_words(prm->max_iter + 1, 8192));
     for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaStreamCreateWithFlags(&m->chain_stream[k], cudaStreamNonBlocking);
     for (int k = 0; k < 3 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&m->chain_ev[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { vm_morph_destroy(m); return cuda_fail(e, "morph_create"); }
@@ -481,8 +481,9 @@ static int enqueue_frame(vm_morph *m, int level, int frame, int flag, float max_
     int iters_cap = (int)ceilf(max_iter) + 1;
     if (iters_cap < 1) iters_cap = 1;
     DevBuf &ctrl = chain ? m->ctrl2 : m->ctrl;
-    if (ctrl.bytes < sizeof(unsigned) * sweep_ctrl_words(iters_cap)) { VM_CUDA(cudaDeviceSynchronize()); VM_CUDA(ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(iters_cap))); }
-    VM_CUDA(cudaMemsetAsync(ctrl.p, 0, sizeof(unsigned) * sweep_ctrl_words(iters_cap), s));
+    const size_t cwords = sweep_ctrl_words(iters_cap, sweep_num_tiles(L.w, L.h));
+    if (ctrl.bytes < sizeof(unsigned) * cwords) { VM_CUDA(cudaDeviceSynchronize()); VM_CUDA(ctrl.ensure(sizeof(unsigned) * cwords)); }
+    VM_CUDA(cudaMemsetAsync(ctrl.p, 0, sizeof(unsigned) * (8 + (size_t)iters_cap + 8), s));      // counters + flags (the tile lists need no clearing)
     m->seqs.push_back({level, frame, (double)L.w * L.h, max_iter});
     while (m->ev.size() < 2 * (size_t)(seq + 1)) { cudaEvent_t e; VM_CUDA(cudaEventCreate(&e)); m->ev.push_back(e); }
     VM_CUDA(cudaEventRecord(m->ev[2 * seq], s));

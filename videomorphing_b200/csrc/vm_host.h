@@ -120,7 +120,8 @@ void free_resample_cache(vm_pyramid *p);
 // kernels (launchers) -- vm_kernels.cu / vm_sweep.cu / vm_render.cu / vm_resample.cu
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
                          unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, int sm_budget, cudaStream_t stream);
-size_t sweep_ctrl_words(int max_iter_ceil);
+size_t sweep_ctrl_words(int max_iter_ceil, int ntiles);
+int sweep_num_tiles(int w, int h);
 
 cudaError_t launch_initialize_level(const LevelView &L, const StencilTables *st, float ssim_clamp, cudaStream_t s);
 cudaError_t launch_ui_splat(const LevelView &L, const Conn *cons_dev, int ncons, int factor, int w0, int h0, int d0, cudaStream_t s);

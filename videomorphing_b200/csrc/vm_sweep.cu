@@ -60,6 +60,7 @@ struct SweepSmem {
     unsigned short queue[NPIX];
     int warp_cnt[NPIX / 32];
     unsigned int stat_any[NPIX / 32];    // per filter warp: ballot of pixels that have a mask index
+    int next_tile;                       // dynamic mode: list entry this CTA works on
     unsigned int accrow[OPT_BH];         // accepted slots of the sub-phase, one 32-bit row per lattice row
     unsigned int mask[MASK_W * MASK_H];  // improving-mask words around the tile (see tile_step)
     float tps[25 * 25];
@@ -526,6 +527,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                 int tx = tid & 31, ty = tid >> 5;
                 int acc = SB.acc[tid];
                 any = acc;
+                if (acc) SB.acc[tid] = 0;              // next written by the cluster two sub-phases from now, after two more barriers
                 unsigned abal = __ballot_sync(0xffffffffu, acc != 0);
                 if (lane == 0) S.accrow[ty] = abal;
                 if (S.status[tid]) {
@@ -538,6 +540,8 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             }
             // ---- commit B: deterministic gather of the SSIM-sum and TPS deltas into the replica, then UpdateSSIM
             //      (morph.cu:973-987,1006-1015,1258-1279).  Contributors in row-major order of the source pixel.
+            //      Every CTA of a cluster repeats the whole gather on its own replica: dealing the cells out to the CTAs and
+            //      broadcasting the results through distributed shared memory was measured slower (profiles/, trace6).
             if (__syncthreads_or(any)) {
                 dirty = true;
                 for (int cc = tid; cc < rcells; cc += NT) {
@@ -587,8 +591,6 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                     }
                     if (ch_t) S.tpsb[c] = tb;
                 }
-                __syncthreads();
-                if (tid < NPIX) SB.acc[tid] = 0;       // next written two sub-phases from now, after the next barrier
             }
             phase++;
             __syncthreads();
@@ -617,12 +619,37 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
     TR(6);
 }
 
+// Is any improving-mask bit of a pixel inside the extent of the tile at (ox, oy) set?  Warp-cooperative version of the
+// skip test at the top of tile_step, used to build the list of active tiles of a step.
+__device__ __forceinline__ bool tile_active_warp(const LevelView &L, const unsigned int *gmask, int ox, int oy, int lane) {
+    const int mcx0 = (ox + 2) / 5, mcy0 = (oy + 2) / 5, irows = L.ips / L.irs;
+    int ex0 = max(ox, 0), ex1 = min(ox + TW - 1, ((L.w + 4) / 5) * 5 - 1), ey0 = max(oy, 0), ey1 = min(oy + TH - 1, ((L.h + 4) / 5) * 5 - 1);
+    int any = 0;
+    for (int k = lane; k < MASK_W * MASK_H; k += 32) {
+        int my = k / MASK_W, mx = k - my * MASK_W;
+        int cx = mcx0 + mx, cy = mcy0 + my, pcx = cx - 1, pcy = cy - 1;
+        if (cx >= L.irs || cy >= irows || pcx < 0 || pcy < 0) continue;
+        unsigned xm = 0, m = 0;
+        for (int r = 0; r < 5; r++) if (pcx * 5 + r >= ex0 && pcx * 5 + r <= ex1) xm |= 1u << r;
+        for (int r = 0; r < 5; r++) if (pcy * 5 + r >= ey0 && pcy * 5 + r <= ey1) m |= xm << (5 * r);
+        if (m) any |= (__ldcg(gmask + cy * L.irs + cx) & m) != 0u;
+    }
+    return __any_sync(0xffffffffu, any);
+}
+
 // ctrl layout (unsigned ints): [0] barrier counter, [1] iterations executed (out), [2] cancelled (out),
-// [8 + it] per-iteration flags: bit0 = improving, bit1 = cancel requested.
+// [4 + par] number of active tiles, [6 + par] next list entry to hand out (par = parity of the non-empty step count),
+// [8 + it] per-iteration flags: bit0 = improving, bit1 = cancel requested; then (dynamic mode) two tile lists.
+//
+// dyn == 0: tile t belongs to cluster t % nclusters (every tile has its own cluster when they all fit).
+// dyn == 1 (levels with more tiles than co-resident CTAs, R == 1): each step first builds the list of tiles that still
+// have an improving pixel -- late iterations touch a few percent of the tiles -- and the CTAs pull tiles from it, so no
+// SM idles behind a converged tile while another one has several active tiles queued.  Tiles of a step are independent,
+// the order in which they are processed does not change the result.
 template <int NW, bool LAT>
 __global__ void __launch_bounds__(NW * 32, (LAT ? 1 : (NW <= 8 ? 3 : 2)))
 k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, int flag, float max_iter,
-        unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq) {
+        unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int dyn, int list_off) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SweepSmem &S = *reinterpret_cast<SweepSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -640,6 +667,7 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
     const int nclusters = gridDim.x / R, cid = blockIdx.x / R;
     unsigned int epoch = 0, phase = 0;
     int iter = 0;
+    unsigned nstep = 0;                 // non-empty steps so far (parity selects the tile list)
     bool go;
     do {
         if (tid == 0) S.cta_improving = 0;
@@ -648,13 +676,40 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
         for (int step = 0; step < 4; step++) {
             const int offx = (step & 1) ? OPT_BW * 2 : 0, offy = (step & 2) ? OPT_BH * 2 : 0;   // morph.cu:1382-1385
             const bool empty = offx >= L.w || offy >= L.h;   // no pixel of any tile inside the image: empty launch
-            if (!empty) {
+            if (!empty && !dyn) {
                 for (int t = cid; t < ntiles; t += nclusters) {
                     int by = t / gx, bx = t - by * gx;
                     int ox = bx * (OPT_BW * 2 + SPACING) + offx - 2, oy = by * (OPT_BH * 2 + SPACING) + offy - 2;
                     if (ox + 2 >= L.w || oy + 2 >= L.h) continue;
                     tile_step<NW, LAT>(S, L, P, st, page, flag != 0, ox, oy, R, rank, phase);
                 }
+            } else if (!empty) {
+                const unsigned par = nstep & 1u;
+                unsigned int *list = ctrl + list_off + par * ntiles;
+                const unsigned int *gmask = L.impmask + (size_t)page * L.ips;
+                // ---- scan: one warp per tile
+                for (int t = blockIdx.x * NW + (tid >> 5); t < ntiles; t += gridDim.x * NW) {
+                    int by = t / gx, bx = t - by * gx;
+                    int ox = bx * (OPT_BW * 2 + SPACING) + offx - 2, oy = by * (OPT_BH * 2 + SPACING) + offy - 2;
+                    if (ox + 2 >= L.w || oy + 2 >= L.h) continue;
+                    if (tile_active_warp(L, gmask, ox, oy, tid & 31) && (tid & 31) == 0) list[atomicAdd(&ctrl[4 + par], 1u)] = (unsigned)t;
+                }
+                grid_barrier(&ctrl[0], epoch, gridDim.x);
+                if (blockIdx.x == 0 && tid == 0) { ctrl[4 + (par ^ 1u)] = 0u; ctrl[6 + (par ^ 1u)] = 0u; }   // lists of the next step
+                const unsigned nact = __ldcg(&ctrl[4 + par]);
+                // ---- pull
+                while (true) {
+                    __syncthreads();
+                    if (tid == 0) S.next_tile = (int)atomicAdd(&ctrl[6 + par], 1u);
+                    __syncthreads();
+                    const unsigned k = (unsigned)S.next_tile;
+                    if (k >= nact) break;
+                    int t = (int)__ldcg(list + k);
+                    int by = t / gx, bx = t - by * gx;
+                    int ox = bx * (OPT_BW * 2 + SPACING) + offx - 2, oy = by * (OPT_BH * 2 + SPACING) + offy - 2;
+                    tile_step<NW, LAT>(S, L, P, st, page, flag != 0, ox, oy, R, rank, phase);
+                }
+                nstep++;
             }
             if (step == 3 && tid == 0) {                      // publish this CTA's vote before the iteration's last barrier
                 unsigned f = S.cta_improving ? 1u : 0u;
@@ -717,6 +772,11 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
     int R = 1 << lg;
     int nclusters = ntiles < cap(lg) ? ntiles : cap(lg);
     if (nclusters < 1) nclusters = 1;
+    // more tiles than co-resident clusters: hand tiles out dynamically from the per-step list of active tiles
+    const char *ed = getenv("VMORPH_DYNAMIC");
+    int dyn = (R == 1 && ntiles > nclusters) ? 1 : 0;
+    if (ed) dyn = (atoi(ed) != 0 && R == 1) ? 1 : 0;
+    int list_off = (int)sweep_ctrl_words((int)ceilf(max_iter) + 1, 0);
     LevelView Lc = L; KParams Pc = P;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(nclusters * R); lc.blockDim = dim3(NW * 32); lc.dynamicSmemBytes = smem; lc.stream = stream;
@@ -725,13 +785,13 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
     at[1].id = cudaLaunchAttributeClusterDimension; at[1].val.clusterDim.x = R; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = (R > 1) ? 2 : 1;
     count_launch();
-    cudaError_t e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq);
+    cudaError_t e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq, dyn, list_off);
     if (e != cudaSuccess && R > 1) {
         // cooperative + cluster attribute combination rejected: the grid is sized to be co-resident
         // (<= cudaOccupancyMaxActiveClusters), launch it as a plain cluster grid.
         cudaGetLastError();
         lc.attrs = at + 1; lc.numAttrs = 1;
-        e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq);
+        e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq, dyn, list_off);
     }
     return e;
 }
@@ -750,14 +810,19 @@ cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTabl
     const char *ec = getenv("VMORPH_CLUSTER"), *ev = getenv("VMORPH_VARIANT");
     int want_r = (ec && atoi(ec) > 0) ? atoi(ec) : 16;
     if (sm_budget <= 0 || sm_budget > sm_count) sm_budget = sm_count;
-    int variant = (ntiles <= sm_budget) ? 0 : (ntiles <= 2 * sm_budget ? 1 : 2);
+    // levels with more tiles than SMs: the latency variant with dynamic tile hand-out (VMORPH_VARIANT=thr16|thr8 keep
+    // the static many-CTAs-per-SM schedule for comparison)
+    int variant = 0;
     if (ev) variant = !strcmp(ev, "lat") ? 0 : (!strcmp(ev, "thr16") ? 1 : (!strcmp(ev, "thr8") ? 2 : variant));
     if (variant == 0) return launch_sweep_t<16, true>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 0, want_r);
     if (variant == 1) return launch_sweep_t<16, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 1, want_r);
     return launch_sweep_t<8, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 2, want_r);
 }
 
-size_t sweep_ctrl_words(int max_iter_ceil) { return 8 + (size_t)max_iter_ceil + 8; }
+size_t sweep_ctrl_words(int max_iter_ceil, int ntiles) { return 8 + (size_t)max_iter_ceil + 8 + 2 * (size_t)ntiles; }
+int sweep_num_tiles(int w, int h) {
+    return ((w + OPT_BW * 2 + SPACING - 1) / (OPT_BW * 2 + SPACING)) * ((h + OPT_BH * 2 + SPACING - 1) / (OPT_BH * 2 + SPACING));
+}
 
 #ifdef VM_TRACE
 extern "C" int vm_debug_trace(unsigned long long *out32, int reset) {

@@ -8,6 +8,7 @@ What shards on this path:
     morph.cu:1374-1439): at most two ranks can own a chain each; they exchange their halves of `v` once per level.
 No collective is used unless a stage really exchanges data; timing reductions are scalar (MAX of seconds, SUM of units).
 """
+import datetime
 import os
 
 import numpy as np
@@ -25,7 +26,7 @@ def init(backend=None, device_id=None):
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
-        kw = {}
+        kw = {"timeout": datetime.timedelta(seconds=int(os.environ.get("VMORPH_DIST_TIMEOUT_S", "300")))}   # fail fast instead of hanging a GPU box
         if backend == "nccl" and device_id is not None:
             kw["device_id"] = torch.device("cuda", device_id)
         dist.init_process_group(backend, **kw)
