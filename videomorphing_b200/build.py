@@ -38,6 +38,20 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_headless(force=False):
+    """tools/vmorph_headless: the headless C++ driver, plain g++ against include/vmorph.h + libvmorph.so (rpath'd in-tree)."""
+    src = os.path.join(HERE, "..", "tools", "vmorph_headless.cpp")
+    out = os.path.join(HERE, "vmorph_headless")
+    if not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(OUT)):
+        return out
+    cmd = ["g++", "-O2", "-std=c++17", "-o", out, src, "-L" + HERE, "-l:libvmorph.so", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("g++ failed building vmorph_headless")
+    return out
+
+
 def build_trace():
     """Development aid: libvmorph_trace.so = the same sources with -DVM_TRACE (per-phase cycle counters in the sweep)."""
     out = os.path.join(HERE, "libvmorph_trace.so")
@@ -54,3 +68,4 @@ if __name__ == "__main__":
     else:
         build(force=True, verbose="-v" in sys.argv)
         print(OUT)
+        print(build_headless(force=True))
