@@ -146,6 +146,14 @@ int vm_level_init_temp(vm_morph *m, int level, int frame, int dir, void *stream)
 /* per-frame do/while of Morph::optimize_level (morph.cu:1377-1391); returns iterations executed in *iters_out */
 int vm_level_optimize_frame(vm_morph *m, int level, int frame, int flag, float max_iter, int *iters_out, void *stream);
 int vm_level_optimize(vm_morph *m, int level, float max_iter, void *stream);       /* Morph::optimize_level morph.cu:1353-1441 */
+/* Multi-GPU exact mode: the middle frame (morph.cu:1377-1391) plus the selected chains of Morph::optimize_level: bit 0 =
+ * forward chain (morph.cu:1392-1415), bit 1 = backward chain (1416-1439).  chains == 3 is vm_level_optimize. */
+int vm_level_optimize_chains(vm_morph *m, int level, float max_iter, int chains, void *stream);
+/* Device pointer + size of a level array (fields / layouts of vm_level_get) for P2P / NCCL exchanges done by the caller;
+ * vm_level_mark_v_valid tells the library that level's v has been written that way (PyramidLevel::v is public in the
+ * reference, Pyramid.h:78). */
+int vm_level_dev_ptr(vm_pyramid *p, int level, int field, void **dev_out, size_t *bytes_out);
+int vm_level_mark_v_valid(vm_pyramid *p, int level);
 /* total energy of SURVEY.md A.6 for one frame; terms_out[4] = ssim, ui, temp, tps parts */
 int vm_level_energy(vm_morph *m, int level, int frame, int flag, double *energy_out, double *terms_out);
 /* CMatchingThread::update_result (MatchingThread.cpp:22-84): level-1 v -> level-0 sized vectors, d0*h0*w0 float2 */
@@ -183,6 +191,7 @@ int vm_dev_alloc(int device, size_t nbytes, void **out_dev);
 int vm_dev_free(int device, void *dev);
 int vm_dev_upload(int device, void *dst_dev, const void *src_host, size_t nbytes, void *stream);
 int vm_dev_download(int device, void *dst_host, const void *src_dev, size_t nbytes, void *stream);
+int vm_dev_copy(int device, void *dst_dev, const void *src_dev, size_t nbytes, void *stream);
 int vm_stream_sync(int device, void *stream);
 /* counts kernels launched by this library since process start (bench.py's gpu_launches claim) */
 uint64_t vm_kernel_launch_count(void);

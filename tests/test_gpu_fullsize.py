@@ -75,3 +75,58 @@ def test_optimisation_lowers_energy_at_every_level(vm, oracle_lib):
         e1 = m.energy(l)[0]
         assert e1 <= e0 * (1 + 1e-6), (l, e0, e1)
         mi /= 2
+
+
+def _two_gpu_worker(rank, port, q):
+    import os
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VMORPH_DIST_TIMEOUT_S="120")
+    import torch
+    import torch.distributed as dist
+    import videomorphing_b200 as vm
+    from videomorphing_b200 import dist as vd, synth
+    torch.cuda.set_device(rank)
+    vd.init("nccl", device_id=rank)
+    v0, v1, flows, _ = synth.video_pair(96, 64, 9, 41, 42, 3.0)
+    prm = vm.Parameters(max_iter=24, start_res=4)
+    pyr = vm.Pyramid(rank); pyr.build(v0, v1, flows, start_res=4)
+    m = vm.Morph(prm, pyr)
+    vd.optimize_video(m, pyr, prm, device=rank)
+    vec = m.get_vectors()
+    dist.barrier()
+    q.put((rank, vec, m.iters_log().copy()))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_chain_split_is_bit_identical_to_one_gpu(vm):
+    # exact multi-GPU mode: forward chain on GPU 0, backward chain on GPU 1, v pages swapped per level over NCCL
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from videomorphing_b200 import synth
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict((r, (v, it)) for r, v, it in (q.get(timeout=240) for _ in range(2)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    v0, v1, flows, _ = synth.video_pair(96, 64, 9, 41, 42, 3.0)
+    prm = vm.Parameters(max_iter=24, start_res=4)
+    pyr = vm.Pyramid(0); pyr.build(v0, v1, flows, start_res=4)
+    m = vm.Morph(prm, pyr); m.run()
+    ref = m.get_vectors()
+    np.testing.assert_array_equal(res[0][0], ref)
+    np.testing.assert_array_equal(res[1][0], ref)
+    # each rank logged the middle frame + its own chain of every level; together they cover the single-GPU log
+    one = {(int(l), int(f)): int(i) for l, f, i in m.iters_log()}
+    both = {}
+    for r in (0, 1):
+        for l, f, i in res[r][1]:
+            assert one[(int(l), int(f))] == int(i)
+            both[(int(l), int(f))] = int(i)
+    assert both == one

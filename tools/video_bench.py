@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--qpath", action="store_true"); ap.add_argument("--qpath-iter", type=int, default=10000)
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--cpu-frames", type=int, default=0, help="also time the CPU oracle on the first N frames (all levels) for the ratio")
     args = ap.parse_args()
     import videomorphing_b200 as vm
     from videomorphing_b200 import synth, api
@@ -54,6 +55,19 @@ def main():
                "launches": int(L.vm_kernel_launch_count())}
         print(json.dumps(out), flush=True)
         m.close()
+    if args.cpu_frames > 0:
+        from oracle import pyoracle as po
+        import subprocess
+        subprocess.run(["make", "-s", "-B", "-C", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"), "liboracle_native.so"], check=True, stdout=subprocess.DEVNULL)
+        n = args.cpu_frames
+        o = po.Oracle(dict(max_iter=args.max_iter), native=True)
+        t = time.perf_counter(); o.build(v0[:n], v1[:n], flows=[f[:n] for f in flows], voxel_cap=cap); tb = time.perf_counter() - t
+        t = time.perf_counter(); o.run(); tr = time.perf_counter() - t
+        L2 = po.lib(native=True); L2.vo_num_threads.restype = C.c_int
+        cpu = {"cpu_oracle_frames": n, "threads": L2.vo_num_threads(), "build_s": tb, "optimize_s": tr, "pixel_iters": o.executed_pixel_iters,
+               "mpixel_iters_per_s": o.executed_pixel_iters / tr / 1e6, "seconds_per_frame": tr / n,
+               "gpu_over_cpu_mpixel_iters": out["mpixel_iters_per_s"] / (o.executed_pixel_iters / tr / 1e6)}
+        print(json.dumps(cpu), flush=True)
 
 
 if __name__ == "__main__":

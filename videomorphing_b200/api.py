@@ -113,6 +113,12 @@ class Pyramid:
             shp = shp + (2,)
         return shp, np.float32
 
+    def dev_ptr(self, l, name):
+        """(device pointer, bytes) of a level array, for P2P / NCCL exchanges."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        check(self.L.vm_level_dev_ptr(self.h, l, FIELDS[name], C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
     def get(self, l, name):
         shp, dt = self._shape(l, name)
         out = np.zeros(shp, dt)
@@ -205,6 +211,10 @@ class Morph:
 
     def optimize_level(self, level, max_iter, stream=None):
         check(self.L.vm_level_optimize(self.h, level, float(max_iter), stream))
+
+    def optimize_chains(self, level, max_iter, chains, stream=None):
+        """Middle frame + the selected chains of Morph::optimize_level (1 forward, 2 backward, 3 both)."""
+        check(self.L.vm_level_optimize_chains(self.h, level, float(max_iter), int(chains), stream))
 
     def energy(self, level, frame=0, flag=False):
         e = C.c_double(0)

@@ -529,12 +529,12 @@ int vm_level_optimize_frame(vm_morph *m, int level, int frame, int flag, float m
 // frame's result, so they are enqueued on two streams and run CONCURRENTLY, each with half of the SMs as its budget
 // (coarse levels occupy a fraction of the GPU anyway).  Same arithmetic, same results as the sequential order; the
 // iteration log keeps the reference's order.  VMORPH_CHAINS=1 forces the sequential schedule (test hook).
-static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s) {
+static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s, int chains = 3) {
     vm_pyramid *p = m->pyr; Level &L = p->lv[level];
     int mid = L.d / 2, rc;
     rc = enqueue_frame(m, level, mid, 0, max_iter, s, nullptr); if (rc) return rc;
     const char *ec = getenv("VMORPH_CHAINS");
-    const bool two = L.d > 2 && !(ec && atoi(ec) == 1);
+    const bool two = L.d > 2 && chains == 3 && !(ec && atoi(ec) == 1);
     cudaStream_t sf = s, sb = s;
     int budget = 0;
     if (two) {
@@ -551,12 +551,12 @@ static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s)
         VM_CUDA(cudaStreamWaitEvent(sf, m->chain_ev[0], 0));
         VM_CUDA(cudaStreamWaitEvent(sb, m->chain_ev[0], 0));
     }
-    for (int i = mid + 1; i < L.d; i++) {
+    for (int i = mid + 1; i < L.d && (chains & 1); i++) {
         if (!keep_running(m)) break;
         rc = init_temp_chain(m, level, i, -1, sf, 0); if (rc) return rc;
         rc = enqueue_frame(m, level, i, 1, max_iter, sf, nullptr, 0, budget); if (rc) return rc;
     }
-    for (int i = mid - 1; i >= 0; i--) {
+    for (int i = mid - 1; i >= 0 && (chains & 2); i--) {
         if (!keep_running(m)) break;
         rc = init_temp_chain(m, level, i, 1, sb, two ? 1 : 0); if (rc) return rc;
         rc = enqueue_frame(m, level, i, 1, max_iter, sb, nullptr, two ? 1 : 0, budget); if (rc) return rc;
@@ -567,6 +567,40 @@ static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s)
         VM_CUDA(cudaStreamWaitEvent(s, m->chain_ev[1], 0));
         VM_CUDA(cudaStreamWaitEvent(s, m->chain_ev[2], 0));
     }
+    return VM_OK;
+}
+
+// Multi-GPU exact mode: the middle frame plus the chains selected by `chains` (bit 0 forward = frames mid+1.., bit 1
+// backward = frames mid-1..0).  Two ranks each own one chain of every level and exchange their `v` pages afterwards
+// (videomorphing_b200/dist.py); chains == 3 is vm_level_optimize.
+int vm_level_optimize_chains(vm_morph *m, int level, float max_iter, int chains, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
+    if (!(max_iter > 0) || max_iter > 4000 || chains < 0 || chains > 3) { set_error("bad max_iter %g / chains %d", max_iter, chains); return VM_ERR_ARG; }
+    int rc = use_device(p->device); if (rc) return rc;
+    size_t from = m->seqs.size();
+    rc = enqueue_level(m, level, max_iter, s, chains); if (rc) return rc;
+    return collect_log(m, from, s);
+}
+
+// Raw device pointer of a level array (same fields / layouts as vm_level_get), for P2P / NCCL exchanges by the caller.
+int vm_level_dev_ptr(vm_pyramid *p, int level, int field, void **dev_out, size_t *bytes_out) {
+    void *ptr; size_t bytes;
+    int rc = field_ptr(p, level, field, &ptr, &bytes); if (rc) return rc;
+    if (dev_out) *dev_out = ptr;
+    if (bytes_out) *bytes_out = bytes;
+    return VM_OK;
+}
+// Marks a level's vector field as valid after the caller wrote it through vm_level_dev_ptr (like vm_level_set does).
+int vm_level_mark_v_valid(vm_pyramid *p, int level) {
+    if (!p || level < 1 || level >= (int)p->lv.size()) { set_error("bad level %d", level); return VM_ERR_ARG; }
+    p->lv[level].v_valid = true;
+    return VM_OK;
+}
+int vm_dev_copy(int device, void *dst_dev, const void *src_dev, size_t nbytes, void *stream) {
+    int rc = use_device(device); if (rc) return rc;
+    VM_CUDA(cudaMemcpyAsync(dst_dev, src_dev, nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return VM_OK;
 }
 

@@ -97,3 +97,76 @@ def render_frames_sharded(w, h, ex, ext0, ext1, vectors, qpaths=None, color_from
         out[z - b] = api.render_halfway_image(w, h, ex, fa, fa, color_from, ext0[z], ext1[z], vectors[z],
                                               None if qpaths is None else qpaths[z], device=device)
     return gather_frames(out, d) if gather else out
+
+
+# ------------------------------------------------------------------------------------------ optimizer, exact mode
+def _exchange_pages(pyramid, level, my_pages, peer_pages, peer, device, stream=None):
+    """Send this rank's `v` pages [a, b) of a level to `peer` and receive the peer's pages: NCCL send / recv over NVLink.
+    The pages are contiguous in the level array (pagestride float2 each), staged through torch tensors."""
+    from . import _lib
+    L = _lib.load()
+    info = pyramid.info(level)
+    page_bytes = info["pagestride"] * 8
+    base, _ = pyramid.dev_ptr(level, "v")
+    ops, recv_t = [], None
+    (a, b), (c, e) = my_pages, peer_pages
+    if b > a:
+        send_t = torch.empty((b - a) * page_bytes, dtype=torch.uint8, device=f"cuda:{device}")
+        _lib.check(L.vm_dev_copy(device, send_t.data_ptr(), base + a * page_bytes, (b - a) * page_bytes, stream))
+        ops.append(dist.P2POp(dist.isend, send_t, peer))
+    if e > c:
+        recv_t = torch.empty((e - c) * page_bytes, dtype=torch.uint8, device=f"cuda:{device}")
+        ops.append(dist.P2POp(dist.irecv, recv_t, peer))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if recv_t is not None:
+        _lib.check(L.vm_dev_copy(device, base + c * page_bytes, recv_t.data_ptr(), (e - c) * page_bytes, stream))
+        torch.cuda.current_stream().synchronize()
+
+
+def optimize_video(morph, pyramid, params, device=0):
+    """Morph::calculate_halfway_parametrization (morph.cu:150-168) for a video with the two frame chains of every level on
+    two GPUs (exact mode: the same arithmetic as one GPU, bit-identical result on ranks 0 and 1).
+
+    Every rank holds the whole pyramid (built from the same frames).  Per level: upsample + initialise all frames (cheap,
+    redundant), rank 0 optimises the middle frame and the forward chain, rank 1 the middle frame and the backward chain
+    (the middle frame is deterministic, so both get the same bits), then they swap the `v` pages of their chains -- the
+    only exchange on the path: one frame's vector field per frame and level, handed to the rank that needs it for the
+    next level's prolongation.  Ranks >= 2 own no chain (the chain is sequential) and receive the level by broadcast.
+    With one rank this is the ordinary run (both chains concurrently on two streams)."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    n = pyramid.num_levels
+    morph.cpu_optimize_level()
+    max_iter = float(params.max_iter)
+    for l in range(n - 2, 0, -1):
+        morph.upsample(l)
+        morph.initialize_level(l)
+        d = pyramid.info(l)["d"]
+        plan = chain_plan(d, world)
+        mid = plan["mid"]
+        if world == 1:
+            morph.optimize_chains(l, max_iter, 3)
+        else:
+            chains = (1 if rank == plan["forward"][0] else 0) | (2 if rank == plan["backward"][0] else 0)
+            if rank <= 1:
+                morph.optimize_chains(l, max_iter, chains)
+                fwd, bwd = (mid + 1, d), (0, mid)
+                if rank == 0:
+                    _exchange_pages(pyramid, l, fwd, bwd, 1, device)
+                else:
+                    _exchange_pages(pyramid, l, bwd, fwd, 0, device)
+            if world > 2:
+                from . import _lib
+                base, nbytes = pyramid.dev_ptr(l, "v")
+                t = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{device}")
+                if rank == 0:
+                    _lib.check(_lib.load().vm_dev_copy(device, t.data_ptr(), base, nbytes, None))
+                dist.broadcast(t, 0)
+                if rank > 1:
+                    _lib.check(_lib.load().vm_dev_copy(device, base, t.data_ptr(), nbytes, None))
+                    _lib.check(_lib.load().vm_level_mark_v_valid(pyramid.h, l))
+                torch.cuda.current_stream().synchronize()
+        max_iter /= params.max_iter_drop_factor
+    return morph
