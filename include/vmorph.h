@@ -136,6 +136,8 @@ double vm_morph_executed_pixel_iters(const vm_morph *m);
  * and their count: the live measurement behind bench.py's roofline (no reference counterpart; the reference only
  * clocks the whole stage, MatchingThread.cpp:141-145) */
 double vm_morph_sweep_ms(const vm_morph *m, uint64_t *launches_out);
+/* device ms of every logged sweep launch, in the order of vm_morph_iters_log; returns count */
+int vm_morph_ms_log(const vm_morph *m, int max_entries, float *out);
 /* (level, frame, iterations) triples logged by optimize_level; returns count */
 int vm_morph_iters_log(const vm_morph *m, int max_triples, int32_t *out);
 /* operator-level entry points (for unit parity with the reference operators) */

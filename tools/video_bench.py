@@ -35,6 +35,10 @@ def main():
         px = m.executed_pixel_iters - px0
         t = time.perf_counter(); vec = m.get_vectors(); t_extract = time.perf_counter() - t
         sw_ms, sw_n = m.sweep_time_ms()
+        il, ml = m.iters_log(), m.ms_log()
+        per_level = {}
+        for (l, f, it), ms in zip(il[-len(ml):], ml):
+            a = per_level.setdefault(int(l), [0, 0, 0.0]); a[0] += 1; a[1] += int(it); a[2] += float(ms)
         levels = [(pyr.info(l)["w"], pyr.info(l)["h"], pyr.info(l)["d"]) for l in range(n)]
         qp = None; t_qpath = None; qit = None
         if args.qpath:
@@ -51,6 +55,7 @@ def main():
                "chains": os.environ.get("VMORPH_CHAINS", "2"), "synth_s": t_synth, "build_s": t_build, "optimize_s": t_run, "extract_s": t_extract,
                "qpath_s": t_qpath, "render_host_buffers_s": t_render, "pixel_iters": px, "mpixel_iters_per_s": px / t_run / 1e6,
                "frames_per_s_optimize_plus_render": args.d / (t_run + t_render), "sweep_launches": sw_n, "sweep_ms_sum": sw_ms,
+               "per_level_frames_iters_ms": {str(k): [v[0], v[1], round(v[2], 1)] for k, v in sorted(per_level.items())},
                "mean_abs_err_vs_true_halfway_px": float(err.mean()), "qpath_iters_first": None if qit is None else qit[0].tolist(),
                "launches": int(L.vm_kernel_launch_count())}
         print(json.dumps(out), flush=True)

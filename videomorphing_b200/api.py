@@ -239,6 +239,12 @@ class Morph:
         ms = self.L.vm_morph_sweep_ms(self.h, C.byref(n))
         return ms, n.value
 
+    def ms_log(self):
+        """Device ms of every logged sweep launch (same order as iters_log)."""
+        out = np.zeros(1 << 20, np.float32)
+        n = check(self.L.vm_morph_ms_log(self.h, len(out), _vp(out)))
+        return out[:n].copy()
+
     def iters_log(self):
         out = np.zeros(3 * 65536, np.int32)
         n = check(self.L.vm_morph_iters_log(self.h, 65536, _vp(out)))

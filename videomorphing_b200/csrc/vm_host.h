@@ -104,6 +104,7 @@ struct vm_morph {
     float max_iter_now = 0;
     double executed_pixel_iters = 0;
     std::vector<int32_t> iters_log;
+    std::vector<float> ms_log;            // device ms of each logged sweep launch (same order as iters_log)
     bool cancelled = false;
     // device time of the sweep launches (CUDA events on the launching stream around every k_sweep launch)
     std::vector<cudaEvent_t> ev;          // 2 per launch: ev[2*seq], ev[2*seq+1]

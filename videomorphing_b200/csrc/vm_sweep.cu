@@ -642,7 +642,7 @@ __device__ __forceinline__ bool tile_active_warp(const LevelView &L, const unsig
 // [8 + it] per-iteration flags: bit0 = improving, bit1 = cancel requested; then (dynamic mode) two tile lists.
 //
 // dyn == 0: tile t belongs to cluster t % nclusters (every tile has its own cluster when they all fit).
-// dyn == 1 (levels with more tiles than co-resident CTAs, R == 1): each step first builds the list of tiles that still
+// dyn == 1 (levels with more tiles than co-resident clusters): each step first builds the list of tiles that still
 // have an improving pixel -- late iterations touch a few percent of the tiles -- and the CTAs pull tiles from it, so no
 // SM idles behind a converged tile while another one has several active tiles queued.  Tiles of a step are independent,
 // the order in which they are processed does not change the result.
@@ -699,9 +699,18 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
                 const unsigned nact = __ldcg(&ctrl[4 + par]);
                 // ---- pull
                 while (true) {
-                    __syncthreads();
-                    if (tid == 0) S.next_tile = (int)atomicAdd(&ctrl[6 + par], 1u);
-                    __syncthreads();
+                    if (R == 1) {
+                        __syncthreads();
+                        if (tid == 0) S.next_tile = (int)atomicAdd(&ctrl[6 + par], 1u);
+                        __syncthreads();
+                    } else {                       // the cluster's first CTA draws the entry and tells its peers through DSMEM
+                        cluster.sync();
+                        if (rank == 0 && tid == 0) {
+                            int v = (int)atomicAdd(&ctrl[6 + par], 1u);
+                            for (int r = 0; r < R; r++) *cluster.map_shared_rank(&S.next_tile, r) = v;
+                        }
+                        cluster.sync();
+                    }
                     const unsigned k = (unsigned)S.next_tile;
                     if (k >= nact) break;
                     int t = (int)__ldcg(list + k);
@@ -732,7 +741,7 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
 }
 
 // ------------------------------------------------------------------ host launcher
-struct SweepCfg { bool init = false; int max_clusters[5] = {0, 0, 0, 0, 0}; };   // index = log2(R)
+struct SweepCfg { bool init = false; int per_sm = 0; int max_clusters[17] = {0}; bool queried[17] = {false}; };   // index = cluster size R
 static SweepCfg g_cfg[3];
 
 template <int NW, bool LAT>
@@ -745,37 +754,46 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
     if (!cfg.init) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.per_sm, kern, NW * 32, smem);
         if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        cfg.max_clusters[0] = per_sm * sm_count;
-        if (LAT) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);      // clusters of 16 CTAs
+        if (cfg.per_sm < 1) return cudaErrorLaunchOutOfResources;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);      // clusters of up to 16 CTAs
         cudaGetLastError();
-        for (int lg = 1; lg <= (LAT ? 4 : 3); lg++) {
+        cfg.max_clusters[1] = cfg.per_sm * sm_count; cfg.queried[1] = true;
+        cfg.init = true;
+    }
+    // co-resident clusters of size R on the whole GPU (cudaOccupancyMaxActiveClusters, cached), limited to this launch's SM budget
+    auto cap = [&](int R) {
+        if (!cfg.queried[R]) {
             cudaLaunchConfig_t qc = {};
-            qc.gridDim = dim3(1 << lg); qc.blockDim = dim3(NW * 32); qc.dynamicSmemBytes = smem;
+            qc.gridDim = dim3(R); qc.blockDim = dim3(NW * 32); qc.dynamicSmemBytes = smem;
             cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1 << lg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             qc.attrs = at; qc.numAttrs = 1;
             int nc = 0;
             if (cudaOccupancyMaxActiveClusters(&nc, kern, &qc) != cudaSuccess) { cudaGetLastError(); nc = 0; }
-            cfg.max_clusters[lg] = nc;
+            cfg.max_clusters[R] = nc; cfg.queried[R] = true;
         }
-        cfg.init = true;
-    }
-    // cluster size: the largest power of two <= want_r for which one cluster per tile is co-resident within the SM
-    // budget of this launch (sm_budget < sm_count when two frame chains share the GPU)
-    auto cap = [&](int c) { int by_budget = (cfg.max_clusters[0] / sm_count) * sm_budget >> c; return cfg.max_clusters[c] < by_budget ? cfg.max_clusters[c] : by_budget; };
-    int lg = 0;
-    for (int c = 4; c >= 1; c--) if ((1 << c) <= want_r && cap(c) >= ntiles) { lg = c; break; }
-    int R = 1 << lg;
-    int nclusters = ntiles < cap(lg) ? ntiles : cap(lg);
-    if (nclusters < 1) nclusters = 1;
-    // more tiles than co-resident clusters: hand tiles out dynamically from the per-step list of active tiles
+        int by_budget = cfg.per_sm * sm_budget / R;
+        return cfg.max_clusters[R] < by_budget ? cfg.max_clusters[R] : by_budget;
+    };
+    // Cluster size: as many CTAs (SMs) per tile as the budget allows, ANY size up to 16 (45 tiles -> clusters of 3 use
+    // 135 SMs where a power of two would stop at 90).  Tiles are handed out dynamically from the per-step list of
+    // active tiles when there are more tiles than co-resident clusters; between sm_budget/2 and sm_budget tiles,
+    // clusters of 2 pulling from the list beat one CTA per tile as soon as some tiles have converged.
+    int R = sm_budget / (ntiles > 0 ? ntiles : 1);
+    if (R > want_r) R = want_r;
+    if (R > 16) R = 16;
+    if (R < 1) R = 1;
+    while (R > 1 && cap(R) < ntiles) R--;
+    int dyn = 0;
+    if (R == 1 && ntiles > cap(1)) dyn = 1;
+    else if (R == 1 && want_r >= 2 && 2 * ntiles > sm_budget && cap(2) >= 1) { R = 2; dyn = 1; }
     const char *ed = getenv("VMORPH_DYNAMIC");
-    int dyn = (R == 1 && ntiles > nclusters) ? 1 : 0;
-    if (ed) dyn = (atoi(ed) != 0 && R == 1) ? 1 : 0;
+    if (ed) { int f = atoi(ed) != 0; if (f != dyn) { dyn = f; if (!dyn) { while (R > 1 && cap(R) < ntiles) R--; } } }
+    int nclusters = ntiles < cap(R) ? ntiles : cap(R);
+    if (nclusters < 1) nclusters = 1;
+    if (!dyn && nclusters < ntiles && R > 1) { R = 1; nclusters = ntiles < cap(1) ? ntiles : cap(1); }   // static: tiles loop over clusters
     int list_off = (int)sweep_ctrl_words((int)ceilf(max_iter) + 1, 0);
     LevelView Lc = L; KParams Pc = P;
     cudaLaunchConfig_t lc = {};
@@ -801,7 +819,7 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
 //         CTAs per tile.  For levels with at most one tile per SM, where the dependent chain of one pixel's line
 //         search, not throughput, bounds the step.
 //   thr16 16 warps, 2 CTAs / SM;  thr8  8 warps, 3 CTAs / SM: sequential line search, for levels with many tiles.
-// Test hooks (read on every launch): VMORPH_CLUSTER=1/2/4/8 caps the cluster size, VMORPH_VARIANT=lat|thr16|thr8.
+// Test hooks (read on every launch): VMORPH_CLUSTER=1..16 caps the cluster size, VMORPH_DYNAMIC=0|1 forces the tile schedule, VMORPH_VARIANT=lat|thr16|thr8.
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
                          unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, int sm_budget, cudaStream_t stream) {
     const int gx = (L.w + OPT_BW * 2 + SPACING - 1) / (OPT_BW * 2 + SPACING);
@@ -809,6 +827,7 @@ cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTabl
     const int ntiles = gx * gy;
     const char *ec = getenv("VMORPH_CLUSTER"), *ev = getenv("VMORPH_VARIANT");
     int want_r = (ec && atoi(ec) > 0) ? atoi(ec) : 16;
+    if (want_r > 16) want_r = 16;
     if (sm_budget <= 0 || sm_budget > sm_count) sm_budget = sm_count;
     // levels with more tiles than SMs: the latency variant with dynamic tile hand-out (VMORPH_VARIANT=thr16|thr8 keep
     // the static many-CTAs-per-SM schedule for comparison)
