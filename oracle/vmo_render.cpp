@@ -71,11 +71,11 @@ void render_halfway(uint8_t *out, int rowstride, int w, int h, int ex, float col
 }
 
 // QuadraticPath.cpp:225-318 restated matrix-free on the 5-point operator assembled at 134-202.
-// D6 (vmo.h): cublasSdot's internal summation order is unspecified.  Here a dot product is DEFINED as: QP_LANES = 32768
+// D6 (vmo.h): cublasSdot's internal summation order is unspecified.  Here a dot product is DEFINED as: QP_LANES = 131072
 // lanes, lane t sums the exact products a[i]*b[i] of the elements i = t, t+QP_LANES, ... sequentially in f64; each group
-// of 256 consecutive lanes is reduced by a binary tree (stride 128, 64, ..., 1); the 128 group sums are added
+// of 1024 consecutive lanes is reduced by a binary tree (stride 512, 256, ..., 1); the 128 group sums are added
 // sequentially; the result is rounded to f32.  The CUDA path uses the same order, so both are bit-identical.
-static const int QP_LANES = 32768, QP_GROUP = 256;
+static const int QP_LANES = 131072, QP_GROUP = 1024;
 static float qp_dot(const float *a, const float *b, int N) {
     std::vector<double> lane(QP_LANES, 0.0);
 #pragma omp parallel for schedule(static)

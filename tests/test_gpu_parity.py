@@ -282,3 +282,33 @@ def test_qpath_parity(vm, oracle_lib, w, h, max_iter):
         q1, it1 = api.quadratic_path(vs[z], min(max_iter, 300), 1e-12)
         np.testing.assert_array_equal(qb[z], q1)
         assert list(itb[z]) == list(it1)
+
+
+@pytest.mark.parametrize("w,h,d,params", [
+    (20, 16, 1, dict(max_iter=30)),                               # smallest pyramid the schedule allows (3 levels)
+    (17, 40, 1, dict(max_iter=1)),                                # single sweep per level, tall image narrower than a warp
+    (70, 22, 1, dict(max_iter=20, ssim_clamp=0.3, eps=0.02)),     # width just past one tile column (69), clamp / eps variants
+    (96, 64, 1, dict(max_iter=25, w_tps=0.5, w_ssim=10.0, max_iter_drop_factor=1.5)),
+    (48, 36, 2, dict(max_iter=12, start_res=4)),                  # two frames: the forward chain is empty
+    (48, 36, 3, dict(max_iter=12, start_res=4, w_temp=100.0)),    # three frames: one frame per chain
+])
+def test_edge_shapes_and_parameters(vm, oracle_lib, w, h, d, params):
+    from videomorphing_b200 import synth
+    if d == 1:
+        v0, v1, _ = synth.image_pair(w, h, 500 + w, 600 + h, 2.0)
+        flows = None
+    else:
+        v0, v1, flows, _ = synth.video_pair(w, h, d, 61, 62, 2.0)
+    sr = int(params.get("start_res", 8))
+    o = oracle_lib.Oracle(params)
+    n = o.build(v0, v1, flows=flows)
+    pyr = vm.Pyramid(0)
+    assert pyr.build(v0, v1, flows, start_res=sr) == n
+    m = vm.Morph(vm.Parameters(**params), pyr)
+    o.run(); m.run()
+    np.testing.assert_array_equal(m.iters_log(), o.iters_log())
+    _assert_vec(m.get_vectors(), o.extract_vectors(), f"{w}x{h}x{d} {params}")
+    for fr in range(d):
+        flag = d > 1 and fr != pyr.info(1)["d"] // 2
+        eo, _ = o.energy(1, fr, flag); eg, _ = m.energy(1, fr, flag)
+        assert abs(eo - eg) <= TOL_ENERGY * max(abs(eo), 1e-12)

@@ -9,14 +9,14 @@
 // (they share the grid barriers); the search-direction update is fused into the operator application (p is
 // double-buffered, neighbours' new p is recomputed on the fly), so an iteration costs two grid barriers; scalars
 // (alpha, beta, r.r) are recomputed redundantly by every CTA from the per-CTA partial sums -- no host round trip.
-// Dot products follow the fixed lane / tree order of oracle deviation D6 (QP_LANES lanes, 256-lane binary trees,
+// Dot products follow the fixed lane / tree order of oracle deviation D6 (QP_LANES = 131072 lanes, 1024-lane binary trees,
 // sequential sum of the 128 group sums, f64), which makes the solve bit-reproducible and equal to the CPU oracle.
 #include "vm_device.cuh"
 #include "vm_host.h"
 
 namespace vm {
 
-constexpr int QP_BLOCKS = 128, QP_THREADS = 256, QP_LANES = QP_BLOCKS * QP_THREADS;
+constexpr int QP_BLOCKS = 128, QP_THREADS = 1024, QP_LANES = QP_BLOCKS * QP_THREADS;
 
 // QuadraticPath.cpp:31-111: blended Jacobian J* of one pixel (column-wise layout [0]=xx,[2]=yx,[1]=xy,[3]=yy)
 __global__ void k_qpath_jacobian(const float2 *__restrict__ V, float4 *__restrict__ J, int cols, int rows) {
