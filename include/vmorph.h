@@ -151,6 +151,12 @@ int vm_level_optimize(vm_morph *m, int level, float max_iter, void *stream);    
 /* Multi-GPU exact mode: the middle frame (morph.cu:1377-1391) plus the selected chains of Morph::optimize_level: bit 0 =
  * forward chain (morph.cu:1392-1415), bit 1 = backward chain (1416-1439).  chains == 3 is vm_level_optimize. */
 int vm_level_optimize_chains(vm_morph *m, int level, float max_iter, int chains, void *stream);
+/* upsample / initialize_level on the frame range [frame0, frame0+nframes) of a level only (the same kernels on a
+ * view of those pages).  Used by the multi-GPU level pipeline, where the rank that owns level l of one frame chain
+ * prolongs and initialises frame i as soon as the rank that owns level l+1 hands over its frame i.  Per-frame upsample
+ * requires depth(l) == depth(l+1) (no temporal in-fill, upsample.cu:286-339); VM_ERR_STATE otherwise. */
+int vm_level_upsample_frames(vm_morph *m, int dest_level, int frame0, int nframes, void *stream);
+int vm_level_initialize_frames(vm_morph *m, int level, int frame0, int nframes, void *stream);
 /* Device pointer + size of a level array (fields / layouts of vm_level_get) for P2P / NCCL exchanges done by the caller;
  * vm_level_mark_v_valid tells the library that level's v has been written that way (PyramidLevel::v is public in the
  * reference, Pyramid.h:78). */
@@ -160,6 +166,11 @@ int vm_level_mark_v_valid(vm_pyramid *p, int level);
 int vm_level_energy(vm_morph *m, int level, int frame, int flag, double *energy_out, double *terms_out);
 /* CMatchingThread::update_result (MatchingThread.cpp:22-84): level-1 v -> level-0 sized vectors, d0*h0*w0 float2 */
 int vm_morph_get_vectors(vm_morph *m, float *host_out, void *stream);
+/* the same at any level el that already holds a result -- what the UI's 1 s preview timer shows while the optimizer
+ * is still on a coarser level (el = Morph::_current_l, MatchingThread.cpp:27-28): spatial Resize to the level-0
+ * size, x (w0/w_el, h0/h_el), frames written at min(i*factor, d0-1) and the frames in between filled by the temporal
+ * lerp of MatchingThread.cpp:61-78; frames the reference leaves untouched are zero. */
+int vm_morph_get_vectors_level(vm_morph *m, int level, float *host_out, void *stream);
 /* stencil tables (stencils.h:13-19): iomask[5][5][5][5], improvmask[5][5][3][3], tps[5][5][5][5]; host arithmetic */
 int vm_stencils_get(int32_t *iomask625, int32_t *improvmask225, float *tps625);
 

@@ -69,6 +69,7 @@ def lib(native=False):
     L.vo_energy.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.vo_energy.restype = C.c_double
     L.vo_extract_vectors.argtypes = [C.c_void_p, _fp]
+    L.vo_extract_vectors_level.argtypes = [C.c_void_p, C.c_int, _fp]
     L.vo_executed_pixel_iters.argtypes = [C.c_void_p]
     L.vo_executed_pixel_iters.restype = C.c_double
     L.vo_iters_log.argtypes = [C.c_void_p, C.c_int, _ip]
@@ -229,10 +230,10 @@ class Oracle:
         e = self.L.vo_energy(self.h, l, frame, int(flag), t)
         return e, list(t)
 
-    def extract_vectors(self):
+    def extract_vectors(self, level=1):
         i = self.info(0)
         out = np.zeros((i["d"], i["h"], i["w"], 2), np.float32)
-        self.L.vo_extract_vectors(self.h, _ptr(out, _fp))
+        self.L.vo_extract_vectors_level(self.h, level, _ptr(out, _fp))
         return out
 
     @property

@@ -136,6 +136,7 @@ void optimize_level(Pyramid &P, int l, float max_iter);                     // m
 void run(Pyramid &P);                                                       // morph.cu:150-168
 double energy(const Pyramid &P, int l, int frame, bool flag, double *terms);
 void extract_vectors(const Pyramid &P, float *out);                         // MatchingThread.cpp:22-84
+void extract_vectors_level(const Pyramid &P, int el, float *out);           // the same at el = Morph::_current_l (live preview)
 
 // --- render / qpath ---
 void render_halfway(uint8_t *out, int rowstride, int w, int h, int ex, float color_fa, float geo_fa,

@@ -117,6 +117,7 @@ void vo_optimize_level(void *h, int l, float max_iter) { optimize_level(*static_
 void vo_run(void *h) { run(*static_cast<Pyramid *>(h)); }
 double vo_energy(void *h, int l, int frame, int flag, double *terms) { return energy(*static_cast<Pyramid *>(h), l, frame, flag != 0, terms); }
 void vo_extract_vectors(void *h, float *out) { extract_vectors(*static_cast<Pyramid *>(h), out); }
+void vo_extract_vectors_level(void *h, int el, float *out) { extract_vectors_level(*static_cast<Pyramid *>(h), el, out); }
 double vo_executed_pixel_iters(void *h) { return static_cast<Pyramid *>(h)->executed_pixel_iters; }
 int vo_iters_log(void *h, int max_triples, int *out) {
     Pyramid *P = static_cast<Pyramid *>(h);

@@ -934,8 +934,9 @@ static f2 bilinear_cpu(const f2 *img, int cols, int rows, float px, float py) {
     return r;
 }
 
-void extract_vectors(const Pyramid &P, float *out) {
-    const Level &L0 = P.lv[0]; const Level &L = P.lv[1];
+void extract_vectors(const Pyramid &P, float *out) { extract_vectors_level(P, 1, out); }
+void extract_vectors_level(const Pyramid &P, int el, float *out) {
+    const Level &L0 = P.lv[0]; const Level &L = P.lv[el];
     int factor = (int)(L0.factor_d / L.factor_d);
     float ratio_x = (float)L0.w / (float)L.w, ratio_y = (float)L0.h / (float)L.h;
     size_t fs0 = (size_t)L0.w * L0.h;

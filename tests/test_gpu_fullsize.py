@@ -77,9 +77,9 @@ def test_optimisation_lowers_energy_at_every_level(vm, oracle_lib):
         mi /= 2
 
 
-def _two_gpu_worker(rank, port, q):
+def _two_gpu_worker(rank, port, q, world=2):
     import os
-    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VMORPH_DIST_TIMEOUT_S="120")
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VMORPH_DIST_TIMEOUT_S="120")
     import torch
     import torch.distributed as dist
     import videomorphing_b200 as vm
@@ -91,7 +91,7 @@ def _two_gpu_worker(rank, port, q):
     pyr = vm.Pyramid(rank); pyr.build(v0, v1, flows, start_res=4)
     m = vm.Morph(prm, pyr)
     vd.optimize_video(m, pyr, prm, device=rank)
-    vec = m.get_vectors()
+    vec = m.get_vectors() if rank < 2 else None            # the level-1 owners hold the result
     dist.barrier()
     q.put((rank, vec, m.iters_log().copy()))
     dist.destroy_process_group()
@@ -130,3 +130,82 @@ def test_two_gpu_chain_split_is_bit_identical_to_one_gpu(vm):
             assert one[(int(l), int(f))] == int(i)
             both[(int(l), int(f))] = int(i)
     assert both == one
+
+
+def test_frame_by_frame_level_ops_match_the_whole_level_run(vm):
+    """vm_level_upsample_frames / vm_level_initialize_frames (the level pipeline's per-frame prolongation + initialisation)
+    in chain order on ONE GPU give the bits of the ordinary run: the schedule dist.run_pipeline spreads over GPUs."""
+    from videomorphing_b200 import dist as vd, synth
+    v0, v1, flows, field = synth.video_pair(96, 64, 9, 41, 42, 3.0)
+    prm = vm.Parameters(max_iter=24, start_res=4)
+    pyr = vm.Pyramid(0); n = pyr.build(v0, v1, flows, start_res=4)
+    # UI point pairs on several frames (level-0 pixel units, p.z = frame): exercises the per-frame UI splat
+    rng = np.random.Generator(np.random.PCG64(43))
+    k = 12
+    lp = np.stack([rng.integers(8, 88, k), rng.integers(8, 56, k), rng.integers(0, 9, k), np.ones(k, np.int64)], 1).astype(np.int32)
+    rp = lp.copy(); rp[:, 0] += rng.integers(-3, 4, k).astype(np.int32); rp[:, 1] += rng.integers(-3, 4, k).astype(np.int32)
+    cons = (lp, np.ones(k, np.float32), rp, np.ones(k, np.float32))
+    m = vm.Morph(prm, pyr)
+    m.set_constraints(*cons)
+    m.run()
+    ref, ref_log = m.get_vectors(), {(int(l), int(f)): int(i) for l, f, i in m.iters_log()}
+    depths = [pyr.info(l)["d"] for l in range(n)]
+    K = 1
+    while K < n - 2 and depths[K] == depths[K + 1]:
+        K += 1
+    assert K >= 3                                         # levels 1 .. K-1 take the frame-by-frame path (level K is prolonged as a whole)
+    m2 = vm.Morph(prm, pyr)
+    m2.set_constraints(*cons)
+    eng = vd.MorphEngine(m2, pyr, 0)
+    eng.coarse_solve()
+    mi = np.float32(24)
+    for l in range(n - 2, 0, -1):
+        if l >= K:
+            eng.upsample(l); eng.initialize(l); eng.optimize_chains(l, float(mi), 3)
+        else:
+            mid = depths[l] // 2
+            for dr in (0, 1):
+                for i in vd.chain_frames(depths[l], dr):
+                    if dr == 1 and i == mid:
+                        continue
+                    eng.upsample_frames(l, i); eng.initialize_frames(l, i)
+                    if i != mid:
+                        eng.init_temp(l, i, -1 if dr == 0 else 1)
+                    eng.optimize_frame(l, i, i != mid, float(mi))
+        mi = np.float32(mi / np.float32(2))
+    np.testing.assert_array_equal(m2.get_vectors(), ref)
+    assert {(int(l), int(f)): int(i) for l, f, i in m2.iters_log()} == ref_log
+
+
+def test_four_gpu_level_pipeline_is_bit_identical_to_one_gpu(vm):
+    # exact multi-GPU mode on 4 GPUs: direction x level pipeline (dist.pipeline_plan), frames handed on over NCCL
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs four CUDA devices")
+    from videomorphing_b200 import synth
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, port, q, 4)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = dict((r, (v, it)) for r, v, it in (q.get(timeout=300) for _ in range(4)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    v0, v1, flows, _ = synth.video_pair(96, 64, 9, 41, 42, 3.0)
+    prm = vm.Parameters(max_iter=24, start_res=4)
+    pyr = vm.Pyramid(0); pyr.build(v0, v1, flows, start_res=4)
+    m = vm.Morph(prm, pyr); m.run()
+    ref = m.get_vectors()
+    np.testing.assert_array_equal(res[0][0], ref)          # the two level-1 owners end with the whole field
+    np.testing.assert_array_equal(res[1][0], ref)
+    one = {(int(l), int(f)): int(i) for l, f, i in m.iters_log()}
+    allr = {}
+    for r in range(4):
+        for l, f, i in res[r][1]:
+            assert one[(int(l), int(f))] == int(i)
+            allr[(int(l), int(f))] = int(i)
+    assert allr == one                                     # together the four ranks ran every (level, frame) of the one-GPU log

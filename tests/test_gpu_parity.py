@@ -312,3 +312,23 @@ def test_edge_shapes_and_parameters(vm, oracle_lib, w, h, d, params):
         flag = d > 1 and fr != pyr.info(1)["d"] // 2
         eo, _ = o.energy(1, fr, flag); eg, _ = m.energy(1, fr, flag)
         assert abs(eo - eg) <= TOL_ENERGY * max(abs(eo), 1e-12)
+
+
+@pytest.mark.parametrize("w,h,d", [(48, 36, 16), (40, 24, 12)])
+def test_preview_extraction_at_every_level(vm, oracle_lib, w, h, d):
+    """update_result at el > 1 (the UI's live preview, MatchingThread.cpp:27-78): spatial Resize, x ratio, frames at
+    min(i*factor, d0-1) and the temporal lerp of the level-0 frames in between; bit-equal to the oracle."""
+    from videomorphing_b200 import synth
+    v0, v1, flows, _ = synth.video_pair(w, h, d, 71, 72, 2.0)
+    params = dict(max_iter=6, start_res=4)
+    o = oracle_lib.Oracle(params)
+    n = o.build(v0, v1, flows=flows)
+    pyr = vm.Pyramid(0)
+    assert pyr.build(v0, v1, flows, start_res=4) == n
+    m = vm.Morph(vm.Parameters(**params), pyr)
+    o.run(); m.run()
+    factors = set()
+    for l in range(1, n):
+        factors.add(int(pyr.info(0)["factor_d"] / pyr.info(l)["factor_d"]))
+        np.testing.assert_array_equal(m.get_vectors(level=l), o.extract_vectors(level=l), err_msg=f"level {l}")
+    assert max(factors) >= 2            # the temporal in-fill path was exercised

@@ -32,9 +32,13 @@ def main():
         dt = time.perf_counter() - t
         px = m.executed_pixel_iters
         px_all, t_max = vd.reduce_throughput(px, dt)
-        vec = m.get_vectors()
         if rank == 0:
-            print(json.dumps({"workload": f"{args.w}x{args.h}x{args.d} video pair, exact chains over {world} GPU(s)", "rep": rep, "optimize_s": t_max,
+            vec = m.get_vectors()
+            plan = vd.pipeline_plan([pyr.info(l)["d"] for l in range(pyr.num_levels)], world)
+            sched = ("direction x level pipeline, %d stages: " % plan["nstages"] + "; ".join(
+                "rank %d %s levels %s" % (r, "fwd" if e["dir"] == 0 else "bwd", e["levels"]) for r, e in sorted(plan["ranks"].items()))) \
+                if plan["nstages"] > 1 else ("one frame chain per rank" if world > 1 else "both chains on one GPU")
+            print(json.dumps({"workload": f"{args.w}x{args.h}x{args.d} video pair, exact mode over {world} GPU(s)", "schedule": sched, "rep": rep, "optimize_s": t_max,
                               "pixel_iters_all_ranks_incl_duplicate_mid_frames": px_all, "frames_per_s_optimize": args.d / t_max,
                               "checksum": float(np.abs(vec).sum())}), flush=True)
         m.close()

@@ -201,6 +201,12 @@ class Morph:
     def initialize_level(self, level, stream=None):
         check(self.L.vm_level_initialize(self.h, level, stream))
 
+    def upsample_frames(self, dest_level, frame0, nframes=1, stream=None):
+        check(self.L.vm_level_upsample_frames(self.h, dest_level, frame0, nframes, stream))
+
+    def initialize_frames(self, level, frame0, nframes=1, stream=None):
+        check(self.L.vm_level_initialize_frames(self.h, level, frame0, nframes, stream))
+
     def initialize_temp(self, level, frame, direction, stream=None):
         check(self.L.vm_level_init_temp(self.h, level, frame, direction, stream))
 
@@ -250,10 +256,11 @@ class Morph:
         n = check(self.L.vm_morph_iters_log(self.h, 65536, _vp(out)))
         return out[:3 * n].reshape(n, 3)
 
-    def get_vectors(self, stream=None):
+    def get_vectors(self, stream=None, level=1):
+        """CMatchingThread::update_result at el = level (1 = the final result; coarser levels = the live preview)."""
         i = self.pyramid.info(0)
         out = np.zeros((i["d"], i["h"], i["w"], 2), np.float32)
-        check(self.L.vm_morph_get_vectors(self.h, _vp(out), stream))
+        check(self.L.vm_morph_get_vectors_level(self.h, level, _vp(out), stream))
         return out
 
 

@@ -119,6 +119,21 @@ LevelView make_view(vm_pyramid *p, int level) {
     return V;
 }
 
+// The same level restricted to the pages [frame0, frame0 + nframes): every per-frame array starts at frame0's page and
+// d = nframes, so the per-level kernels (grid z = page) work on a frame range unchanged.
+LevelView make_frames_view(vm_pyramid *p, int level, int frame0, int nframes) {
+    LevelView V = make_view(p, level);
+    const size_t po = (size_t)frame0 * V.ps, io = (size_t)frame0 * V.ips, fo = (size_t)frame0 * V.w * V.h;
+    V.d = nframes;
+    V.v += po; V.mean += po; V.var += po; V.luma += po; V.tps_b += po; V.ui_b += po; V.temp_ref += po;
+    V.cross += po; V.value += po; V.counter += po; V.tps_axy += po; V.ui_axy += po; V.temp_mask += po;
+    V.impmask += io;
+    if (V.img0) V.img0 += fo;
+    if (V.img1) V.img1 += fo;
+    if (V.f0) { V.f0 += fo; V.f1 += fo; V.b0 += fo; V.b1 += fo; }
+    return V;
+}
+
 static KParams kparams(const vm_params &p) {
     KParams k; k.w_temp = p.w_temp; k.w_ui = p.w_ui; k.w_tps = p.w_tps; k.w_ssim = p.w_ssim; k.ssim_clamp = p.ssim_clamp; k.eps = p.eps; k.bcond = p.bcond;
     return k;
@@ -449,6 +464,48 @@ int vm_level_initialize(vm_morph *m, int level, void *stream) {
     return VM_OK;
 }
 
+// Frame-range variants of upsample / initialize_level for the multi-GPU level pipeline (videomorphing_b200/dist.py): a
+// rank that owns one level of one frame chain prolongs and initialises frame i as soon as the coarser level's frame i
+// arrives.  Same kernels on a view of the pages [frame0, frame0 + nframes); only levels without temporal in-fill
+// (same depth as the coarser level) can be prolonged frame by frame.
+int vm_level_upsample_frames(vm_morph *m, int dest_level, int frame0, int nframes, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    if (dest_level < 1 || dest_level + 1 >= (int)p->lv.size()) { set_error("bad upsample level %d", dest_level); return VM_ERR_ARG; }
+    Level &D = p->lv[dest_level]; Level &O = p->lv[dest_level + 1];
+    if (D.d != O.d) { set_error("level %d is temporally subsampled against level %d: no per-frame upsample", dest_level + 1, dest_level); return VM_ERR_STATE; }
+    if (frame0 < 0 || nframes < 1 || frame0 + nframes > D.d) { set_error("bad frame range %d+%d", frame0, nframes); return VM_ERR_ARG; }
+    int rc = use_device(p->device); if (rc) return rc;
+    VM_CUDA(cudaMemsetAsync(D.v.as<float2>() + (size_t)frame0 * D.ps, 0, sizeof(float2) * (size_t)D.ps * nframes, s));
+    LevelView V = make_frames_view(p, dest_level, frame0, nframes);
+    VM_CUDA(launch_upsample(V, O.v.as<float2>() + (size_t)frame0 * O.ps, O.w, O.h, O.rs, O.ps, nframes, 1, s));
+    D.v_valid = true;
+    return VM_OK;
+}
+
+int vm_level_initialize_frames(vm_morph *m, int level, int frame0, int nframes, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    if (level < 1 || level + 1 >= (int)p->lv.size()) { set_error("bad level %d", level); return VM_ERR_ARG; }
+    Level &L = p->lv[level];
+    if (!L.img0.p || !L.img1.p) { set_error("level %d has no images", level); return VM_ERR_STATE; }
+    if (frame0 < 0 || nframes < 1 || frame0 + nframes > L.d) { set_error("bad frame range %d+%d", frame0, nframes); return VM_ERR_ARG; }
+    int rc = use_device(p->device); if (rc) return rc;
+    LevelView V = make_frames_view(p, level, frame0, nframes);
+    size_t n = (size_t)L.ps * nframes;
+    VM_CUDA(cudaMemsetAsync(V.mean, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(V.var, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(V.luma, 0, 8 * n, s));
+    VM_CUDA(cudaMemsetAsync(V.cross, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(V.value, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(V.counter, 0, 4 * n, s));
+    VM_CUDA(cudaMemsetAsync(V.tps_axy, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(V.tps_b, 0, 8 * n, s));
+    VM_CUDA(cudaMemsetAsync(V.ui_axy, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(V.ui_b, 0, 8 * n, s));
+    VM_CUDA(cudaMemsetAsync(V.temp_ref, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(V.temp_mask, 0, 4 * n, s));
+    VM_CUDA(cudaMemsetAsync(V.impmask, 0, 4 * (size_t)L.ips * nframes, s));
+    VM_CUDA(launch_initialize_level(V, p->stencils.as<StencilTables>(), m->prm.ssim_clamp, s));
+    int factor = (int)(p->lv[0].factor_d / L.factor_d);
+    VM_CUDA(launch_ui_splat(V, m->cons_dev.as<Conn>(), (int)m->cons.size(), factor, p->lv[0].w, p->lv[0].h, p->lv[0].d, s, frame0));
+    p->state_level = level;
+    return VM_OK;
+}
+
 static int init_temp_chain(vm_morph *m, int level, int frame, int dir, cudaStream_t s, int chain);
 int vm_level_init_temp(vm_morph *m, int level, int frame, int dir, void *stream) { return init_temp_chain(m, level, frame, dir, (cudaStream_t)stream, 0); }
 static int init_temp_chain(vm_morph *m, int level, int frame, int dir, cudaStream_t stream, int chain) {
@@ -692,21 +749,22 @@ int vm_level_energy(vm_morph *m, int level, int frame, int flag, double *energy_
     return VM_OK;
 }
 
-int vm_morph_get_vectors(vm_morph *m, float *host_out, void *stream) {
+int vm_morph_get_vectors_level(vm_morph *m, int level, float *host_out, void *stream) {
     if (!m || !host_out) { set_error("null argument"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    if (level < 1 || level >= (int)p->lv.size()) { set_error("bad level %d", level); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
-    Level &L0 = p->lv[0]; Level &L1 = p->lv[1];
-    if (!L1.v_valid) { set_error("level 1 has no result yet"); return VM_ERR_STATE; }
-    int factor = (int)(L0.factor_d / L1.factor_d);
-    if (factor != 1) { set_error("level 1 is temporally subsampled (factor %d): unsupported", factor); return VM_ERR_STATE; }
+    Level &L0 = p->lv[0]; Level &L1 = p->lv[level];
+    if (!L1.v_valid) { set_error("level %d has no result yet", level); return VM_ERR_STATE; }
+    int factor = (int)(L0.factor_d / L1.factor_d);                                // MatchingThread.cpp:29
     size_t bytes = sizeof(float2) * (size_t)L0.w * L0.h * L0.d;
     DevBuf &out = m->extract_buf; VM_CUDA(out.ensure(bytes));
-    VM_CUDA(launch_extract(make_view(p, 1), out.as<float2>(), L0.w, L0.h, L0.d, factor, s));
+    VM_CUDA(launch_extract(make_view(p, level), out.as<float2>(), L0.w, L0.h, L0.d, factor, s));
     VM_CUDA(cudaMemcpyAsync(host_out, out.p, bytes, cudaMemcpyDeviceToHost, s));
     VM_CUDA(cudaStreamSynchronize(s));
     return VM_OK;
 }
+int vm_morph_get_vectors(vm_morph *m, float *host_out, void *stream) { return vm_morph_get_vectors_level(m, 1, host_out, stream); }
 
 // ---------------------------------------------------------------- render
 int vm_render_halfway_dev(uint8_t *out_dev, int rowstride, int w, int h, int ex, float color_fa, float geo_fa, int color_from,

@@ -116,6 +116,7 @@ struct vm_morph {
 namespace vm {
 
 LevelView make_view(vm_pyramid *p, int level);
+LevelView make_frames_view(vm_pyramid *p, int level, int frame0, int nframes);   // pages [frame0, frame0+nframes) as a level of depth nframes
 void free_resample_cache(vm_pyramid *p);
 
 // kernels (launchers) -- vm_kernels.cu / vm_sweep.cu / vm_render.cu / vm_resample.cu
@@ -125,7 +126,7 @@ size_t sweep_ctrl_words(int max_iter_ceil, int ntiles);
 int sweep_num_tiles(int w, int h);
 
 cudaError_t launch_initialize_level(const LevelView &L, const StencilTables *st, float ssim_clamp, cudaStream_t s);
-cudaError_t launch_ui_splat(const LevelView &L, const Conn *cons_dev, int ncons, int factor, int w0, int h0, int d0, cudaStream_t s);
+cudaError_t launch_ui_splat(const LevelView &L, const Conn *cons_dev, int ncons, int factor, int w0, int h0, int d0, cudaStream_t s, int z0 = 0);
 cudaError_t launch_upsample(const LevelView &dst, const float2 *src_v, int sw, int sh, int srs, int sps, int sd, int factor, cudaStream_t s);
 cudaError_t launch_temporal_infill(const LevelView &dst, long long *acc /*3*ps*/, float2 *vtmp /*ps*/, float *wtmp /*ps*/, cudaStream_t s);
 cudaError_t launch_initialize_temp(const LevelView &L, int frame, int dir, long long *acc /*3*ps*/, cudaStream_t s);

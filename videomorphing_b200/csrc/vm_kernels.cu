@@ -81,10 +81,11 @@ cudaError_t launch_initialize_level(const LevelView &L, const StencilTables *st,
 
 // UI splat (morph.cu:345-388): the reference copies v to the host and loops there.  One thread per frame walks the
 // connection list in order (same accumulation order), directly on the device arrays.
-__global__ void k_ui_splat(LevelView L, const Conn *__restrict__ cons, int ncons, int factor, int w0, int h0, int d0) {
+// (z0: frame number of the view's first page, for views that cover a frame range of the level)
+__global__ void k_ui_splat(LevelView L, const Conn *__restrict__ cons, int ncons, int factor, int w0, int h0, int d0, int z0) {
     int z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= L.d) return;
-    int conz = min(z * factor, d0 - 1);
+    int conz = min((z0 + z) * factor, d0 - 1);
     for (int k = 0; k < ncons; k++) {
         vm_conp l = cons[k].l, r = cons[k].r;
         if (conz != l.z) continue;                                  // left point's frame only (morph.cu:359)
@@ -109,9 +110,9 @@ __global__ void k_ui_splat(LevelView L, const Conn *__restrict__ cons, int ncons
     }
 }
 
-cudaError_t launch_ui_splat(const LevelView &L, const Conn *cons_dev, int ncons, int factor, int w0, int h0, int d0, cudaStream_t s) {
+cudaError_t launch_ui_splat(const LevelView &L, const Conn *cons_dev, int ncons, int factor, int w0, int h0, int d0, cudaStream_t s, int z0) {
     if (ncons <= 0) return cudaSuccess;
-    k_ui_splat<<<(L.d + 63) / 64, 64, 0, s>>>(L, cons_dev, ncons, factor, w0, h0, d0);
+    k_ui_splat<<<(L.d + 63) / 64, 64, 0, s>>>(L, cons_dev, ncons, factor, w0, h0, d0, z0);
     count_launch();
     return cudaGetLastError();
 }
@@ -468,7 +469,7 @@ cudaError_t launch_energy(const LevelView &L, const KParams &P, int frame, int f
 }
 
 // =====================================================================================================
-// CMatchingThread::update_result at el = 1 (MatchingThread.cpp:22-84) with Resize/BiLinear (86-136).
+// CMatchingThread::update_result at level el (MatchingThread.cpp:22-84) with Resize/BiLinear (86-136).
 // =====================================================================================================
 __global__ void k_extract(LevelView L, float2 *__restrict__ out, int w0, int h0, int d0, int factor) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, i = blockIdx.z;
@@ -492,11 +493,38 @@ __global__ void k_extract(LevelView L, float2 *__restrict__ out, int w0, int h0,
         float2 t = src[(size_t)y * L.rs + x];
         r = (ratio_x != 1 || ratio_y != 1) ? make_float2(t.x * ratio_x, t.y * ratio_y) : t;
     }
+    // two source frames clamped onto the last level-0 frame: the later one wins (the reference's loop order)
+    if (i + 1 < L.d && min(i * factor, d0 - 1) == min((i + 1) * factor, d0 - 1)) return;
     out[(size_t)min(i * factor, d0 - 1) * w0 * h0 + (size_t)y * w0 + x] = r;
 }
+// MatchingThread.cpp:61-78: the level-0 frames between two extracted frames are their temporal lerp.  One thread per
+// float2 of one in-between frame f = i*factor + k (blockIdx.y enumerates the (i, k) pairs); frames the reference skips
+// (f >= d0-1) and frames it never writes stay zero (the buffer is cleared first).
+__global__ void k_extract_lerp(float2 *__restrict__ out, size_t fs0, int d0, int d1, int factor) {
+    int pair = blockIdx.y, i = pair / (factor - 1), k = pair - i * (factor - 1) + 1;
+    if (i >= d1 - 1 || i * factor + k >= d0 - 1) return;
+    int beg = i * factor, end = min((i + 1) * factor, d0 - 1);
+    float fa = (float)k / (float)(end - beg);
+    const float2 *a = out + fs0 * beg, *b = out + fs0 * end;
+    float2 *dst = out + fs0 * (size_t)(i * factor + k);
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < fs0; q += (size_t)gridDim.x * blockDim.x) {
+        float2 va = a[q], vb = b[q];
+        dst[q] = make_float2(va.x * (1 - fa) + vb.x * fa, va.y * (1 - fa) + vb.y * fa);
+    }
+}
 cudaError_t launch_extract(const LevelView &L1, float2 *out, int w0, int h0, int d0, int factor, cudaStream_t s) {
+    size_t fs0 = (size_t)w0 * h0;
+    if (factor > 1) {
+        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float2) * fs0 * d0, s);
+        if (e != cudaSuccess) return e;
+    }
     k_extract<<<grid2(w0, h0, 32, 8, L1.d), dim3(32, 8), 0, s>>>(L1, out, w0, h0, d0, factor);
     count_launch();
+    if (factor > 1 && L1.d > 1) {
+        unsigned gx = (unsigned)((fs0 + 255) / 256); if (gx > 1184u) gx = 1184u;
+        k_extract_lerp<<<dim3(gx, (unsigned)((L1.d - 1) * (factor - 1))), 256, 0, s>>>(out, fs0, d0, L1.d, factor);
+        count_launch();
+    }
     return cudaGetLastError();
 }
 

@@ -125,7 +125,7 @@ def _exchange_pages(pyramid, level, my_pages, peer_pages, peer, device, stream=N
         torch.cuda.current_stream().synchronize()
 
 
-def optimize_video(morph, pyramid, params, device=0):
+def _optimize_video_two_chains(morph, pyramid, params, device=0):
     """Morph::calculate_halfway_parametrization (morph.cu:150-168) for a video with the two frame chains of every level on
     two GPUs (exact mode: the same arithmetic as one GPU, bit-identical result on ranks 0 and 1).
 
@@ -169,4 +169,175 @@ def optimize_video(morph, pyramid, params, device=0):
                     _lib.check(_lib.load().vm_level_mark_v_valid(pyramid.h, l))
                 torch.cuda.current_stream().synchronize()
         max_iter /= params.max_iter_drop_factor
+    return morph
+
+
+# ------------------------------------------------------------------------------------------ optimizer, level pipeline
+def pipeline_plan(depths, world):
+    """Exact-mode plan for `world` ranks (direction x level wavefront).
+
+    depths[l] = number of frames of pyramid level l (l = 0 .. n-1; levels 1 .. n-2 are optimised, n-1 is the dense solve).
+    Ranks come in pairs: rank = 2*pair + direction (0 = forward chain mid+1.., 1 = backward chain mid-1..0).
+    Pair 0 owns level 1, pair 1 level 2, ..., the last pair ("coarse") owns every remaining level: it runs them level by
+    level as on two GPUs (pages swapped with its partner per level) and streams the frames of its finest level out one
+    by one.  A pair that owns a single level receives frame i of the coarser level from the pair above (same
+    direction), prolongs + initialises + optimises its own frame i, and hands it on: level l of frame i only needs level
+    l+1 of frame i and level l of frame i -/+ 1, so the levels run as a wavefront behind each other.  A level can only be
+    streamed into when it has the depth of the level above (no temporal in-fill between them); that bounds the number
+    of stages.  Returns {"nstages", "ranks": {rank: {"pair", "dir", "levels", "recv_from", "send_to"}}}; ranks that
+    own nothing are absent."""
+    n = len(depths)
+    nopt = n - 2                                     # optimised levels 1 .. n-2
+    nst = 1
+    while nst < world // 2 and nst < nopt and depths[nst] == depths[nst + 1]:
+        nst += 1                                     # level `nst` may be streamed into from level nst+1
+    if world < 2 or nopt < 1:
+        nst = 1
+    ranks = {}
+    ndir = 2 if world >= 2 else 1
+    for pair in range(nst):
+        levels = [pair + 1] if pair < nst - 1 else list(range(nopt, pair, -1))       # coarse pair: n-2 .. nst
+        for dr in range(ndir):
+            r = 2 * pair + dr
+            ranks[r] = {"pair": pair, "dir": dr, "levels": levels,
+                        "recv_from": (r + 2) if pair < nst - 1 else None,
+                        "send_to": (r - 2) if pair > 0 else None}
+    return {"nstages": nst, "ranks": ranks}
+
+
+def chain_frames(d, direction):
+    """Frames of one chain in processing order, the middle frame first (morph.cu:1374-1439)."""
+    mid = d // 2
+    return [mid] + (list(range(mid + 1, d)) if direction == 0 else list(range(mid - 1, -1, -1)))
+
+
+class MorphEngine:
+    """The operations the level pipeline needs, on a vm.Morph / vm.Pyramid of this rank's GPU."""
+
+    def __init__(self, morph, pyramid, device):
+        self.m, self.p, self.device = morph, pyramid, device
+        from . import _lib
+        self._lib, self.L = _lib, _lib.load()
+        self.depths = [pyramid.info(l)["d"] for l in range(pyramid.num_levels)]
+
+    def coarse_solve(self): self.m.cpu_optimize_level()
+    def upsample(self, l): self.m.upsample(l)
+    def initialize(self, l): self.m.initialize_level(l)
+    def optimize_chains(self, l, max_iter, chains): self.m.optimize_chains(l, max_iter, chains)
+    def upsample_frames(self, l, i): self.m.upsample_frames(l, i, 1)
+    def initialize_frames(self, l, i): self.m.initialize_frames(l, i, 1)
+    def init_temp(self, l, i, direction): self.m.initialize_temp(l, i, direction)
+    def optimize_frame(self, l, i, flag, max_iter): return self.m.optimize_frame(l, i, flag, max_iter)
+
+    def _page(self, l):
+        base, _ = self.p.dev_ptr(l, "v")
+        return base, self.p.info(l)["pagestride"] * 8
+
+    def new_pages(self, l, n=1):
+        return torch.empty(n * self._page(l)[1], dtype=torch.uint8, device=f"cuda:{self.device}")
+
+    def get_pages(self, l, a, b):
+        """Copy of the `v` pages [a, b) of level l (one contiguous byte tensor on this GPU)."""
+        base, pb = self._page(l)
+        t = self.new_pages(l, b - a)
+        self._lib.check(self.L.vm_dev_copy(self.device, t.data_ptr(), base + a * pb, (b - a) * pb, None))
+        return t
+
+    def set_pages(self, l, a, t):
+        base, pb = self._page(l)
+        self._lib.check(self.L.vm_dev_copy(self.device, base + a * pb, t.data_ptr(), t.numel(), None))
+        self._lib.check(self.L.vm_level_mark_v_valid(self.p.h, l))
+
+    def sync(self):
+        torch.cuda.current_stream().synchronize()
+
+
+def _swap_pages(eng, l, mine, theirs, peer):
+    """Send this rank's pages `mine` = (a, b) of level l to `peer` and receive the peer's pages `theirs`."""
+    ops, rt = [], None
+    if mine[1] > mine[0]:
+        ops.append(dist.P2POp(dist.isend, eng.get_pages(l, *mine), peer))
+    if theirs[1] > theirs[0]:
+        rt = eng.new_pages(l, theirs[1] - theirs[0])
+        ops.append(dist.P2POp(dist.irecv, rt, peer))
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
+    if rt is not None:
+        eng.set_pages(l, theirs[0], rt)
+    eng.sync()
+
+
+def run_pipeline(eng, max_iter0, drop, rank, world):
+    """The level pipeline on one rank (see pipeline_plan).  `eng` is a MorphEngine (or, in the CPU tests, a stand-in with the
+    same methods).  Returns the plan; afterwards ranks 0 and 1 hold the complete level-1 field."""
+    depths = eng.depths
+    n = len(depths)
+    plan = pipeline_plan(depths, world)
+    me = plan["ranks"].get(rank)
+    if me is None:
+        return plan                                                      # this rank owns nothing
+    nst, dr = plan["nstages"], me["dir"]
+    partner = rank ^ 1 if world >= 2 else None
+    max_iter, mi = {}, np.float32(max_iter0)
+    for l in range(n - 2, 0, -1):                                        # morph.cu:163, float like the reference
+        max_iter[l] = float(mi)
+        mi = np.float32(mi / np.float32(drop))
+    sends = []
+
+    def stream_level(l, recv_from, send_to, prepared):
+        """One chain of level l frame by frame; `prepared`: the whole level is already prolonged and initialised."""
+        tdir = -1 if dr == 0 else 1                                      # the neighbour the temporal term looks at
+        for i in chain_frames(depths[l], dr):
+            if recv_from is not None:
+                t = eng.new_pages(l + 1)
+                dist.recv(t, recv_from)
+                eng.set_pages(l + 1, i, t)
+            if not prepared:
+                eng.upsample_frames(l, i)
+                eng.initialize_frames(l, i)
+            mid = i == depths[l] // 2
+            if not mid:
+                eng.init_temp(l, i, tdir)
+            eng.optimize_frame(l, i, not mid, max_iter[l])
+            if send_to is not None:
+                t = eng.get_pages(l, i, i + 1)
+                sends.append((t, dist.isend(t, send_to)))
+
+    if me["pair"] == nst - 1:                                            # coarse pair
+        eng.coarse_solve()
+        for l in me["levels"]:
+            eng.upsample(l)
+            eng.initialize(l)
+            d = depths[l]
+            mid = d // 2
+            if l == nst and nst > 1:
+                stream_level(l, None, me["send_to"], True)
+            else:
+                eng.optimize_chains(l, max_iter[l], 3 if partner is None else (1 << dr))
+                if partner is not None and d > 1:
+                    fwd, bwd = (mid + 1, d), (0, mid)
+                    _swap_pages(eng, l, fwd if dr == 0 else bwd, bwd if dr == 0 else fwd, partner)
+    else:
+        stream_level(me["levels"][0], me["recv_from"], me["send_to"], False)
+    for t, w in sends:
+        w.wait()
+    if me["pair"] == 0 and nst > 1 and partner is not None:              # both level-1 owners end with the whole field
+        d = depths[1]
+        mid = d // 2
+        fwd, bwd = (mid + 1, d), (0, mid)
+        _swap_pages(eng, 1, fwd if dr == 0 else bwd, bwd if dr == 0 else fwd, partner)
+    eng.sync()
+    return plan
+
+
+def optimize_video(morph, pyramid, params, device=0):
+    """Morph::calculate_halfway_parametrization (morph.cu:150-168) for a video on 1 .. 8 GPUs, exact mode (the same
+    arithmetic as one GPU; ranks 0 and 1 end with the bit-identical level-1 field).  2-3 ranks: one frame chain per rank.
+    4+ ranks: direction x level pipeline (pipeline_plan).  Every rank holds the whole pyramid, built from the same frames."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    depths = [pyramid.info(l)["d"] for l in range(pyramid.num_levels)]
+    if pipeline_plan(depths, world)["nstages"] < 2:
+        return _optimize_video_two_chains(morph, pyramid, params, device)
+    run_pipeline(MorphEngine(morph, pyramid, device), float(params.max_iter), float(params.max_iter_drop_factor), rank, world)
     return morph
