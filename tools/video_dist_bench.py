@@ -32,6 +32,11 @@ def main():
         dt = time.perf_counter() - t
         px = m.executed_pixel_iters
         px_all, t_max = vd.reduce_throughput(px, dt)
+        # device time this rank spent inside sweep launches (CUDA events around every k_sweep): which stage bounds the pipeline
+        busy = torch.tensor([m.sweep_time_ms()[0]], dtype=torch.float64, device="cuda")
+        busy_all = [torch.zeros_like(busy) for _ in range(world)]
+        if world > 1: dist.all_gather(busy_all, busy)
+        else: busy_all = [busy]
         if rank == 0:
             vec = m.get_vectors()
             plan = vd.pipeline_plan([pyr.info(l)["d"] for l in range(pyr.num_levels)], world)
@@ -40,6 +45,7 @@ def main():
                 if plan["nstages"] > 1 else ("one frame chain per rank" if world > 1 else "both chains on one GPU")
             print(json.dumps({"workload": f"{args.w}x{args.h}x{args.d} video pair, exact mode over {world} GPU(s)", "schedule": sched, "rep": rep, "optimize_s": t_max,
                               "pixel_iters_all_ranks_incl_duplicate_mid_frames": px_all, "frames_per_s_optimize": args.d / t_max,
+                              "sweep_busy_ms_per_rank": [round(float(b.item()), 1) for b in busy_all],
                               "checksum": float(np.abs(vec).sum())}), flush=True)
         m.close()
     if world > 1:

@@ -21,6 +21,7 @@
 #include "vm_device.cuh"
 #include "vm_host.h"
 #include <cooperative_groups.h>
+#include <cstdio>
 #include <cstring>
 #include <cstdlib>
 namespace cg = cooperative_groups;
@@ -774,21 +775,40 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
             if (cudaOccupancyMaxActiveClusters(&nc, kern, &qc) != cudaSuccess) { cudaGetLastError(); nc = 0; }
             cfg.max_clusters[R] = nc; cfg.queried[R] = true;
         }
+        // a launch that was given part of the GPU (two frame chains side by side) takes the same part of the clusters that
+        // can be co-resident: GPC boundaries make that fewer than SMs / R, and two launches that together ask for more
+        // than the GPU can hold run one after the other
         int by_budget = cfg.per_sm * sm_budget / R;
-        return cfg.max_clusters[R] < by_budget ? cfg.max_clusters[R] : by_budget;
+        int share = (int)((long long)cfg.max_clusters[R] * sm_budget / (sm_count > 0 ? sm_count : 1));
+        return share < by_budget ? share : by_budget;
     };
-    // Cluster size: as many CTAs (SMs) per tile as the budget allows, ANY size up to 16 (45 tiles -> clusters of 3 use
-    // 135 SMs where a power of two would stop at 90).  Tiles are handed out dynamically from the per-step list of
-    // active tiles when there are more tiles than co-resident clusters; between sm_budget/2 and sm_budget tiles,
-    // clusters of 2 pulling from the list beat one CTA per tile as soon as some tiles have converged.
-    int R = sm_budget / (ntiles > 0 ? ntiles : 1);
-    if (R > want_r) R = want_r;
-    if (R > 16) R = 16;
-    if (R < 1) R = 1;
-    while (R > 1 && cap(R) < ntiles) R--;
-    int dyn = 0;
-    if (R == 1 && ntiles > cap(1)) dyn = 1;
-    else if (R == 1 && want_r >= 2 && 2 * ntiles > sm_budget && cap(2) >= 1) { R = 2; dyn = 1; }
+    // Cluster size and tile schedule (measured per level on cfg2 / cfg3, profiles/r1_rdyn_*.txt):
+    //  * few tiles (6 * ntiles <= budget): every tile gets its own cluster of floor(budget / ntiles) CTAs, any size up to
+    //    16 (static schedule: tile t belongs to cluster t);
+    //  * more tiles: clusters of 2..6 CTAs PULL tiles from the per-step list of active tiles.  After the first dense
+    //    iterations most tiles have converged (1080p: 92 % of the tile steps are skipped) and the step time is the slowest
+    //    active tile's chain of pixels; a cluster finishes such a tile R times faster, and while every tile is still active
+    //    the clusters simply take several tiles each.  R = 2 + 2 * budget / ntiles, clamped to [2, 6]: 52 tiles -> 6,
+    //    91 -> 5, 200 -> 3, >= 296 -> 2 (best or within 3 % of the best measured size at every level).
+    int R, dyn = 0;
+    const int nt = ntiles > 0 ? ntiles : 1;
+    if (6 * nt <= sm_budget) {
+        R = sm_budget / nt;
+        if (R > want_r) R = want_r;
+        if (R > 16) R = 16;
+        if (R < 1) R = 1;
+        while (R > 1 && cap(R) < ntiles) R--;
+    } else {
+        R = 2 + 2 * sm_budget / nt;
+        if (R > 6) R = 6;
+        if (R > want_r) R = want_r;
+        if (R < 1) R = 1;
+        while (R > 1 && cap(R) < 1) R--;
+        dyn = ntiles > cap(R) ? 1 : 0;
+        if (!dyn) { R = sm_budget / nt; if (R > want_r) R = want_r; if (R < 1) R = 1; while (R > 1 && cap(R) < ntiles) R--; }
+    }
+    const char *er = getenv("VMORPH_R_DYN");          // experiment hook: clusters of this size pulling from the tile list
+    if (er && atoi(er) > 1 && atoi(er) <= 16 && cap(atoi(er)) >= 1 && ntiles > cap(atoi(er))) { R = atoi(er); dyn = 1; }
     const char *ed = getenv("VMORPH_DYNAMIC");
     if (ed) { int f = atoi(ed) != 0; if (f != dyn) { dyn = f; if (!dyn) { while (R > 1 && cap(R) < ntiles) R--; } } }
     int nclusters = ntiles < cap(R) ? ntiles : cap(R);
@@ -803,6 +823,8 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
     at[1].id = cudaLaunchAttributeClusterDimension; at[1].val.clusterDim.x = R; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = (R > 1) ? 2 : 1;
     count_launch();
+    if (getenv("VMORPH_LOG_LAUNCH"))
+        fprintf(stderr, "[vmorph] sweep %dx%d page %d: %d tiles, budget %d SMs -> %d clusters of %d, %s tiles\n", L.w, L.h, page, ntiles, sm_budget, nclusters, R, dyn ? "pulled" : "static");
     cudaError_t e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq, dyn, list_off);
     if (e != cudaSuccess && R > 1) {
         // cooperative + cluster attribute combination rejected: the grid is sized to be co-resident

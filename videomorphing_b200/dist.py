@@ -267,15 +267,36 @@ def _swap_pages(eng, l, mine, theirs, peer):
     eng.sync()
 
 
+_link_groups = {}
+
+
+def _links(plan, world):
+    """One 2-rank process group per hand-off link (downstream, upstream), created once per plan shape by ALL ranks in the
+    same order.  Separate groups keep a stage's receive from the level above and its send to the level below on
+    independent NCCL communicators / streams (P2P ops on one group are serialised in issue order)."""
+    key = (world, plan["nstages"])
+    if key not in _link_groups:
+        g = {}
+        for r in sorted(plan["ranks"]):
+            to = plan["ranks"][r]["send_to"]
+            if to is not None:
+                g[(to, r)] = dist.new_group([to, r])
+        _link_groups[key] = g
+    return _link_groups[key]
+
+
 def run_pipeline(eng, max_iter0, drop, rank, world):
     """The level pipeline on one rank (see pipeline_plan).  `eng` is a MorphEngine (or, in the CPU tests, a stand-in with the
     same methods).  Returns the plan; afterwards ranks 0 and 1 hold the complete level-1 field."""
     depths = eng.depths
     n = len(depths)
     plan = pipeline_plan(depths, world)
+    links = _links(plan, world) if plan["nstages"] > 1 else {}
     me = plan["ranks"].get(rank)
     if me is None:
         return plan                                                      # this rank owns nothing
+    g_up = links.get((rank, me["recv_from"]))
+    g_down = links.get((me["send_to"], rank))
     nst, dr = plan["nstages"], me["dir"]
     partner = rank ^ 1 if world >= 2 else None
     max_iter, mi = {}, np.float32(max_iter0)
@@ -290,7 +311,7 @@ def run_pipeline(eng, max_iter0, drop, rank, world):
         for i in chain_frames(depths[l], dr):
             if recv_from is not None:
                 t = eng.new_pages(l + 1)
-                dist.recv(t, recv_from)
+                dist.recv(t, recv_from, group=g_up)
                 eng.set_pages(l + 1, i, t)
             if not prepared:
                 eng.upsample_frames(l, i)
@@ -301,7 +322,7 @@ def run_pipeline(eng, max_iter0, drop, rank, world):
             eng.optimize_frame(l, i, not mid, max_iter[l])
             if send_to is not None:
                 t = eng.get_pages(l, i, i + 1)
-                sends.append((t, dist.isend(t, send_to)))
+                sends.append((t, dist.isend(t, send_to, group=g_down)))
 
     if me["pair"] == nst - 1:                                            # coarse pair
         eng.coarse_solve()
