@@ -186,6 +186,13 @@ int vm_render_halfway_dev(uint8_t *out_dev, int rowstride, int w, int h, int ex,
 int vm_render_halfway(int device, uint8_t *out, int w, int h, int ex, float color_fa, float geo_fa, int color_from,
                       const uint8_t *ext0, const uint8_t *ext1, const float *vector, const float *qpath, void *stream);
 
+/* The in-between sequence of one frame pair: what the reference does by calling RenderStage2 once per slider position
+ * / exported frame with the same four inputs (UI/RenderWidget.cpp:85-97,229-266), each call re-uploading them.  Here the
+ * inputs go up once; frame k (color_fa[k], geo_fa[k]) is rendered while frame k-1 is copied back.  out = nframes
+ * consecutive h*w*3 RGB8 frames (pinned memory makes the copies asynchronous). */
+int vm_render_sequence(int device, uint8_t *out, int nframes, int w, int h, int ex, const float *color_fa, const float *geo_fa,
+                       int color_from, const uint8_t *ext0, const uint8_t *ext1, const float *vector, const float *qpath, void *stream);
+
 /* ---- QuadraticPath (QuadraticPath.h:10-14, QuadraticPath.cpp:24-318) ---- */
 /* one frame: vector (w*h float2, host) -> qpath (w*h float2, host). max_iter=10000, tol=1e-12 reproduce the reference */
 int vm_qpath_optimize(int device, const float *vector, float *qpath, int w, int h, int max_iter, float tol, int *iters_out, void *stream);

@@ -332,3 +332,43 @@ def test_preview_extraction_at_every_level(vm, oracle_lib, w, h, d):
         factors.add(int(pyr.info(0)["factor_d"] / pyr.info(l)["factor_d"]))
         np.testing.assert_array_equal(m.get_vectors(level=l), o.extract_vectors(level=l), err_msg=f"level {l}")
     assert max(factors) >= 2            # the temporal in-fill path was exercised
+
+
+@pytest.mark.parametrize("w,h,amp,with_q", [
+    (151, 90, 5.0, True),        # odd width: no tensor map for the field pitch -> the global-memory kernel
+    (200, 120, 70.0, False),     # |v| up to 35 px: fetches leave the 16-px halo of the TMA window -> per-fetch global fallback
+    (96, 64, 3.0, True),         # two full 32x32 blocks high, partial blocks nowhere
+    (1280, 720, 8.0, False),     # BASELINE "morphed 720p frames/s" shape
+])
+def test_render_tma_window_and_fallbacks(vm, oracle_lib, w, h, amp, with_q, monkeypatch):
+    """k_render_halfway_tma (field window staged by TMA) == oracle == k_render_halfway (VMORPH_RENDER=plain), byte for byte."""
+    from videomorphing_b200 import synth
+    rgb0, rgb1, field = synth.image_pair(w, h, 161, 162, amp)
+    ex = int(max(w, h) * 0.1)
+    e0, e1 = synth.extended_rgba(rgb0[0], ex), synth.extended_rgba(rgb1[0], ex)
+    vec = (field / 2).astype(np.float32)
+    q = (np.random.Generator(np.random.PCG64(19)).standard_normal((h, w, 2)) * 0.5).astype(np.float32) if with_q else None
+    for fa in (0.0, 0.37, 1.0):
+        monkeypatch.delenv("VMORPH_RENDER", raising=False)
+        got = vm.render_halfway_image(w, h, ex, fa, fa, 1, e0, e1, vec, q)
+        monkeypatch.setenv("VMORPH_RENDER", "plain")
+        plain = vm.render_halfway_image(w, h, ex, fa, fa, 1, e0, e1, vec, q)
+        ref = oracle_lib.render_halfway(w, h, ex, fa, fa, 1, e0, e1, vec, q)[:, :w]
+        np.testing.assert_array_equal(got, ref)
+        np.testing.assert_array_equal(plain, ref)
+
+
+def test_render_sequence_equals_frame_by_frame(vm):
+    """vm_render_sequence (inputs uploaded once, double-buffered copy-back) == vm_render_halfway called once per frame."""
+    from videomorphing_b200 import synth
+    w, h = 320, 200
+    rgb0, rgb1, field = synth.image_pair(w, h, 171, 172, 6.0)
+    ex = int(max(w, h) * 0.1)
+    e0, e1 = synth.extended_rgba(rgb0[0], ex), synth.extended_rgba(rgb1[0], ex)
+    vec = (field / 2).astype(np.float32)
+    ts = [float(synth.smoothstep(k / 6)) for k in range(7)]
+    seq = vm.render_sequence(w, h, ex, ts, ts, 1, e0, e1, vec)
+    assert seq.shape == (7, h, w, 3)
+    for k, t in enumerate(ts):
+        np.testing.assert_array_equal(seq[k], vm.render_halfway_image(w, h, ex, t, t, 1, e0, e1, vec), err_msg=f"frame {k}")
+    assert not np.array_equal(seq[0], seq[-1])

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--max-iter", type=int, default=1000)
     ap.add_argument("--qpath", action="store_true"); ap.add_argument("--qpath-iter", type=int, default=10000)
     ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--pinned", action="store_true", help="keep the input frames / flows in page-locked host memory")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--cpu-frames", type=int, default=0, help="also time the CPU oracle on the first N frames (all levels) for the ratio")
     args = ap.parse_args()
@@ -24,6 +25,11 @@ def main():
     t = time.time()
     v0, v1, flows, field = synth.video_pair(args.w, args.h, args.d, 4001, 4002, 8.0)
     t_synth = time.time() - t
+    if args.pinned:                        # page-locked inputs: Pyramid::build's H2D copies run at PCIe speed instead of through the pageable staging path
+        import torch
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        v0, v1 = pin(v0), pin(v1)
+        flows = tuple(pin(f) for f in flows)
     L = vm._lib.load()
     pyr = vm.Pyramid(args.device)
     out = {}

@@ -5,4 +5,4 @@ libvmorph.so (include/vmorph.h).  Importing it does not need a GPU; every comput
 """
 from . import _lib  # noqa: F401
 from .api import (BCOND_BORDER, BCOND_CORNER, BCOND_NONE, REFERENCE_VOXEL_CAP, Morph, Parameters, Pyramid,  # noqa: F401
-                  level_schedule, quadratic_path, render_halfway_image, stencils)
+                  level_schedule, quadratic_path, render_halfway_image, render_sequence, stencils)

@@ -43,7 +43,7 @@ EXPORTS = [
     "vm_morph_set_tracks", "vm_morph_set_constraints", "vm_morph_run", "vm_morph_progress", "vm_morph_executed_pixel_iters",
     "vm_morph_sweep_ms", "vm_morph_ms_log", "vm_morph_iters_log", "vm_level_cpu_solve", "vm_level_upsample", "vm_level_initialize", "vm_level_init_temp", "vm_level_upsample_frames", "vm_level_initialize_frames",
     "vm_level_optimize_frame", "vm_level_optimize", "vm_level_optimize_chains", "vm_level_dev_ptr", "vm_level_mark_v_valid", "vm_dev_copy", "vm_level_energy", "vm_morph_get_vectors", "vm_morph_get_vectors_level", "vm_stencils_get",
-    "vm_render_halfway_dev", "vm_render_halfway", "vm_qpath_optimize", "vm_qpath_optimize_frames", "vm_dev_alloc", "vm_dev_free", "vm_dev_upload",
+    "vm_render_halfway_dev", "vm_render_halfway", "vm_render_sequence", "vm_qpath_optimize", "vm_qpath_optimize_frames", "vm_dev_alloc", "vm_dev_free", "vm_dev_upload",
     "vm_dev_download", "vm_stream_sync", "vm_kernel_launch_count", "vm_selftest_exact_arith",
 ]
 
@@ -105,6 +105,7 @@ def load():
     L.vm_stencils_get.argtypes = [vp, vp, vp]
     L.vm_render_halfway_dev.argtypes = [vp, i32, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, vp]
     L.vm_render_halfway.argtypes = [i32, vp, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, vp]
+    L.vm_render_sequence.argtypes = [i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp]
     L.vm_qpath_optimize.argtypes = [i32, vp, vp, i32, i32, i32, f32, C.POINTER(i32), vp]
     L.vm_qpath_optimize_frames.argtypes = [i32, vp, vp, i32, i32, i32, i32, f32, vp, vp]
     L.vm_dev_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp)]

@@ -276,6 +276,24 @@ def render_halfway_image(w, h, ex, color_fa, geo_fa, color_from, ext0, ext1, vec
     return out
 
 
+def render_sequence(w, h, ex, color_fa, geo_fa, color_from, ext0, ext1, vector, qpath=None, device=0, stream=None, out=None):
+    """The in-between frames of one pair (RenderStage2 once per t, UI/RenderWidget.cpp:85-97): inputs uploaded once, frames
+    streamed back while the next one renders.  color_fa / geo_fa: one value per frame.  Returns (n,h,w,3) uint8."""
+    cf = np.ascontiguousarray(color_fa, np.float32)
+    gf = np.ascontiguousarray(geo_fa, np.float32)
+    n = len(cf)
+    assert len(gf) == n and n >= 1
+    ext0 = np.ascontiguousarray(ext0, np.uint8)
+    ext1 = np.ascontiguousarray(ext1, np.uint8)
+    vector = np.ascontiguousarray(vector, np.float32)
+    qp = np.ascontiguousarray(qpath, np.float32) if qpath is not None else None
+    if out is None:
+        out = np.zeros((n, h, w, 3), np.uint8)
+    check(_lib.load().vm_render_sequence(device, _vp(out), n, w, h, ex, _vp(cf), _vp(gf), int(color_from),
+                                         _vp(ext0), _vp(ext1), _vp(vector), _vp(qp), stream))
+    return out
+
+
 def parse_config_xml(path):
     """parse_config_xml (param_io.h:8) for the live settings.xml schema (UI/MdiEditor.cpp:566-749): returns Parameters with
     lp / rp as lists of tracks of (x, y, frame, keyflag, weight) and cnt as lists of groups of (li_track, li_idx, ri_track, ri_idx)."""

@@ -805,6 +805,48 @@ int vm_render_halfway(int device, uint8_t *out, int w, int h, int ex, float colo
     return VM_OK;
 }
 
+// The in-between sequence of ONE frame pair (RenderWidget's slider / export loop calls RenderStage2 once per t with the
+// same images and vectors, UI/RenderWidget.cpp:85-97,229-266): inputs are uploaded once, frame k is rendered while frame
+// k-1 travels back (two device output buffers, copy stream + events).
+namespace { struct SeqScratch { cudaStream_t copy = nullptr; cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr}; DevBuf o2; }; SeqScratch g_seq[16]; }
+
+int vm_render_sequence(int device, uint8_t *out, int nframes, int w, int h, int ex, const float *color_fa, const float *geo_fa, int color_from,
+                       const uint8_t *ext0, const uint8_t *ext1, const float *vector, const float *qpath, void *stream) {
+    if (!out || !ext0 || !ext1 || !vector || !color_fa || !geo_fa || nframes < 1 || w <= 0 || h <= 0 || ex < 0) { set_error("bad render arguments"); return VM_ERR_ARG; }
+    int rc = use_device(device); if (rc) return rc;
+    if (device >= 16) { set_error("device %d: at most 16 devices", device); return VM_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rowstride = (w + 31) / 32 * 32;
+    size_t eb = (size_t)(w + 2 * ex) * (h + 2 * ex) * 4, vb = sizeof(float2) * (size_t)w * h, ob = (size_t)rowstride * h * 3, fb = (size_t)w * h * 3;
+    std::lock_guard<std::mutex> lock(g_render_mu);
+    RenderScratch &R = g_render[device]; SeqScratch &Q = g_seq[device];
+    if (R.e0.bytes < eb || R.e1.bytes < eb || R.v.bytes < vb || R.o.bytes < ob || Q.o2.bytes < ob || (qpath && R.q.bytes < vb)) VM_CUDA(cudaDeviceSynchronize());
+    VM_CUDA(R.e0.ensure(eb)); VM_CUDA(R.e1.ensure(eb)); VM_CUDA(R.v.ensure(vb)); VM_CUDA(R.o.ensure(ob)); VM_CUDA(Q.o2.ensure(ob));
+    if (!Q.copy) {
+        VM_CUDA(cudaStreamCreateWithFlags(&Q.copy, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) { VM_CUDA(cudaEventCreateWithFlags(&Q.rendered[k], cudaEventDisableTiming)); VM_CUDA(cudaEventCreateWithFlags(&Q.copied[k], cudaEventDisableTiming)); }
+    }
+    VM_CUDA(cudaMemcpyAsync(R.e0.p, ext0, eb, cudaMemcpyHostToDevice, s));
+    VM_CUDA(cudaMemcpyAsync(R.e1.p, ext1, eb, cudaMemcpyHostToDevice, s));
+    VM_CUDA(cudaMemcpyAsync(R.v.p, vector, vb, cudaMemcpyHostToDevice, s));
+    if (qpath) { VM_CUDA(R.q.ensure(vb)); VM_CUDA(cudaMemcpyAsync(R.q.p, qpath, vb, cudaMemcpyHostToDevice, s)); }
+    uint8_t *ob2[2] = {R.o.as<uint8_t>(), Q.o2.as<uint8_t>()};
+    for (int k = 0; k < nframes; k++) {
+        int b = k & 1;
+        if (k >= 2) VM_CUDA(cudaStreamWaitEvent(s, Q.copied[b], 0));                       // buffer b has left the device
+        rc = vm_render_halfway_dev(ob2[b], rowstride, w, h, ex, color_fa[k], geo_fa[k], color_from, R.e0.as<uint8_t>(), R.e1.as<uint8_t>(),
+                                   R.v.as<float>(), qpath ? R.q.as<float>() : nullptr, stream);
+        if (rc) return rc;
+        VM_CUDA(cudaEventRecord(Q.rendered[b], s));
+        VM_CUDA(cudaStreamWaitEvent(Q.copy, Q.rendered[b], 0));
+        VM_CUDA(cudaMemcpy2DAsync(out + (size_t)k * fb, (size_t)w * 3, ob2[b], (size_t)rowstride * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, Q.copy));
+        VM_CUDA(cudaEventRecord(Q.copied[b], Q.copy));
+    }
+    VM_CUDA(cudaStreamSynchronize(Q.copy));
+    VM_CUDA(cudaStreamSynchronize(s));
+    return VM_OK;
+}
+
 // ---------------------------------------------------------------- diagnostics
 int vm_selftest_exact_arith(int device, uint64_t n_div, uint64_t *mismatches3) {
     if (!mismatches3) { set_error("null out"); return VM_ERR_ARG; }

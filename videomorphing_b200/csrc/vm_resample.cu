@@ -233,74 +233,116 @@ __global__ void __launch_bounds__(128) k_filter_cols(const float *__restrict__ i
 }
 
 // dlti.cpp:133-171 solve_columns: one thread per column, in place.  CURVE: lrgb2srgb of every sample first (scale.cpp:77-83).
+// The recurrence x_i -= l_i * x_{i-1} is sequential per column (and stays so: a parallel scan would round differently),
+// but only the multiply-subtract is on the chain: each thread fetches TC_U rows ahead (independent coalesced loads) and
+// evaluates the sRGB curve of those samples (double-precision det_powf) before it walks them, so load latency and the
+// curve overlap across the unrolled rows instead of sitting between two links of the chain.
+constexpr int TC_U = 8;
 template <bool CURVE>
 __global__ void __launch_bounds__(128) k_tridiag_cols(float *planes, int h, int w, const float *__restrict__ l,
                                                       const float *__restrict__ u, const float *__restrict__ dinv) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= w) return;
     float *c = planes + (size_t)blockIdx.y * h * w + j;
-    float prev = c[0];
-    if (CURVE) { prev = srgb_curve(prev); c[0] = prev; }
-    for (int i = 1; i < h; i++) {
-        float x = c[(size_t)i * w];
-        if (CURVE) x = srgb_curve(x);
-        x -= __ldg(l + i) * prev;
-        c[(size_t)i * w] = x;
-        prev = x;
+    float prev = 0.f;
+    for (int i0 = 0; i0 < h; i0 += TC_U) {
+        float x[TC_U];
+#pragma unroll
+        for (int k = 0; k < TC_U; k++) if (i0 + k < h) x[k] = c[(size_t)(i0 + k) * w];
+        if (CURVE) {
+#pragma unroll
+            for (int k = 0; k < TC_U; k++) if (i0 + k < h) x[k] = srgb_curve(x[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < TC_U; k++)
+            if (i0 + k < h) {
+                if (i0 + k > 0) x[k] -= __ldg(l + i0 + k) * prev;
+                prev = x[k];
+            }
+#pragma unroll
+        for (int k = 0; k < TC_U; k++) if (i0 + k < h) c[(size_t)(i0 + k) * w] = x[k];
     }
     float next = 0.f;
-    for (int i = h - 1; i >= 0; i--) {
-        float x = c[(size_t)i * w];
-        if (i + 1 < h) x -= __ldg(u + i) * next;
-        x *= __ldg(dinv + i);
-        c[(size_t)i * w] = x;
-        next = x;
+    for (int i1 = h - 1; i1 >= 0; i1 -= TC_U) {
+        float x[TC_U];
+#pragma unroll
+        for (int k = 0; k < TC_U; k++) if (i1 - k >= 0) x[k] = c[(size_t)(i1 - k) * w];
+#pragma unroll
+        for (int k = 0; k < TC_U; k++)
+            if (i1 - k >= 0) {
+                int i = i1 - k;
+                if (i + 1 < h) x[k] -= __ldg(u + i) * next;
+                x[k] *= __ldg(dinv + i);
+                next = x[k];
+            }
+#pragma unroll
+        for (int k = 0; k < TC_U; k++) if (i1 - k >= 0) c[(size_t)(i1 - k) * w] = x[k];
     }
 }
 
-// dlti.cpp:98-128 solve_rows: one warp per 32 lines; 32x32 tiles staged (transposed access) through shared memory so
-// that global traffic is coalesced while lane r walks line r sequentially.
+// dlti.cpp:98-128 solve_rows: a block of TR_LINES threads owns TR_LINES lines.  32-column chunks are staged through a
+// padded shared-memory tile: warps load / store whole 128-byte line segments (coalesced; the sRGB curve is applied
+// here, in parallel over the whole block), then thread r walks the 32 samples of line r (bank-conflict free).
+constexpr int TR_LINES = 128;
 template <bool CURVE>
-__global__ void __launch_bounds__(32) k_tridiag_rows(float *planes, long long nlines, int w, const float *__restrict__ l,
-                                                     const float *__restrict__ u, const float *__restrict__ dinv) {
-    __shared__ float tile[32][33];
-    const int lane = threadIdx.x;
-    const long long line0 = (long long)blockIdx.x * 32;
-    const int nl = (int)min((long long)32, nlines - line0);
+__global__ void __launch_bounds__(TR_LINES) k_tridiag_rows(float *planes, long long nlines, int w, const float *__restrict__ l,
+                                                           const float *__restrict__ u, const float *__restrict__ dinv) {
+    __shared__ float tile[TR_LINES][33];
+    __shared__ float sc[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = TR_LINES / 32;
+    const long long line0 = (long long)blockIdx.x * TR_LINES;
+    const int nl = (int)min((long long)TR_LINES, nlines - line0);
     float *base = planes + line0 * w;
     float carry = 0.f;
     for (int c0 = 0; c0 < w; c0 += 32) {
-        int nc = min(32, w - c0);
-        for (int r = 0; r < nl; r++) if (lane < nc) tile[r][lane] = base[(size_t)r * w + c0 + lane];
-        __syncwarp();
-        if (lane < nl)
+        const int nc = min(32, w - c0);
+        if (lane < nc) {
+#pragma unroll 4
+            for (int r = warp; r < nl; r += NWARP) {
+                float x = base[(size_t)r * w + c0 + lane];
+                tile[r][lane] = CURVE ? srgb_curve(x) : x;
+            }
+        }
+        if (tid < nc) sc[0][tid] = __ldg(l + c0 + tid);
+        __syncthreads();
+        if (tid < nl) {
+#pragma unroll 8
             for (int c = 0; c < nc; c++) {
-                float x = tile[lane][c];
-                if (CURVE) x = srgb_curve(x);
-                if (c0 + c > 0) x -= __ldg(l + c0 + c) * carry;
-                tile[lane][c] = x;
+                float x = tile[tid][c];
+                if (c0 + c > 0) x -= sc[0][c] * carry;
+                tile[tid][c] = x;
                 carry = x;
             }
-        __syncwarp();
-        for (int r = 0; r < nl; r++) if (lane < nc) base[(size_t)r * w + c0 + lane] = tile[r][lane];
-        __syncwarp();
+        }
+        __syncthreads();
+        if (lane < nc)
+            for (int r = warp; r < nl; r += NWARP) base[(size_t)r * w + c0 + lane] = tile[r][lane];
+        __syncthreads();
     }
-    int last0 = ((w - 1) / 32) * 32;
+    const int last0 = ((w - 1) / 32) * 32;
     for (int c0 = last0; c0 >= 0; c0 -= 32) {
-        int nc = min(32, w - c0);
-        for (int r = 0; r < nl; r++) if (lane < nc) tile[r][lane] = base[(size_t)r * w + c0 + lane];
-        __syncwarp();
-        if (lane < nl)
+        const int nc = min(32, w - c0);
+        if (lane < nc) {
+#pragma unroll 4
+            for (int r = warp; r < nl; r += NWARP) tile[r][lane] = base[(size_t)r * w + c0 + lane];
+        }
+        if (tid < nc) { sc[0][tid] = __ldg(u + c0 + tid); sc[1][tid] = __ldg(dinv + c0 + tid); }
+        __syncthreads();
+        if (tid < nl) {
+#pragma unroll 8
             for (int c = nc - 1; c >= 0; c--) {
-                float x = tile[lane][c];
-                if (c0 + c + 1 < w) x -= __ldg(u + c0 + c) * carry;
-                x *= __ldg(dinv + c0 + c);
-                tile[lane][c] = x;
+                float x = tile[tid][c];
+                if (c0 + c + 1 < w) x -= sc[0][c] * carry;
+                x *= sc[1][c];
+                tile[tid][c] = x;
                 carry = x;
             }
-        __syncwarp();
-        for (int r = 0; r < nl; r++) if (lane < nc) base[(size_t)r * w + c0 + lane] = tile[r][lane];
-        __syncwarp();
+        }
+        __syncthreads();
+        if (lane < nc)
+            for (int r = warp; r < nl; r += NWARP) base[(size_t)r * w + c0 + lane] = tile[r][lane];
+        __syncthreads();
     }
 }
 
@@ -415,9 +457,9 @@ struct Resampler {
     void prefilter_rows(float *pl, int np, int h, int w, bool curve) {
         const TridiagDev *t = tri(w); if (!t) return;
         long long nlines = (long long)np * h;
-        unsigned blocks = (unsigned)((nlines + 31) / 32);
-        if (curve) k_tridiag_rows<true><<<blocks, 32, 0, s>>>(pl, nlines, w, t->l.as<float>(), t->u.as<float>(), t->dinv.as<float>());
-        else k_tridiag_rows<false><<<blocks, 32, 0, s>>>(pl, nlines, w, t->l.as<float>(), t->u.as<float>(), t->dinv.as<float>());
+        unsigned blocks = (unsigned)((nlines + TR_LINES - 1) / TR_LINES);
+        if (curve) k_tridiag_rows<true><<<blocks, TR_LINES, 0, s>>>(pl, nlines, w, t->l.as<float>(), t->u.as<float>(), t->dinv.as<float>());
+        else k_tridiag_rows<false><<<blocks, TR_LINES, 0, s>>>(pl, nlines, w, t->l.as<float>(), t->u.as<float>(), t->dinv.as<float>());
         count_launch();
     }
     void prefilter_cols(float *pl, int np, int h, int w, bool curve) {
