@@ -8,7 +8,8 @@ from videomorphing_b200 import synth
 
 NAMES = {0: "tile-skip test", 1: "LoadSSIM", 2: "filter+queue", 3: "compute loop total", 4: "cluster/cta sync after compute",
          5: "commit B + syncs", 6: "SaveSSIM", 7: "grid barrier", 8: "pixel setup loads", 9: "gradient (4 evals)",
-         10: "fold-over", 11: "golden section", 12: "commit A"}
+         10: "fold-over", 11: "golden section", 12: "commit A",
+         16: "commit A (mask bits, accepted rows) + vote", 17: "commit B gather + UpdateSSIM"}
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 w, h, d, s1, s2, amp = synth.CONFIGS[cfg]
 rgb0, rgb1, field = synth.image_pair(w, h, s1, s2, amp)
@@ -18,7 +19,7 @@ n = pyr.build(rgb0, rgb1)
 m = vm.Morph(vm.Parameters(), pyr)
 if cfg == "cfg2":
     m.set_constraints(*synth.point_pairs(20, w, h, 2003, field))
-buf = (C.c_ulonglong * 32)()
+buf = (C.c_ulonglong * 64)()
 for rep in range(2):
     m.cpu_optimize_level()
     mi = 1000.0
@@ -29,10 +30,10 @@ for rep in range(2):
         L.vm_debug_trace(buf, 0)
         i = pyr.info(l)
         if rep == 1:
-            tot = sum(buf[k] for k in (0, 1, 2, 3, 4, 5, 6, 7))
+            tot = sum(buf[k] for k in (0, 1, 2, 3, 4, 5, 6, 7, 16, 17))
             print(f"level {l} {i['w']}x{i['h']} iters={it}: CTA0/thread0 cycles total {tot/1e6:.1f} M")
             print(f"   tile steps executed {buf[13]} skipped {buf[14]}; active pixels per executed sub-phase {buf[15] / max(1, buf[31]):.1f}")
-            for k in range(13):
-                if buf[16 + k]:
-                    print(f"   {NAMES[k]:32s} {buf[k]/1e6:9.2f} Mcyc  n={buf[16+k]:8d}  avg={buf[k]/buf[16+k]:9.0f}")
+            for k in list(range(13)) + [16, 17]:
+                if buf[32 + k]:
+                    print(f"   {NAMES[k]:32s} {buf[k]/1e6:9.2f} Mcyc  n={buf[32+k]:8d}  avg={buf[k]/buf[32+k]:9.0f}")
         mi /= 2

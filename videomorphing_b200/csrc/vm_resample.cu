@@ -18,6 +18,7 @@
 #include <map>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 namespace vm {
@@ -283,8 +284,7 @@ __global__ void __launch_bounds__(128) k_tridiag_cols(float *planes, int h, int 
 // dlti.cpp:98-128 solve_rows: a block of TR_LINES threads owns TR_LINES lines.  32-column chunks are staged through a
 // padded shared-memory tile: warps load / store whole 128-byte line segments (coalesced; the sRGB curve is applied
 // here, in parallel over the whole block), then thread r walks the 32 samples of line r (bank-conflict free).
-constexpr int TR_LINES = 128;
-template <bool CURVE>
+template <bool CURVE, int TR_LINES>
 __global__ void __launch_bounds__(TR_LINES) k_tridiag_rows(float *planes, long long nlines, int w, const float *__restrict__ l,
                                                            const float *__restrict__ u, const float *__restrict__ dinv) {
     __shared__ float tile[TR_LINES][33];
@@ -457,9 +457,11 @@ struct Resampler {
     void prefilter_rows(float *pl, int np, int h, int w, bool curve) {
         const TridiagDev *t = tri(w); if (!t) return;
         long long nlines = (long long)np * h;
-        unsigned blocks = (unsigned)((nlines + TR_LINES - 1) / TR_LINES);
-        if (curve) k_tridiag_rows<true><<<blocks, TR_LINES, 0, s>>>(pl, nlines, w, t->l.as<float>(), t->u.as<float>(), t->dinv.as<float>());
-        else k_tridiag_rows<false><<<blocks, TR_LINES, 0, s>>>(pl, nlines, w, t->l.as<float>(), t->u.as<float>(), t->dinv.as<float>());
+        // one warp per 32 lines: a row is one sequential chain, so the parallelism is the number of independent blocks
+        // (128 lines per block measured slower or equal at every frame count: profiles/r1_kernel_tables.md)
+        unsigned blocks = (unsigned)((nlines + 31) / 32);
+        if (curve) k_tridiag_rows<true, 32><<<blocks, 32, 0, s>>>(pl, nlines, w, t->l.as<float>(), t->u.as<float>(), t->dinv.as<float>());
+        else k_tridiag_rows<false, 32><<<blocks, 32, 0, s>>>(pl, nlines, w, t->l.as<float>(), t->u.as<float>(), t->dinv.as<float>());
         count_launch();
     }
     void prefilter_cols(float *pl, int np, int h, int w, bool curve) {

@@ -31,9 +31,9 @@ namespace vm {
 // Development-only phase timing (built into libvmorph_trace.so with -DVM_TRACE; never in libvmorph.so):
 // cycle counts of CTA 0 / warp 0 accumulated per phase of tile_step.
 #ifdef VM_TRACE
-__device__ unsigned long long g_trace[32];
+__device__ unsigned long long g_trace[64];      // [k] cycles, [32 + k] counts (k < 24); [13..15], [31] plain counters
 #define TR_DECL long long tr_t0 = clock64()
-#define TR(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t1 = clock64(); atomicAdd(&g_trace[k], (unsigned long long)(t1 - tr_t0)); atomicAdd(&g_trace[16 + (k)], 1ull); tr_t0 = t1; } else tr_t0 = clock64(); } while (0)
+#define TR(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t1 = clock64(); atomicAdd(&g_trace[k], (unsigned long long)(t1 - tr_t0)); atomicAdd(&g_trace[32 + (k)], 1ull); tr_t0 = t1; } else tr_t0 = clock64(); } while (0)
 #else
 #define TR_DECL
 #define TR(k)
@@ -66,6 +66,7 @@ struct SweepSmem {
     unsigned int mask[MASK_W * MASK_H];  // improving-mask words around the tile (see tile_step)
     float tps[25 * 25];
     unsigned int iomask[25];
+    unsigned int improv[25 * 9];         // improving-mask check stencil (stencils.cpp:90-118), [oy*5+ox][i*3+j]
     int cta_improving;
 };
 
@@ -411,7 +412,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                 if (px >= 0 && px < L.w && py >= 0 && py < L.h) {
                     int bx = px / 5, by = py / 5, oxx = px - bx * 5, oyy = py - by * 5;
                     int begi = oyy >= 2 ? 1 : 0, begj = oxx >= 2 ? 1 : 0;
-                    const unsigned *imp = st->improv[oyy * 5 + oxx];
+                    const unsigned *imp = &S.improv[(oyy * 5 + oxx) * 9];
                     int lx = bx + 1 - mcx0, ly = by + 1 - mcy0;           // this pixel's cell inside the replica
                     bool hit = false;
 #pragma unroll
@@ -419,7 +420,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             int ii = begi + i, jj = begj + j;
-                            hit |= (S.mask[(ly + ii - 1) * MASK_W + (lx + jj - 1)] & __ldg(imp + ii * 3 + jj)) != 0u;
+                            hit |= (S.mask[(ly + ii - 1) * MASK_W + (lx + jj - 1)] & imp[ii * 3 + jj]) != 0u;
                         }
                     if (hit) { stt = 1; act = !pixel_on_border(L, P.bcond, px, py); }
                     S.bcls[tid] = (unsigned char)(border_class(py, L.h) * 5 + border_class(px, L.w));
@@ -543,7 +544,11 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             //      (morph.cu:973-987,1006-1015,1258-1279).  Contributors in row-major order of the source pixel.
             //      Every CTA of a cluster repeats the whole gather on its own replica: dealing the cells out to the CTAs and
             //      broadcasting the results through distributed shared memory was measured slower (profiles/, trace6).
-            if (__syncthreads_or(any)) {
+            //      The gather is instruction-issue bound, not latency bound (every CTA runs ~350 instructions for each of up
+            //      to 1 360 cells): a branch-free / batched-UpdateSSIM rewrite measured the same time (trace7, profiles/).
+            const int any_acc = __syncthreads_or(any);
+            TR(16);
+            if (any_acc) {
                 dirty = true;
                 for (int cc = tid; cc < rcells; cc += NT) {
                     int ry = cc / rw, sy = ry0 + ry, sx = rx0 + (cc - ry * rw);
@@ -593,6 +598,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                     if (ch_t) S.tpsb[c] = tb;
                 }
             }
+            TR(17);
             phase++;
             __syncthreads();
             TR(5);
@@ -658,6 +664,7 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
     const int R = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     for (int k = tid; k < 625; k += NW * 32) S.tps[k] = (&st->tps[0][0])[k];
     if (tid < 25) S.iomask[tid] = st->iomask[tid];
+    for (int k = tid; k < 225; k += NW * 32) S.improv[k] = (&st->improv[0][0])[k];
     if (tid < NPIX) { S.slot[0].acc[tid] = 0; S.slot[1].acc[tid] = 0; }
     __syncthreads();
     if (R > 1) cluster.sync();          // slot buffers of every CTA are initialised before any remote write
@@ -868,8 +875,8 @@ int sweep_num_tiles(int w, int h) {
 #ifdef VM_TRACE
 extern "C" int vm_debug_trace(unsigned long long *out32, int reset) {
     cudaDeviceSynchronize();
-    if (out32) cudaMemcpyFromSymbol(out32, g_trace, sizeof(unsigned long long) * 32);
-    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_trace, z, sizeof(z)); }
+    if (out32) cudaMemcpyFromSymbol(out32, g_trace, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_trace, z, sizeof(z)); }
     return 0;
 }
 #endif
