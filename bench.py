@@ -115,8 +115,14 @@ def oracle_run(name, rank, threads=None):
     subprocess.run(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), "liboracle_native.so"], check=True, stdout=subprocess.DEVNULL)
     L = po.lib(native=True)
     L.vo_num_threads.restype = C.c_int
-    if threads:
-        L.vo_set_num_threads(int(threads))
+    if not threads:
+        # all host threads this process may use: torchrun exports OMP_NUM_THREADS=1 for its workers, which would silently
+        # turn the CPU arm into a single-thread run
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    L.vo_set_num_threads(int(threads))
     nthreads = L.vo_num_threads()
     w, h, rgb0, rgb1, cons = workload_inputs(name, rank)
     o = po.Oracle(native=True)
