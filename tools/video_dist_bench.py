@@ -1,5 +1,6 @@
-"""Video optimizer in exact multi-GPU mode (forward chain on rank 0, backward chain on rank 1, v pages swapped per level).
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port P tools/video_dist_bench.py --width 1280 --height 720 --frames 120
+"""Video optimizer in exact multi-GPU mode (dist.optimize_video): 2 ranks = one frame chain per rank, `v` halves swapped per
+level; 4+ ranks = direction x level pipeline (frames handed from level to level over NCCL send / recv).
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P tools/video_dist_bench.py --width 1280 --height 720 --frames 120
 With one process it runs the single-GPU schedule (both chains concurrently on two streams)."""
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

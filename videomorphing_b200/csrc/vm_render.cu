@@ -99,14 +99,14 @@ __global__ void __launch_bounds__(RB_W *RB_H) k_render_halfway(uint8_t *__restri
 // TMA-staged variant (the production path when the vector field's pitch allows a tensor map).
 //
 // The 21 dependent bilinear fetches of the fixed-point inversion land within a few pixels of the output pixel (|p - q| <=
-// |s1| |v| + |s2| |u|), so a block of 32 x 32 output pixels keeps the field window [x0-16, x0+48) x [y0-16, y0+48)
+// |s1| |v| + |s2| |u|), so a block of 32 x 16 output pixels keeps the field window [x0-16, x0+48) x [y0-16, y0+32)
 // in shared memory: ONE cp.async.bulk.tensor (TMA) box per field, issued by one thread, completion on an mbarrier.  Out
 // of image parts of the box are zero-filled by the TMA unit and never read (indices are clamped to the image first,
 // exactly like the global-memory fetch); a fetch whose 2x2 footprint leaves the window falls back to global memory with
 // the same arithmetic, so results are bit-identical to k_render_halfway for any field.  The loop then runs on 64-bit
 // shared-memory loads with 32-bit addressing instead of four 64-bit-addressed global loads per fetch.
 // =====================================================================================================
-constexpr int RT_W = 32, RT_H = 32, RT_HALO = 16, RT_WW = RT_W + 2 * RT_HALO, RT_WH = RT_H + 2 * RT_HALO;
+constexpr int RT_W = 32, RT_H = 16, RT_HALO = 16, RT_WW = RT_W + 2 * RT_HALO, RT_WH = RT_H + 2 * RT_HALO;
 
 __device__ __forceinline__ float2 tex2d2_win(const float2 *__restrict__ img, const float2 *win, int wx0, int wy0, int w, int h, float x, float y) {
     float xb = x - 0.5f, yb = y - 0.5f;
@@ -136,12 +136,53 @@ __device__ __forceinline__ float2 tex2d2_win(const float2 *__restrict__ img, con
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2 process the .x/.y pair of a float2 in one instruction) -----------
+// Every operation is a correctly rounded IEEE add / multiply of each half, i.e. exactly what the scalar code does per
+// component.  There is no packed multiply instruction: a * b is issued as fma(a, b, -0.0), which is exact (x + -0.0 == x
+// for every x including +-0).  ptxas contracts "fma(a, b, <constant -0.0>) followed by an add" into ONE fused FFMA2 (even
+// with .rn and --fmad=false), which would round differently from the reference arithmetic; the -0.0 therefore comes from a
+// kernel argument the compiler cannot see through, and the SASS is checked for the absence of any other FFMA2 addend.
+typedef unsigned long long f2x;
+__device__ __forceinline__ f2x pk2(float lo, float hi) { f2x r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2x pk2(float2 v) { return pk2(v.x, v.y); }
+__device__ __forceinline__ float2 unpk2(f2x v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f2x add2(f2x a, f2x b) { f2x r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2x sub2(f2x a, f2x b) { f2x r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2x mul2(f2x a, f2x b, f2x negzero) { f2x r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(negzero)); return r; }
+
+// tex2d2_win with the bilinear blend of the .x/.y pair in packed arithmetic; xy = (x, y) sample position, packed
+__device__ __forceinline__ f2x tex2d2_win_pk(const float2 *__restrict__ img, const float2 *win, int wx0, int wy0, int w, int h, f2x xy, f2x half, f2x nz) {
+    float2 xyb = unpk2(sub2(xy, half));                                   // x - 0.5f, y - 0.5f
+    float xb = minf_std(maxf_std(xyb.x, -1.0f), (float)w);
+    float yb = minf_std(maxf_std(xyb.y, -1.0f), (float)h);
+    float fx0 = floorf(xb), fy0 = floorf(yb);
+    float2 ab = unpk2(sub2(pk2(xb, yb), pk2(fx0, fy0)));                  // a = xb - fx0, b = yb - fy0
+    int i = (int)fx0, j = (int)fy0;
+    int i0 = min(max(i, 0), w - 1), i1 = min(max(i + 1, 0), w - 1);
+    int j0 = min(max(j, 0), h - 1), j1 = min(max(j + 1, 0), h - 1);
+    const int li0 = i0 - wx0, li1 = i1 - wx0, lj0 = j0 - wy0, lj1 = j1 - wy0;
+    f2x t00, t10, t01, t11;
+    if (li0 >= 0 && li1 < RT_WW && lj0 >= 0 && lj1 < RT_WH) {
+        const f2x *wp = reinterpret_cast<const f2x *>(win);
+        t00 = wp[lj0 * RT_WW + li0]; t10 = wp[lj0 * RT_WW + li1];
+        t01 = wp[lj1 * RT_WW + li0]; t11 = wp[lj1 * RT_WW + li1];
+    } else {
+        const f2x *gp = reinterpret_cast<const f2x *>(img);
+        t00 = __ldg(gp + j0 * w + i0); t10 = __ldg(gp + j0 * w + i1);
+        t01 = __ldg(gp + j1 * w + i0); t11 = __ldg(gp + j1 * w + i1);
+    }
+    const f2x A = pk2(ab.x, ab.x), Bq = pk2(ab.y, ab.y);
+    f2x top = add2(t00, mul2(A, sub2(t10, t00), nz));                     // t00 + a * (t10 - t00), both components
+    f2x bot = add2(t01, mul2(A, sub2(t11, t01), nz));
+    return add2(top, mul2(Bq, sub2(bot, top), nz));                       // top + b * (bot - top)
+}
+
 template <bool HAS_Q>
-__global__ void __launch_bounds__(RT_W *RT_H, 2) k_render_halfway_tma(uint8_t *__restrict__ out, int rowstride, int w, int h, int ex,
+__global__ void __launch_bounds__(RT_W *RT_H, 3) k_render_halfway_tma(uint8_t *__restrict__ out, int rowstride, int w, int h, int ex,
                                                                      float color_fa, float geo_fa, int color_from,
                                                                      const uchar4 *__restrict__ ext0, const uchar4 *__restrict__ ext1,
                                                                      const float2 *__restrict__ V, const float2 *__restrict__ Q,
-                                                                     const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapQ) {
+                                                                     const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapQ, float negzero) {
     extern __shared__ __align__(128) unsigned char rt_smem[];
     float2 *winV = reinterpret_cast<float2 *>(rt_smem);
     float2 *winQ = winV + (HAS_Q ? RT_WW * RT_WH : 0);
@@ -176,18 +217,23 @@ __global__ void __launch_bounds__(RT_W *RT_H, 2) k_render_halfway_tma(uint8_t *_
     if (px < w && py < h) {
         const float alpha = 0.8f;
         const float s1 = 2 * geo_fa - 1, s2 = 4 * geo_fa - 4 * geo_fa * geo_fa;     // render.cu:34
-        float2 q = make_float2((float)px, (float)py), p = q;
-        float2 v = tex2d2_win(V, winV, wx0, wy0, w, h, p.x + 0.5f, p.y + 0.5f);
-        float2 u = HAS_Q ? tex2d2_win(Q, winQ, wx0, wy0, w, h, p.x + 0.5f, p.y + 0.5f) : make_float2(0.f, 0.f);
+        // the loop of render.cu:36-40 on packed (.x, .y) pairs: same operations, same order, one instruction per pair
+        const f2x nz = pk2(negzero, negzero), half = pk2(0.5f, 0.5f);
+        const f2x S1 = pk2(s1, s1), S2 = pk2(s2, s2), AL = pk2(alpha, alpha), BE = pk2(1 - alpha, 1 - alpha);
+        const f2x qq = pk2((float)px, (float)py);
+        f2x pp = qq;
+        f2x vv = tex2d2_win_pk(V, winV, wx0, wy0, w, h, add2(pp, half), half, nz);
+        f2x uu = HAS_Q ? tex2d2_win_pk(Q, winQ, wx0, wy0, w, h, add2(pp, half), half, nz) : pk2(0.f, 0.f);
 #pragma unroll 1
         for (int i = 0; i < 20; i++) {
-            p.x = q.x - s1 * v.x - s2 * u.x;
-            p.y = q.y - s1 * v.y - s2 * u.y;
-            float2 tv = tex2d2_win(V, winV, wx0, wy0, w, h, p.x + 0.5f, p.y + 0.5f);
-            v = make_float2(alpha * tv.x + (1 - alpha) * v.x, alpha * tv.y + (1 - alpha) * v.y);
-            float2 tu = HAS_Q ? tex2d2_win(Q, winQ, wx0, wy0, w, h, p.x + 0.5f, p.y + 0.5f) : make_float2(0.f, 0.f);
-            u = make_float2(alpha * tu.x + (1 - alpha) * u.x, alpha * tu.y + (1 - alpha) * u.y);
+            pp = sub2(sub2(qq, mul2(S1, vv, nz)), mul2(S2, uu, nz));                                  // p = q - s1 * v - s2 * u
+            const f2x at = add2(pp, half);
+            f2x tv = tex2d2_win_pk(V, winV, wx0, wy0, w, h, at, half, nz);
+            vv = add2(mul2(AL, tv, nz), mul2(BE, vv, nz));                                           // alpha * tv + (1 - alpha) * v
+            f2x tu = HAS_Q ? tex2d2_win_pk(Q, winQ, wx0, wy0, w, h, at, half, nz) : pk2(0.f, 0.f);
+            uu = add2(mul2(AL, tu, nz), mul2(BE, uu, nz));
         }
+        const float2 p = unpk2(pp), v = unpk2(vv);
         float3 c0 = tex_rgba8(ext0, ew, eh, p.x - v.x + ex + 0.5f, p.y - v.y + ex + 0.5f);     // render.cu:41
         float3 c1 = tex_rgba8(ext1, ew, eh, p.x + v.x + ex + 0.5f, p.y + v.y + ex + 0.5f);     // render.cu:42
         float3 c;
@@ -260,10 +306,10 @@ cudaError_t launch_render(uint8_t *out, int rowstride, int w, int h, int ex, flo
         }
         if (qpath)
             k_render_halfway_tma<true><<<g, b, smem, s>>>(out, rowstride, w, h, ex, color_fa, geo_fa, color_from, reinterpret_cast<const uchar4 *>(ext0),
-                                                          reinterpret_cast<const uchar4 *>(ext1), vec, qpath, mv, mq);
+                                                          reinterpret_cast<const uchar4 *>(ext1), vec, qpath, mv, mq, -0.0f);
         else
             k_render_halfway_tma<false><<<g, b, smem, s>>>(out, rowstride, w, h, ex, color_fa, geo_fa, color_from, reinterpret_cast<const uchar4 *>(ext0),
-                                                           reinterpret_cast<const uchar4 *>(ext1), vec, qpath, mv, mq);
+                                                           reinterpret_cast<const uchar4 *>(ext1), vec, qpath, mv, mq, -0.0f);
         count_launch();
         return cudaGetLastError();
     }

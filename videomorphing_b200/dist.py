@@ -5,7 +5,10 @@ What shards on this path:
   * the frame-parallel stages of a video (pyramid image levels, render, QuadraticPath) split into contiguous frame
     blocks, no exchange; results are gathered only when one host wants all frames;
   * the optimizer is two sequential frame chains per level (forward / backward from the middle frame,
-    morph.cu:1374-1439): at most two ranks can own a chain each; they exchange their halves of `v` once per level.
+    morph.cu:1374-1439).  Exact mode (same arithmetic as one GPU): with 2-3 ranks each chain gets a rank and the ranks swap
+    their halves of `v` once per level; with 4+ ranks the levels of a chain additionally run as a wavefront on different
+    ranks (pipeline_plan / run_pipeline): frame i of level l+1 is handed to the rank that owns level l as soon as it is
+    final -- NCCL send / recv of one `v` page per frame and link, no collective.
 No collective is used unless a stage really exchanges data; timing reductions are scalar (MAX of seconds, SUM of units).
 """
 import datetime
