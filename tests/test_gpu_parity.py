@@ -372,3 +372,36 @@ def test_render_sequence_equals_frame_by_frame(vm):
     for k, t in enumerate(ts):
         np.testing.assert_array_equal(seq[k], vm.render_halfway_image(w, h, ex, t, t, 1, e0, e1, vec), err_msg=f"frame {k}")
     assert not np.array_equal(seq[0], seq[-1])
+
+
+@pytest.mark.parametrize("w,h,d,start_res,cap", [(130, 100, 1, 8, 4000), (64, 48, 12, 4, 12000)])
+def test_voxel_capped_run_and_resize_parity(vm, oracle_lib, w, h, d, start_res, cap):
+    """The reference's voxel cap (pyramid.cu:223-226: level 1 is smaller than the frames) end to end: UI constraints given
+    in level-0 pixels land on the down-sampled levels, update_result resizes level 1 back to the frame size
+    (MatchingThread.cpp:31-57, Resize / BiLinear) -- vectors, iteration log and energies equal the oracle's."""
+    from videomorphing_b200 import synth
+    if d == 1:
+        v0, v1, field = synth.image_pair(w, h, 300 + w, 400 + h, 3.0)
+        flows = None
+        cons = synth.point_pairs(5, w, h, 77, field, margin=10)
+    else:
+        v0, v1, flows, _ = synth.video_pair(w, h, d, 51, 52, 3.0)
+        rng = np.random.Generator(np.random.PCG64(78))
+        k = 8
+        lp = np.stack([rng.integers(6, w - 6, k), rng.integers(6, h - 6, k), rng.integers(0, d, k), np.ones(k, np.int64)], 1).astype(np.int32)
+        rp = lp.copy(); rp[:, 0] += rng.integers(-2, 3, k).astype(np.int32); rp[:, 1] += rng.integers(-2, 3, k).astype(np.int32)
+        cons = (lp, np.ones(k, np.float32), rp, np.ones(k, np.float32))
+    params = dict(max_iter=16, start_res=start_res)
+    o = oracle_lib.Oracle(params)
+    n = o.build(v0, v1, flows=flows, voxel_cap=cap)
+    pyr = vm.Pyramid(0)
+    assert pyr.build(v0, v1, flows, start_res=start_res, voxel_cap=cap) == n
+    assert pyr.info(1)["w"] < w and pyr.info(1)["h"] < h            # the cap really shrank level 1
+    m = vm.Morph(vm.Parameters(**params), pyr)
+    o.set_constraints(*cons); m.set_constraints(*cons)
+    o.run(); m.run()
+    np.testing.assert_array_equal(m.iters_log(), o.iters_log())
+    got, ref = m.get_vectors(), o.extract_vectors()
+    assert got.shape == (d, h, w, 2)
+    _assert_vec(got, ref, f"capped {w}x{h}x{d}")
+    np.testing.assert_array_equal(got, ref)
