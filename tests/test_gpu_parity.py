@@ -405,3 +405,24 @@ def test_voxel_capped_run_and_resize_parity(vm, oracle_lib, w, h, d, start_res, 
     assert got.shape == (d, h, w, 2)
     _assert_vec(got, ref, f"capped {w}x{h}x{d}")
     np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("w,h,max_iter", [(640, 360, 80), (1280, 720, 40), (1000, 1047, 25), (1100, 1000, 12)])
+def test_qpath_resident_and_streaming_kernels_agree(vm, oracle_lib, w, h, max_iter, monkeypatch):
+    """k_qpath_cg_res (r / p of the own lanes in shared memory, x / Ap in registers; frames up to 8 x 131072 unknowns) ==
+    k_qpath_cg (everything through global memory; VMORPH_QPATH=global, and automatically above that size) == oracle:
+    several lane steps per thread, a partial last step, run ends in the middle of rows."""
+    from videomorphing_b200 import api
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    rng = np.random.Generator(np.random.PCG64(w + 3 * h))
+    v = np.stack([3 * np.sin(xx / 37) * np.cos(yy / 29), 2.5 * np.cos(xx / 41 + yy / 23)], -1).astype(np.float32)
+    v += (rng.standard_normal(v.shape) * 0.01).astype(np.float32)
+    monkeypatch.delenv("VMORPH_QPATH", raising=False)
+    q_auto, it_auto = api.quadratic_path(v, max_iter, 1e-12)
+    monkeypatch.setenv("VMORPH_QPATH", "global")
+    q_glob, it_glob = api.quadratic_path(v, max_iter, 1e-12)
+    assert list(it_auto) == list(it_glob)
+    np.testing.assert_array_equal(q_auto, q_glob)
+    qo, ito = oracle_lib.qpath_optimize(v, max_iter, 1e-12)
+    assert list(it_auto) == list(ito)
+    np.testing.assert_array_equal(q_auto, qo)

@@ -13,6 +13,8 @@
 // sequential sum of the 128 group sums, f64), which makes the solve bit-reproducible and equal to the CPU oracle.
 #include "vm_device.cuh"
 #include "vm_host.h"
+#include <cstring>
+#include <cstdlib>
 
 namespace vm {
 
@@ -181,6 +183,204 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg(float *X0, float *X1, f
     if (blockIdx.x == 0 && threadIdx.x == 0) { iters_out[0] = k[0]; iters_out[1] = k[1]; }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Resident variant (frames of up to QP_MAXK * QP_LANES unknowns, e.g. 1280x720): the same iteration, the same fixed dot
+// order, but every CTA keeps the r and p of ITS lanes' pixels in shared memory and x / A p in registers for the whole
+// solve.  Lane t owns the pixels t, t + QP_LANES, ...; the 1024 lanes of a CTA own one contiguous run of 1024 pixels per
+// step k, so left / right neighbours are in shared memory and only the rows above / below (other CTAs' pixels) are read
+// from global memory -- their new search direction is recomputed from the r and p_old their owners published, like in
+// k_qpath_cg, so no third grid barrier is needed.  Global traffic per unknown and iteration: 4 loads + 2 stores instead
+// of 14 loads + 4 stores.  Both systems share each block reduction (intra-warp levels by shuffle, same pairing as the
+// D6 tree) and their group sums are added by two threads side by side.
+constexpr int QP_MAXK = 8;
+struct QpResSmem {
+    float p[2][QP_MAXK][QP_THREADS];       // current search direction of the own pixels
+    float r[2][QP_MAXK][QP_THREADS];       // residual
+    float x[2][QP_MAXK][QP_THREADS];       // solution (private to the owning thread; kept here to leave registers for loads in flight)
+    double red[2][QP_THREADS];             // block reductions, one row per system
+    double tot[2];
+};
+
+// D6 block tree for two values at once: strides 512 .. 32 through shared memory, 16 .. 1 by shuffle (thread t pairs with t + stride)
+__device__ __forceinline__ void qp_block_sum2(double v0, double v1, QpResSmem &S, double *part0, double *part1) {
+    const int t = threadIdx.x;
+    S.red[0][t] = v0; S.red[1][t] = v1;
+    __syncthreads();
+    for (int off = QP_THREADS / 2; off >= 32; off >>= 1) {
+        if (t < off) { S.red[0][t] += S.red[0][t + off]; S.red[1][t] += S.red[1][t + off]; }
+        __syncthreads();
+    }
+    if (t < 32) {
+        double a = S.red[0][t], b = S.red[1][t];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) { a += __shfl_down_sync(0xffffffffu, a, off); b += __shfl_down_sync(0xffffffffu, b, off); }
+        if (t == 0) { part0[blockIdx.x] = a; part1[blockIdx.x] = b; }
+    }
+}
+// sequential sums of the 128 group sums of both systems (threads 0 and 32 side by side), rounded to f32
+__device__ __forceinline__ void qp_total2(const double *part0, const double *part1, QpResSmem &S, float &t0, float &t1) {
+    const int t = threadIdx.x;
+    if (t < QP_BLOCKS) { S.red[0][t] = __ldcg(part0 + t); S.red[1][t] = __ldcg(part1 + t); }
+    __syncthreads();
+    if (t == 0 || t == 32) {
+        const int s = t >> 5;
+        double acc = 0;
+        for (int g = 0; g < QP_BLOCKS; g++) acc += S.red[s][g];
+        S.tot[s] = acc;
+    }
+    __syncthreads();
+    t0 = (float)S.tot[0]; t1 = (float)S.tot[1];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X1, float *R0, float *R1, float *P00, float *P01, float *P10, float *P11,
+                                                             int cols, int rows, int max_iter, float tol, double *part, unsigned int *bar, int *iters_out) {
+    extern __shared__ __align__(16) unsigned char qp_smem_raw[];
+    QpResSmem &S = *reinterpret_cast<QpResSmem *>(qp_smem_raw);
+    const int N = cols * rows, tid = threadIdx.x;
+    const int lane0 = blockIdx.x * QP_THREADS + tid;
+    const int K = (N + QP_LANES - 1) / QP_LANES;                     // <= QP_MAXK (checked by the launcher)
+    float *X[2] = {X0, X1}, *R[2] = {R0, R1};
+    float *P[2][2] = {{P00, P01}, {P10, P11}};
+    double *part_po[2] = {part + 0 * QP_BLOCKS, part + 2 * QP_BLOCKS}, *part_rr[2] = {part + 1 * QP_BLOCKS, part + 3 * QP_BLOCKS};
+    // per pixel: which of the four neighbours exist (bits 4k .. 4k+3 = up, left, right, down)
+    unsigned nbmask = 0;
+#pragma unroll
+    for (int k = 0; k < QP_MAXK; k++) {
+        int i = lane0 + k * QP_LANES;
+        if (k < K && i < N) {
+            int y = i / cols, x = i - y * cols;
+            nbmask |= ((y - 1 >= 0 ? 1u : 0u) | (x - 1 >= 0 ? 2u : 0u) | (x + 1 < cols ? 4u : 0u) | (y + 1 < rows ? 8u : 0u)) << (4 * k);
+        }
+    }
+    float om[2][QP_MAXK];
+    unsigned int epoch = 0;
+    {   // r = B (written by k_qpath_rhs), x = 0, p = 0; r1 = r.r
+        double acc[2] = {0, 0};
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+#pragma unroll
+            for (int k = 0; k < QP_MAXK; k++) {
+                int i = lane0 + k * QP_LANES;
+                float v = 0.f;
+                if (k < K && i < N) { v = R[s][i]; acc[s] += (double)v * (double)v; }
+                S.r[s][k][tid] = v; S.p[s][k][tid] = 0.f; S.x[s][k][tid] = 0.f; om[s][k] = 0.f;
+            }
+        qp_block_sum2(acc[0], acc[1], S, part_rr[0], part_rr[1]);
+    }
+    qp_grid_barrier(bar, epoch);
+    float r1[2], r0[2] = {0.f, 0.f};
+    int kk[2] = {0, 0};
+    bool active[2];
+    qp_total2(part_rr[0], part_rr[1], S, r1[0], r1[1]);
+    for (int s = 0; s < 2; s++) active[s] = r1[s] > tol * tol && kk[s] <= max_iter;
+    int cur = 0;
+    while (active[0] || active[1]) {
+        // ---- phase A, pass 1: own p_new = r (+ beta p_old) into shared memory and into the global array the neighbours read next iteration
+        float beta[2]; bool first[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            beta[s] = 0.f; first[s] = true;
+            if (!active[s]) continue;                                   // uniform
+            kk[s]++;
+            first[s] = (kk[s] == 1);
+            beta[s] = first[s] ? 0.0f : r1[s] / r0[s];
+            float *pnew = P[s][cur ^ 1];
+#pragma unroll
+            for (int k = 0; k < QP_MAXK; k++) {
+                int i = lane0 + k * QP_LANES;
+                if (k < K && i < N) {
+                    float rv = S.r[s][k][tid];
+                    float pc = rv;
+                    if (!first[s]) { float t = beta[s] * S.p[s][k][tid]; pc = 1.0f * rv + t; }
+                    S.p[s][k][tid] = pc;
+                    pnew[i] = pc;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase A, pass 2: om = A p_new (QuadraticPath.cpp:170-202), partial p_new.om
+        double accA[2] = {0, 0};
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (!active[s]) continue;
+            const float *pold = P[s][cur], *rr = R[s];
+            // the rows above / below belong to other CTAs: fetch their r and p_old for every step first (independent loads, all
+            // in flight together), then walk the steps
+            float ru[QP_MAXK], pu[QP_MAXK], rd[QP_MAXK], pd[QP_MAXK];
+#pragma unroll
+            for (int k = 0; k < QP_MAXK; k++) {
+                int i = lane0 + k * QP_LANES;
+                const unsigned nb = nbmask >> (4 * k);
+                ru[k] = pu[k] = rd[k] = pd[k] = 0.f;
+                if (nb & 1u) { ru[k] = __ldcg(rr + i - cols); if (!first[s]) pu[k] = __ldcg(pold + i - cols); }
+                if (nb & 8u) { rd[k] = __ldcg(rr + i + cols); if (!first[s]) pd[k] = __ldcg(pold + i + cols); }
+            }
+#pragma unroll
+            for (int k = 0; k < QP_MAXK; k++) {
+                int i = lane0 + k * QP_LANES;
+                if (k < K && i < N) {
+                    const unsigned nb = nbmask >> (4 * k);
+                    float pc = S.p[s][k][tid];
+                    float diag = 0, sum = 0;
+                    if (nb & 1u) { diag += 1.0f; float pn = first[s] ? ru[k] : 1.0f * ru[k] + beta[s] * pu[k]; sum += -1.0f * pn; }
+                    if (nb & 2u) { diag += 1.0f; sum += -1.0f * (tid > 0 ? S.p[s][k][tid - 1] : qp_pnew(rr, pold, beta[s], first[s], i - 1)); }
+                    float right = 0, down = 0;
+                    if (nb & 4u) { diag += 1.0f; right = -1.0f * (tid < QP_THREADS - 1 ? S.p[s][k][tid + 1] : qp_pnew(rr, pold, beta[s], first[s], i + 1)); }
+                    if (nb & 8u) { diag += 1.0f; float pn = first[s] ? rd[k] : 1.0f * rd[k] + beta[s] * pd[k]; down = -1.0f * pn; }
+                    if (diag != 0) sum += diag * pc;
+                    if (nb & 4u) sum += right;
+                    if (nb & 8u) sum += down;
+                    om[s][k] = sum;
+                    accA[s] += (double)pc * (double)sum;
+                }
+            }
+        }
+        qp_block_sum2(accA[0], accA[1], S, part_po[0], part_po[1]);
+        qp_grid_barrier(bar, epoch);
+        // ---- phase B: alpha = r1 / (p.om); x += alpha p; r -= alpha om (published for the neighbours); partial r.r
+        float dt[2];
+        qp_total2(part_po[0], part_po[1], S, dt[0], dt[1]);
+        double accB[2] = {0, 0};
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (!active[s]) continue;
+            float alpha = r1[s] / dt[s], nalpha = -alpha;
+#pragma unroll
+            for (int k = 0; k < QP_MAXK; k++) {
+                int i = lane0 + k * QP_LANES;
+                if (k < K && i < N) {
+                    float pv = S.p[s][k][tid];
+                    S.x[s][k][tid] = alpha * pv + S.x[s][k][tid];
+                    float rv = nalpha * om[s][k] + S.r[s][k][tid];
+                    S.r[s][k][tid] = rv;
+                    R[s][i] = rv;
+                    accB[s] += (double)rv * (double)rv;
+                }
+            }
+        }
+        qp_block_sum2(accB[0], accB[1], S, part_rr[0], part_rr[1]);
+        qp_grid_barrier(bar, epoch);
+        float nr[2];
+        qp_total2(part_rr[0], part_rr[1], S, nr[0], nr[1]);
+        for (int s = 0; s < 2; s++) {
+            if (!active[s]) continue;
+            r0[s] = r1[s];
+            r1[s] = nr[s];
+            active[s] = r1[s] > tol * tol && kk[s] <= max_iter;
+        }
+        cur ^= 1;
+    }
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int k = 0; k < QP_MAXK; k++) {
+            int i = lane0 + k * QP_LANES;
+            if (k < K && i < N) X[s][i] = S.x[s][k][tid];
+        }
+    if (blockIdx.x == 0 && tid == 0) { iters_out[0] = kk[0]; iters_out[1] = kk[1]; }
+}
+
 // interleave the two solutions into the float2 result (QuadraticPath.cpp:208-211)
 __global__ void k_qpath_pack(const float *__restrict__ X, const float *__restrict__ Y, float2 *__restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,8 +408,22 @@ cudaError_t launch_qpath(const float2 *vec, float2 *out, int cols, int rows, int
     dim3 b(32, 8), g((cols + 31) / 32, (rows + 7) / 8);
     k_qpath_jacobian<<<g, b, 0, s>>>(vec, J, cols, rows);
     k_qpath_rhs<<<g, b, 0, s>>>(J, R0, R1, cols, rows);                                // r = B
-    void *args[] = {&X0, &X1, &R0, &R1, &P00, &P01, &P10, &P11, &OM0, &OM1, &cols, &rows, &max_iter, &tol, &part, &bar, &iters_dev};
-    e = cudaLaunchCooperativeKernel((const void *)k_qpath_cg, dim3(QP_BLOCKS), dim3(QP_THREADS), args, 0, s);
+    // frames whose unknowns fit QP_MAXK steps of the lane grid keep r / p on chip (VMORPH_QPATH=global forces the streaming kernel: test hook)
+    const char *eq = getenv("VMORPH_QPATH");
+    const bool resident = N <= (size_t)QP_MAXK * QP_LANES && !(eq && !strcmp(eq, "global"));
+    if (resident) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            e = cudaFuncSetAttribute(k_qpath_cg_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QpResSmem));
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        void *args[] = {&X0, &X1, &R0, &R1, &P00, &P01, &P10, &P11, &cols, &rows, &max_iter, &tol, &part, &bar, &iters_dev};
+        e = cudaLaunchCooperativeKernel((const void *)k_qpath_cg_res, dim3(QP_BLOCKS), dim3(QP_THREADS), args, sizeof(QpResSmem), s);
+    } else {
+        void *args[] = {&X0, &X1, &R0, &R1, &P00, &P01, &P10, &P11, &OM0, &OM1, &cols, &rows, &max_iter, &tol, &part, &bar, &iters_dev};
+        e = cudaLaunchCooperativeKernel((const void *)k_qpath_cg, dim3(QP_BLOCKS), dim3(QP_THREADS), args, 0, s);
+    }
     if (e != cudaSuccess) return e;
     k_qpath_pack<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(X0, X1, out, (int)N);
     count_launch(4);
