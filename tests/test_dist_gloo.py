@@ -24,6 +24,12 @@ def _worker(rank, world, port, q):
     local = np.arange(d * 6, dtype=np.float32).reshape(d, 3, 2)[b:e] * 2.0          # this rank's frames of a (d,3,2) result
     whole = vd.gather_frames(local, d)
     units, secs = vd.reduce_throughput(10.0 * (rank + 1), 0.5 + rank)                # SUM of units, MAX of seconds
+    # frame-sharded QuadraticPath: every rank solves its block (stand-in solver), everyone gets all frames back in order
+    vecs = np.arange(d * 4 * 5 * 2, dtype=np.float32).reshape(d, 4, 5, 2)
+    fake = lambda v: (v * np.float32(3.0) + np.float32(1.0), np.full((v.shape[0], 2), 7 + rank, np.int32))
+    qp, its = vd.quadratic_path_sharded(vecs, solve=fake)
+    assert qp.shape == vecs.shape and np.array_equal(qp, vecs * np.float32(3.0) + np.float32(1.0))
+    assert [int(x) for x in its[:, 0]] == [7 + r for r, (bb, ee) in enumerate(blocks) for _ in range(ee - bb)]
     dist.barrier()
     q.put((rank, whole, units, secs))
     dist.destroy_process_group()

@@ -102,6 +102,25 @@ def render_frames_sharded(w, h, ex, ext0, ext1, vectors, qpaths=None, color_from
     return gather_frames(out, d) if gather else out
 
 
+def quadratic_path_sharded(vectors, max_iter=10000, tol=1e-12, device=0, gather=True, solve=None):
+    """CQuadraticPath::optimize (QuadraticPath.cpp:24-223 loops z over the frames; the frames are independent): each rank
+    solves its contiguous frame block on its own GPU, no exchange; with gather=True every rank gets all d frames back.
+    Returns (qpaths, iterations (d, 2)).  `solve` replaces the GPU call in the CPU tests."""
+    from . import api
+    solve = solve or (lambda v: api.quadratic_path_frames(v, max_iter, tol, device=device))
+    d = vectors.shape[0]
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    b, e = frame_blocks(d, world)[rank]
+    if e > b:
+        q, it = solve(np.ascontiguousarray(vectors[b:e]))
+    else:
+        q, it = np.zeros((0,) + vectors.shape[1:], np.float32), np.zeros((0, 2), np.int32)
+    if not gather:
+        return q, it
+    return gather_frames(q, d), gather_frames(np.asarray(it, np.int32), d)
+
+
 # ------------------------------------------------------------------------------------------ optimizer, exact mode
 def _exchange_pages(pyramid, level, my_pages, peer_pages, peer, device, stream=None):
     """Send this rank's `v` pages [a, b) of a level to `peer` and receive the peer's pages: NCCL send / recv over NVLink.
