@@ -62,12 +62,7 @@ __global__ void k_qpath_rhs(const float4 *__restrict__ J, float *__restrict__ Bx
 __device__ __forceinline__ void qp_grid_barrier(unsigned int *counter, unsigned int &epoch) {
     __syncthreads();
     epoch += QP_BLOCKS;
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*((volatile unsigned int *)counter) < epoch) { __nanosleep(20); }
-        __threadfence();
-    }
+    if (threadIdx.x == 0) grid_arrive_and_wait(counter, epoch);
     __syncthreads();
 }
 

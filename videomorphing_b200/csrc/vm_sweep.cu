@@ -76,12 +76,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
     __syncthreads();
     epoch += nblocks;
     if (nblocks > 1) {
-        if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd(counter, 1u);
-            while (*((volatile unsigned int *)counter) < epoch) { __nanosleep(32); }
-            __threadfence();
-        }
+        if (threadIdx.x == 0) grid_arrive_and_wait(counter, epoch);
         __syncthreads();
     }
 }
