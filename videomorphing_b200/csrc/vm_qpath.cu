@@ -187,6 +187,14 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg(float *X0, float *X1, f
 // k_qpath_cg, so no third grid barrier is needed.  Global traffic per unknown and iteration: 4 loads + 2 stores instead
 // of 14 loads + 4 stores.  Both systems share each block reduction (intra-warp levels by shuffle, same pairing as the
 // D6 tree) and their group sums are added by two threads side by side.
+#ifdef VM_TRACE
+__device__ unsigned long long g_qtrace[16];     // development-only phase cycles of CTA 0 / thread 0 (libvmorph_trace.so)
+#define QTR_DECL long long qtr_t0 = clock64()
+#define QTR(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t1 = clock64(); atomicAdd(&g_qtrace[k], (unsigned long long)(t1 - qtr_t0)); qtr_t0 = t1; } } while (0)
+#else
+#define QTR_DECL
+#define QTR(k)
+#endif
 constexpr int QP_MAXK = 8;
 struct QpResSmem {
     float p[2][QP_MAXK][QP_THREADS];       // current search direction of the own pixels
@@ -270,7 +278,9 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X
     qp_total2(part_rr[0], part_rr[1], S, r1[0], r1[1]);
     for (int s = 0; s < 2; s++) active[s] = r1[s] > tol * tol && kk[s] <= max_iter;
     int cur = 0;
+    QTR_DECL;
     while (active[0] || active[1]) {
+        QTR(7);
         // ---- phase A, pass 1: own p_new = r (+ beta p_old) into shared memory and into the global array the neighbours read next iteration
         float beta[2]; bool first[2];
 #pragma unroll
@@ -294,6 +304,7 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X
             }
         }
         __syncthreads();
+        QTR(0);
         // ---- phase A, pass 2: om = A p_new (QuadraticPath.cpp:170-202), partial p_new.om
         double accA[2] = {0, 0};
 #pragma unroll
@@ -331,11 +342,15 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X
                 }
             }
         }
+        QTR(1);
         qp_block_sum2(accA[0], accA[1], S, part_po[0], part_po[1]);
+        QTR(2);
         qp_grid_barrier(bar, epoch);
+        QTR(3);
         // ---- phase B: alpha = r1 / (p.om); x += alpha p; r -= alpha om (published for the neighbours); partial r.r
         float dt[2];
         qp_total2(part_po[0], part_po[1], S, dt[0], dt[1]);
+        QTR(4);
         double accB[2] = {0, 0};
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -354,10 +369,14 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X
                 }
             }
         }
+        QTR(5);
         qp_block_sum2(accB[0], accB[1], S, part_rr[0], part_rr[1]);
+        QTR(2);
         qp_grid_barrier(bar, epoch);
+        QTR(3);
         float nr[2];
         qp_total2(part_rr[0], part_rr[1], S, nr[0], nr[1]);
+        QTR(4);
         for (int s = 0; s < 2; s++) {
             if (!active[s]) continue;
             r0[s] = r1[s];
@@ -424,6 +443,15 @@ cudaError_t launch_qpath(const float2 *vec, float2 *out, int cols, int rows, int
     count_launch(4);
     return cudaGetLastError();
 }
+
+#ifdef VM_TRACE
+extern "C" int vm_debug_qtrace(unsigned long long *out16, int reset) {
+    cudaDeviceSynchronize();
+    if (out16) cudaMemcpyFromSymbol(out16, g_qtrace, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_qtrace, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 }  // namespace vm
 
