@@ -73,8 +73,8 @@ void render_halfway(uint8_t *out, int rowstride, int w, int h, int ex, float col
 // QuadraticPath.cpp:225-318 restated matrix-free on the 5-point operator assembled at 134-202.
 // D6 (vmo.h): cublasSdot's internal summation order is unspecified.  Here a dot product is DEFINED as: QP_LANES = 131072
 // lanes, lane t sums the exact products a[i]*b[i] of the elements i = t, t+QP_LANES, ... sequentially in f64; each group
-// of 1024 consecutive lanes is reduced by a binary tree (stride 512, 256, ..., 1); the 128 group sums are added
-// sequentially; the result is rounded to f32.  The CUDA path uses the same order, so both are bit-identical.
+// of 1024 consecutive lanes is reduced by a binary tree (stride 512, 256, ..., 1); the 128 group sums are reduced by a
+// binary tree (stride 64, ..., 1); the result is rounded to f32.  The CUDA path uses the same order, so both are bit-identical.
 static const int QP_LANES = 131072, QP_GROUP = 1024;
 static float qp_dot(const float *a, const float *b, int N) {
     std::vector<double> lane(QP_LANES, 0.0);
@@ -84,14 +84,17 @@ static float qp_dot(const float *a, const float *b, int N) {
         for (int i = t; i < N; i += QP_LANES) s += (double)a[i] * (double)b[i];
         lane[t] = s;
     }
-    double total = 0;
-    for (int g = 0; g < QP_LANES / QP_GROUP; g++) {
+    const int ng = QP_LANES / QP_GROUP;
+    double gs[QP_LANES / QP_GROUP];
+    for (int g = 0; g < ng; g++) {
         double *sh = lane.data() + (size_t)g * QP_GROUP;
         for (int off = QP_GROUP / 2; off > 0; off >>= 1)
             for (int t = 0; t < off; t++) sh[t] += sh[t + off];
-        total += sh[0];
+        gs[g] = sh[0];
     }
-    return (float)total;
+    for (int off = ng / 2; off > 0; off >>= 1)
+        for (int t = 0; t < off; t++) gs[t] += gs[t + off];
+    return (float)gs[0];
 }
 static int cg_solve(int cols, int rows, const std::vector<float> &B, std::vector<float> &X, int max_iter, float tol) {
     int N = cols * rows;

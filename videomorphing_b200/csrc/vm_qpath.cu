@@ -10,7 +10,7 @@
 // double-buffered, neighbours' new p is recomputed on the fly), so an iteration costs two grid barriers; scalars
 // (alpha, beta, r.r) are recomputed redundantly by every CTA from the per-CTA partial sums -- no host round trip.
 // Dot products follow the fixed lane / tree order of oracle deviation D6 (QP_LANES = 131072 lanes, 1024-lane binary trees,
-// sequential sum of the 128 group sums, f64), which makes the solve bit-reproducible and equal to the CPU oracle.
+// binary tree over the 128 group sums, f64), which makes the solve bit-reproducible and equal to the CPU oracle.
 #include "vm_device.cuh"
 #include "vm_host.h"
 #include <cstring>
@@ -77,17 +77,19 @@ __device__ __forceinline__ void qp_block_sum(double v, double *sh, double *part)
     if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
     __syncthreads();
 }
-// sequential sum of the 128 group sums (oracle D6 order), rounded to f32; every CTA computes it redundantly
+// binary tree over the 128 group sums (oracle D6: stride 64, ..., 1), rounded to f32; every CTA computes it redundantly
 __device__ __forceinline__ float qp_total(const double *part, double *sh) {
-    if (threadIdx.x < QP_BLOCKS) sh[threadIdx.x] = __ldcg(part + threadIdx.x);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0;
-        for (int g = 0; g < QP_BLOCKS; g++) t += sh[g];
-        sh[QP_BLOCKS] = t;
+    const int t = threadIdx.x;
+    if (t < 32) {
+        double a0 = __ldcg(part + t), a1 = __ldcg(part + t + 32), a2 = __ldcg(part + t + 64), a3 = __ldcg(part + t + 96);
+        a0 += a2; a1 += a3;                      // stride 64
+        a0 += a1;                                // stride 32
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) a0 += __shfl_down_sync(0xffffffffu, a0, off);
+        if (t == 0) sh[0] = a0;
     }
     __syncthreads();
-    float r = (float)sh[QP_BLOCKS];
+    float r = (float)sh[0];
     __syncthreads();
     return r;
 }
@@ -201,35 +203,51 @@ struct QpResSmem {
     float r[2][QP_MAXK][QP_THREADS];       // residual
     float x[2][QP_MAXK][QP_THREADS];       // solution (private to the owning thread; kept here to leave registers for loads in flight)
     double red[2][QP_THREADS];             // block reductions, one row per system
+    double fold[2][4][32];
     double tot[2];
 };
 
-// D6 block tree for two values at once: strides 512 .. 32 through shared memory, 16 .. 1 by shuffle (thread t pairs with t + stride)
+// D6 group tree (stride 512 ... 1 over the 1024 lanes) for two values at once with two CTA barriers instead of six.  In
+// units of warps the strides 512 .. 32 pair warp w with w + 16, 8, 4, 2, 1.  Warp q (q = 0..3) of a value's four worker
+// warps folds the eight warps w = q (mod 4) -- pairs (m, m + 4), (m, m + 2), (0, 1) over w = q + 4 m are exactly the
+// stride-16, -8, -4 pairs; the four results meet through shared memory for the strides 2 and 1, the lane strides 16 .. 1
+// are shuffles.  Same pairs as the loop `for (off = 512; off; off >>= 1) if (t < off) sh[t] += sh[t + off]`.
 __device__ __forceinline__ void qp_block_sum2(double v0, double v1, QpResSmem &S, double *part0, double *part1) {
     const int t = threadIdx.x;
     S.red[0][t] = v0; S.red[1][t] = v1;
     __syncthreads();
-    for (int off = QP_THREADS / 2; off >= 32; off >>= 1) {
-        if (t < off) { S.red[0][t] += S.red[0][t + off]; S.red[1][t] += S.red[1][t + off]; }
-        __syncthreads();
-    }
-    if (t < 32) {
-        double a = S.red[0][t], b = S.red[1][t];
+    const int s = t >> 7, q = (t >> 5) & 3, l = t & 31;
+    if (t < 256) {
+        double a[8];
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) { a += __shfl_down_sync(0xffffffffu, a, off); b += __shfl_down_sync(0xffffffffu, b, off); }
-        if (t == 0) { part0[blockIdx.x] = a; part1[blockIdx.x] = b; }
+        for (int m = 0; m < 8; m++) a[m] = S.red[s][32 * (q + 4 * m) + l];
+#pragma unroll
+        for (int m = 0; m < 4; m++) a[m] += a[m + 4];
+        a[0] += a[2]; a[1] += a[3];
+        a[0] += a[1];
+        S.fold[s][q][l] = a[0];
+    }
+    __syncthreads();
+    if (t < 256 && q == 0) {
+        double e0 = S.fold[s][0][l] + S.fold[s][2][l], e1 = S.fold[s][1][l] + S.fold[s][3][l];
+        double f = e0 + e1;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) f += __shfl_down_sync(0xffffffffu, f, off);
+        if (l == 0) (s ? part1 : part0)[blockIdx.x] = f;
     }
 }
-// sequential sums of the 128 group sums of both systems (threads 0 and 32 side by side), rounded to f32
+// binary trees over the 128 group sums of both systems (warp 0 / warp 1 side by side), rounded to f32
 __device__ __forceinline__ void qp_total2(const double *part0, const double *part1, QpResSmem &S, float &t0, float &t1) {
     const int t = threadIdx.x;
-    if (t < QP_BLOCKS) { S.red[0][t] = __ldcg(part0 + t); S.red[1][t] = __ldcg(part1 + t); }
-    __syncthreads();
-    if (t == 0 || t == 32) {
-        const int s = t >> 5;
-        double acc = 0;
-        for (int g = 0; g < QP_BLOCKS; g++) acc += S.red[s][g];
-        S.tot[s] = acc;
+    if (t < 64) {
+        const int s = t >> 5, l = t & 31;
+        const double *pp = s ? part1 : part0;
+        double a0 = __ldcg(pp + l), a1 = __ldcg(pp + l + 32), a2 = __ldcg(pp + l + 64), a3 = __ldcg(pp + l + 96);
+        a0 += a2; a1 += a3;                      // stride 64
+        a0 += a1;                                // stride 32
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) a0 += __shfl_down_sync(0xffffffffu, a0, off);
+        if (l == 0) S.tot[s] = a0;
     }
     __syncthreads();
     t0 = (float)S.tot[0]; t1 = (float)S.tot[1];
