@@ -181,14 +181,16 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg(float *X0, float *X1, f
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Resident variant (frames of up to QP_MAXK * QP_LANES unknowns, e.g. 1280x720): the same iteration, the same fixed dot
-// order, but every CTA keeps the r and p of ITS lanes' pixels in shared memory and x / A p in registers for the whole
+// Resident variant (frames of up to QP_MAXK * QP_LANES unknowns, e.g. 1280x720): the same arithmetic, the same fixed dot
+// order, but every CTA keeps the r, p and x of ITS lanes' pixels in shared memory and A p in registers for the whole
 // solve.  Lane t owns the pixels t, t + QP_LANES, ...; the 1024 lanes of a CTA own one contiguous run of 1024 pixels per
-// step k, so left / right neighbours are in shared memory and only the rows above / below (other CTAs' pixels) are read
-// from global memory -- their new search direction is recomputed from the r and p_old their owners published, like in
-// k_qpath_cg, so no third grid barrier is needed.  Global traffic per unknown and iteration: 4 loads + 2 stores instead
-// of 14 loads + 4 stores.  Both systems share each block reduction (intra-warp levels by shuffle, same pairing as the
-// D6 tree) and their group sums are added by two threads side by side.
+// step k, so left / right neighbours are in shared memory and only the rows above / below (other CTAs' pixels) come
+// from global memory: every CTA publishes its new search direction, a grid barrier follows, and the operator reads ONE
+// value per neighbour row (k_qpath_cg avoids that barrier by recomputing the neighbours' p from r and p_old: four loads
+// where this kernel needs two -- measured slower here, profiles/r1_qpath.md).  Global traffic per unknown and iteration:
+// 2 loads + 1 store instead of 14 loads + 4 stores.  Both systems share each block reduction (two CTA barriers per
+// 1024-lane tree, intra-warp levels by shuffle, same pairs as the D6 tree) and their group sums are reduced by two warps
+// side by side.
 #ifdef VM_TRACE
 __device__ unsigned long long g_qtrace[16];     // development-only phase cycles of CTA 0 / thread 0 (libvmorph_trace.so)
 #define QTR_DECL long long qtr_t0 = clock64()
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X
             kk[s]++;
             first[s] = (kk[s] == 1);
             beta[s] = first[s] ? 0.0f : r1[s] / r0[s];
-            float *pnew = P[s][cur ^ 1];
+            float *pnew = P[s][0];
 #pragma unroll
             for (int k = 0; k < QP_MAXK; k++) {
                 int i = lane0 + k * QP_LANES;
@@ -321,25 +323,31 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X
                 }
             }
         }
-        __syncthreads();
+        // the search direction is published before anybody applies the operator: a third grid barrier per iteration, which costs
+        // less than fetching r AND p_old of every neighbour row to recompute their p_new (4 loads per unknown -> 2; trace in profiles/)
+        qp_grid_barrier(bar, epoch);
         QTR(0);
         // ---- phase A, pass 2: om = A p_new (QuadraticPath.cpp:170-202), partial p_new.om
         double accA[2] = {0, 0};
+        // the rows above / below belong to other CTAs: fetch their published p_new for every step of both systems first
+        // (independent loads, all in flight together), then walk the steps
+        float pu[2][QP_MAXK], pd[2][QP_MAXK];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            if (!active[s]) continue;
-            const float *pold = P[s][cur], *rr = R[s];
-            // the rows above / below belong to other CTAs: fetch their r and p_old for every step first (independent loads, all
-            // in flight together), then walk the steps
-            float ru[QP_MAXK], pu[QP_MAXK], rd[QP_MAXK], pd[QP_MAXK];
+            const float *pn = P[s][0];
 #pragma unroll
             for (int k = 0; k < QP_MAXK; k++) {
                 int i = lane0 + k * QP_LANES;
                 const unsigned nb = nbmask >> (4 * k);
-                ru[k] = pu[k] = rd[k] = pd[k] = 0.f;
-                if (nb & 1u) { ru[k] = __ldcg(rr + i - cols); if (!first[s]) pu[k] = __ldcg(pold + i - cols); }
-                if (nb & 8u) { rd[k] = __ldcg(rr + i + cols); if (!first[s]) pd[k] = __ldcg(pold + i + cols); }
+                pu[s][k] = pd[s][k] = 0.f;
+                if (active[s] && (nb & 1u)) pu[s][k] = __ldcg(pn + i - cols);
+                if (active[s] && (nb & 8u)) pd[s][k] = __ldcg(pn + i + cols);
             }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (!active[s]) continue;
+            const float *pn = P[s][0];
 #pragma unroll
             for (int k = 0; k < QP_MAXK; k++) {
                 int i = lane0 + k * QP_LANES;
@@ -347,11 +355,11 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X
                     const unsigned nb = nbmask >> (4 * k);
                     float pc = S.p[s][k][tid];
                     float diag = 0, sum = 0;
-                    if (nb & 1u) { diag += 1.0f; float pn = first[s] ? ru[k] : 1.0f * ru[k] + beta[s] * pu[k]; sum += -1.0f * pn; }
-                    if (nb & 2u) { diag += 1.0f; sum += -1.0f * (tid > 0 ? S.p[s][k][tid - 1] : qp_pnew(rr, pold, beta[s], first[s], i - 1)); }
+                    if (nb & 1u) { diag += 1.0f; sum += -1.0f * pu[s][k]; }
+                    if (nb & 2u) { diag += 1.0f; sum += -1.0f * (tid > 0 ? S.p[s][k][tid - 1] : __ldcg(pn + i - 1)); }
                     float right = 0, down = 0;
-                    if (nb & 4u) { diag += 1.0f; right = -1.0f * (tid < QP_THREADS - 1 ? S.p[s][k][tid + 1] : qp_pnew(rr, pold, beta[s], first[s], i + 1)); }
-                    if (nb & 8u) { diag += 1.0f; float pn = first[s] ? rd[k] : 1.0f * rd[k] + beta[s] * pd[k]; down = -1.0f * pn; }
+                    if (nb & 4u) { diag += 1.0f; right = -1.0f * (tid < QP_THREADS - 1 ? S.p[s][k][tid + 1] : __ldcg(pn + i + 1)); }
+                    if (nb & 8u) { diag += 1.0f; down = -1.0f * pd[s][k]; }
                     if (diag != 0) sum += diag * pc;
                     if (nb & 4u) sum += right;
                     if (nb & 8u) sum += down;
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X
         QTR(2);
         qp_grid_barrier(bar, epoch);
         QTR(3);
-        // ---- phase B: alpha = r1 / (p.om); x += alpha p; r -= alpha om (published for the neighbours); partial r.r
+        // ---- phase B: alpha = r1 / (p.om); x += alpha p; r -= alpha om; partial r.r
         float dt[2];
         qp_total2(part_po[0], part_po[1], S, dt[0], dt[1]);
         QTR(4);
@@ -382,7 +390,6 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X
                     S.x[s][k][tid] = alpha * pv + S.x[s][k][tid];
                     float rv = nalpha * om[s][k] + S.r[s][k][tid];
                     S.r[s][k][tid] = rv;
-                    R[s][i] = rv;
                     accB[s] += (double)rv * (double)rv;
                 }
             }
