@@ -56,11 +56,12 @@ struct SweepSmem {
     float2 mean[TCELLS], var[TCELLS], tpsb[TCELLS];     // this CTA's replica of the tile state
     float cross[TCELLS], value[TCELLS], cnt[TCELLS];
     SlotBuf slot[2];                                     // double-buffered by sub-phase parity
-    unsigned char status[NPIX];      // 0 = no mask index, 1 = has a mask index
-    unsigned char bcls[NPIX];        // By*5+Bx of the pixel
+    // filter outputs, double-buffered by sub-phase parity: the filter of sub-phase k+1 runs during the commit of sub-phase k
+    unsigned char status[2][NPIX];   // 0 = no mask index, 1 = has a mask index
+    unsigned char bcls[2][NPIX];     // By*5+Bx of the pixel
     unsigned short queue[NPIX];
-    int warp_cnt[NPIX / 32];
-    unsigned int stat_any[NPIX / 32];    // per filter warp: ballot of pixels that have a mask index
+    int warp_cnt[2][NPIX / 32];
+    unsigned int stat_any[2][NPIX / 32]; // per filter warp: ballot of pixels that have a mask index
     int next_tile;                       // dynamic mode: list entry this CTA works on
     unsigned int accrow[OPT_BH];         // accepted slots of the sub-phase, one 32-bit row per lattice row
     unsigned int mask[MASK_W * MASK_H];  // improving-mask words around the tile (see tile_step)
@@ -394,44 +395,51 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
     __syncthreads();
     TR(1);
 
-    for (int si = 0; si < 2; ++si)
-        for (int sj = 0; sj < 2; ++sj) {
-            SlotBuf &SB = S.slot[phase & 1u];
-            // ---- filter: which pixels of this colour have an improving neighbourhood (morph.cu:1041-1054, 621-646);
-            //      deterministic compaction (slot order) so every CTA of the cluster builds the same queue
-            bool act = false; unsigned bal = 0;
-            if (tid < NPIX) {
-                int tx = tid & 31, ty = tid >> 5;
-                int px = ox + tx * 2 + sj + 2, py = oy + ty * 2 + si + 2;
-                unsigned char stt = 0;
-                if (px >= 0 && px < L.w && py >= 0 && py < L.h) {
-                    int bx = px / 5, by = py / 5, oxx = px - bx * 5, oyy = py - by * 5;
-                    int begi = oyy >= 2 ? 1 : 0, begj = oxx >= 2 ? 1 : 0;
-                    const unsigned *imp = &S.improv[(oyy * 5 + oxx) * 9];
-                    int lx = bx + 1 - mcx0, ly = by + 1 - mcy0;           // this pixel's cell inside the replica
-                    bool hit = false;
+    // ---- filter: which pixels of a colour have an improving neighbourhood (morph.cu:1041-1054, 621-646).  Executed by the
+    //      first NPIX threads; results go to buffer fb.  Only reads the mask replica, so the filter of sub-phase k+1 can run
+    //      as soon as sub-phase k's mask bits are final (right after commit A), next to the commit gather, instead of
+    //      sitting on the critical path between two barriers at the start of the next sub-phase.
+    auto filter = [&](int si, int sj, int fb, bool &act, unsigned &bal) {
+        act = false; bal = 0;
+        if (tid < NPIX) {
+            int tx = tid & 31, ty = tid >> 5;
+            int px = ox + tx * 2 + sj + 2, py = oy + ty * 2 + si + 2;
+            unsigned char stt = 0;
+            if (px >= 0 && px < L.w && py >= 0 && py < L.h) {
+                int bx = px / 5, by = py / 5, oxx = px - bx * 5, oyy = py - by * 5;
+                int begi = oyy >= 2 ? 1 : 0, begj = oxx >= 2 ? 1 : 0;
+                const unsigned *imp = &S.improv[(oyy * 5 + oxx) * 9];
+                int lx = bx + 1 - mcx0, ly = by + 1 - mcy0;           // this pixel's cell inside the replica
+                bool hit = false;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
+                for (int i = 0; i < 2; ++i)
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            int ii = begi + i, jj = begj + j;
-                            hit |= (S.mask[(ly + ii - 1) * MASK_W + (lx + jj - 1)] & imp[ii * 3 + jj]) != 0u;
-                        }
-                    if (hit) { stt = 1; act = !pixel_on_border(L, P.bcond, px, py); }
-                    S.bcls[tid] = (unsigned char)(border_class(py, L.h) * 5 + border_class(px, L.w));
-                }
-                S.status[tid] = stt;
-                bal = __ballot_sync(0xffffffffu, act);
-                unsigned sbal = __ballot_sync(0xffffffffu, stt != 0);
-                if (lane == 0) { S.warp_cnt[warp] = __popc(bal); S.stat_any[warp] = sbal; }
+                    for (int j = 0; j < 2; ++j) {
+                        int ii = begi + i, jj = begj + j;
+                        hit |= (S.mask[(ly + ii - 1) * MASK_W + (lx + jj - 1)] & imp[ii * 3 + jj]) != 0u;
+                    }
+                if (hit) { stt = 1; act = !pixel_on_border(L, P.bcond, px, py); }
+                S.bcls[fb][tid] = (unsigned char)(border_class(py, L.h) * 5 + border_class(px, L.w));
             }
-            __syncthreads();
+            S.status[fb][tid] = stt;
+            bal = __ballot_sync(0xffffffffu, act);
+            unsigned sbal = __ballot_sync(0xffffffffu, stt != 0);
+            if (lane == 0) { S.warp_cnt[fb][warp] = __popc(bal); S.stat_any[fb][warp] = sbal; }
+        }
+    };
+    bool act; unsigned bal;
+    filter(0, 0, 0, act, bal);
+    __syncthreads();
+    for (int sp = 0; sp < 4; ++sp) {
+            const int si = sp >> 1, sj = sp & 1, fb = sp & 1;                 // sub-phase order i outer / j inner (morph.cu:1281-1345)
+            SlotBuf &SB = S.slot[phase & 1u];
+            // deterministic compaction (slot order) so every CTA of the cluster builds the same queue
             int qn = 0; unsigned stat_any = 0;
 #pragma unroll
-            for (int k = 0; k < NPIX / 32; k++) { qn += S.warp_cnt[k]; stat_any |= S.stat_any[k]; }
+            for (int k = 0; k < NPIX / 32; k++) { qn += S.warp_cnt[fb][k]; stat_any |= S.stat_any[fb][k]; }
             if (tid < NPIX && act) {
                 int base = 0;
-                for (int k = 0; k < warp; k++) base += S.warp_cnt[k];
+                for (int k = 0; k < warp; k++) base += S.warp_cnt[fb][k];
                 S.queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)tid;
             }
             if (qn > 0) __syncthreads();
@@ -462,7 +470,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                 if (flag) { E.tref = __ldcg(L.temp_ref + idx); E.tmask = __ldcg(L.temp_mask + idx); }
                 E.w_ui = P.w_ui; E.w_tps = P.w_tps; E.w_ssim = P.w_ssim; E.w_temp = P.w_temp; E.ssim_clamp = P.ssim_clamp;
                 E.inv_wh = L.inv_wh; E.factor_d = L.factor_d;
-                int B = S.bcls[slot];
+                int B = S.bcls[fb][slot];
                 E.w_valid = false; E.w_mean = E.w_var = make_float2(0.f, 0.f); E.w_cross = E.w_value = 0.f; E.w_cnt = 0.f;
                 if (lane < 25) {
                     int wi = lane / 5, wj = lane - wi * 5;
@@ -513,7 +521,13 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             // every v / luma / slot update of this sub-phase is ordered before the commit by this barrier
             // Nothing to commit and no mask bit to clear (uniform).  A cluster still needs its barrier: the slot buffers
             // are double-buffered by sub-phase parity and the barrier is what orders their reuse.
-            if (stat_any == 0 && R == 1) { phase++; __syncthreads(); continue; }
+            bool act_n = false; unsigned bal_n = 0;
+            if (stat_any == 0 && R == 1) {
+                if (sp < 3) filter((sp + 1) >> 1, (sp + 1) & 1, fb ^ 1, act_n, bal_n);       // mask unchanged by this sub-phase
+                phase++; __syncthreads();
+                act = act_n; bal = bal_n;
+                continue;
+            }
             if (R > 1) cluster.sync(); else __syncthreads();
             TR(4);
             // ---- commit A: improving-mask bits of every pixel that had a mask index: set if accepted, cleared otherwise
@@ -527,7 +541,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                 if (acc) SB.acc[tid] = 0;              // next written by the cluster two sub-phases from now, after two more barriers
                 unsigned abal = __ballot_sync(0xffffffffu, acc != 0);
                 if (lane == 0) S.accrow[ty] = abal;
-                if (S.status[tid]) {
+                if (S.status[fb][tid]) {
                     int px = ox + tx * 2 + sj + 2, py = oy + ty * 2 + si + 2;
                     int bx = px / 5, by = py / 5;
                     unsigned bit = 1u << ((px - bx * 5) + (py - by * 5) * 5);
@@ -542,6 +556,9 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             //      The gather is instruction-issue bound, not latency bound (every CTA runs ~350 instructions for each of up
             //      to 1 360 cells): a branch-free / batched-UpdateSSIM rewrite measured the same time (trace7, profiles/).
             const int any_acc = __syncthreads_or(any);
+            // the mask bits of this sub-phase are final: filter the next colour now (its outputs are published by the barrier
+            // that ends this sub-phase)
+            if (sp < 3) filter((sp + 1) >> 1, (sp + 1) & 1, fb ^ 1, act_n, bal_n);
             TR(16);
             if (any_acc) {
                 dirty = true;
@@ -576,7 +593,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                             if (!((cand >> (ky * 3 + kx)) & 1u)) continue;
                             int dy = dyb + 2 * ky, dx = dxb + 2 * kx;
                             int slot = (tyb + ky) * OPT_BW + (txb + kx);
-                            int B = S.bcls[slot];
+                            int B = S.bcls[fb][slot];
                             int k = (2 - dy) * 5 + (2 - dx);
                             if ((S.iomask[B] >> k) & 1u) {
                                 float2 dm = SB.dm[slot], dv = SB.dv[slot];
@@ -596,6 +613,7 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             TR(17);
             phase++;
             __syncthreads();
+            act = act_n; bal = bal_n;
             TR(5);
         }
     // --- SaveSSIM (morph.cu:1236-1256) + tps.b, only when something was committed; replicas are identical, rank 0 stores
