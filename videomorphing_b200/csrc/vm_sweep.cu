@@ -425,6 +425,15 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
             bal = __ballot_sync(0xffffffffu, act);
             unsigned sbal = __ballot_sync(0xffffffffu, stt != 0);
             if (lane == 0) { S.warp_cnt[fb][warp] = __popc(bal); S.stat_any[fb][warp] = sbal; }
+            // deterministic compaction (slot order) so every CTA of the cluster builds the same queue.  Only the NPIX filter
+            // threads (whole warps) take part: a named barrier among them, not a CTA barrier.  The queue of the previous
+            // sub-phase is no longer read (its compute loop ended before the barrier that precedes every filter call).
+            asm volatile("bar.sync 1, %0;" ::"n"(NPIX) : "memory");
+            if (act) {
+                int base = 0;
+                for (int k = 0; k < warp; k++) base += S.warp_cnt[fb][k];
+                S.queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)tid;
+            }
         }
     };
     bool act; unsigned bal;
@@ -433,16 +442,9 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
     for (int sp = 0; sp < 4; ++sp) {
             const int si = sp >> 1, sj = sp & 1, fb = sp & 1;                 // sub-phase order i outer / j inner (morph.cu:1281-1345)
             SlotBuf &SB = S.slot[phase & 1u];
-            // deterministic compaction (slot order) so every CTA of the cluster builds the same queue
             int qn = 0; unsigned stat_any = 0;
 #pragma unroll
             for (int k = 0; k < NPIX / 32; k++) { qn += S.warp_cnt[fb][k]; stat_any |= S.stat_any[fb][k]; }
-            if (tid < NPIX && act) {
-                int base = 0;
-                for (int k = 0; k < warp; k++) base += S.warp_cnt[fb][k];
-                S.queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)tid;
-            }
-            if (qn > 0) __syncthreads();
             TR(2);
 #ifdef VM_TRACE
             if (threadIdx.x == 0 && rank == 0) { atomicAdd(&g_trace[15], (unsigned long long)qn); atomicAdd(&g_trace[31], 1ull); }   // active pixels / sub-phases
