@@ -1,0 +1,127 @@
+"""ctypes binding of oracle/_ref/libref_devfn.so: the reference's own device code (Algorithm/morph.cu, upsample.cu,
+render.cu) and stencils.cpp compiled for the host by oracle/refdev/make_refdev.py.
+
+TEST INFRASTRUCTURE ONLY (tests/test_oracle_refdev.py): it pins the oracle's restatement to reference code.  The product
+package never imports this module.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PATH = os.path.join(_HERE, "_ref", "libref_devfn.so")
+
+from .pyoracle import FIELDS as po_fields
+
+_F2 = ("v", "mean", "var", "luma", "tps_b", "ui_b", "temp_ref")
+_F1 = ("cross", "value", "counter", "tps_axy", "ui_axy", "temp_mask")
+STATE = _F2 + _F1 + ("impmask",)
+
+
+class RefLevelC(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("w", "h", "d", "rs", "ps", "irs", "ips")] + [("inv_wh", C.c_float), ("factor_d", C.c_float)] +
+                [(n, C.c_void_p) for n in _F2] + [(n, C.c_void_p) for n in _F1] + [("impmask", C.c_void_p)] +
+                [(n, C.c_void_p) for n in ("img0", "img1", "f0", "f1", "b0", "b1")])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(PATH):
+            return None
+        L = C.CDLL(PATH)
+        ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+        L.ref_setup_stencils.argtypes = [C.c_int]
+        L.ref_stencils_get.argtypes = [C.c_int, ip, ip, ip, fp]
+        L.ref_set_params.argtypes = [C.c_float] * 6 + [C.c_int]
+        L.ref_ssim.argtypes = [C.c_float] * 7
+        L.ref_ssim.restype = C.c_float
+        L.ref_calc_border.argtypes = [C.c_int] * 4 + [ip]
+        L.ref_initialize_level.argtypes = [C.POINTER(RefLevelC), C.c_float]
+        L.ref_sweep_launch.argtypes = [C.POINTER(RefLevelC)] + [C.c_int] * 4
+        L.ref_optimize_frame.argtypes = [C.POINTER(RefLevelC), C.c_int, C.c_int, C.c_float]
+        L.ref_initialize_temp.argtypes = [C.POINTER(RefLevelC), C.c_int, C.c_int]
+        L.ref_infill_frame.argtypes = [C.POINTER(RefLevelC), C.c_int]
+        u8 = C.POINTER(C.c_uint8)
+        L.ref_render_halfway.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, u8, u8, fp, fp]
+        _lib = L
+    return _lib
+
+
+def stencils(impmask_rowstride):
+    io = np.zeros((5, 5, 5, 5), np.int32)
+    im = np.zeros((5, 5, 3, 3), np.int32)
+    off = np.zeros((3, 3), np.int32)
+    tps = np.zeros((5, 5, 5, 5), np.float32)
+    ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+    lib().ref_stencils_get(impmask_rowstride, io.ctypes.data_as(ip), im.ctypes.data_as(ip), off.ctypes.data_as(ip), tps.ctypes.data_as(fp))
+    return io, im, off, tps
+
+
+def set_params(p):
+    lib().ref_set_params(p["w_temp"], p["w_ui"], p["w_tps"], p["w_ssim"], p["ssim_clamp"], p["eps"], int(p["bcond"]))
+
+
+class RefLevel:
+    """One pyramid level's state as numpy arrays (the oracle's layout), operated on by the reference's device code."""
+
+    def __init__(self, oracle, l):
+        i = oracle.info(l)
+        self.info = i
+        self.a = {}
+        for n in STATE:                                   # arrays the oracle has not allocated yet (before initialize_level) start as zeros
+            shp, dt = oracle._shape(l, n)
+            have = oracle.L.vo_field_bytes(oracle.h, l, po_fields[n]) == int(np.prod(shp)) * 4
+            self.a[n] = oracle.get(l, n).copy() if have else np.zeros(shp, dt)
+        self.img = {n: oracle.get(l, n).copy() for n in ("img0", "img1")}
+        self.flow = {}
+        if i["d"] > 1:
+            self.flow = {n: oracle.get(l, n).copy() for n in ("f0", "f1", "b0", "b1")}
+        c = RefLevelC()
+        c.w, c.h, c.d, c.rs, c.ps, c.irs, c.ips = i["w"], i["h"], i["d"], i["rowstride"], i["pagestride"], i["impmask_rowstride"], i["impmask_pagestride"]
+        c.inv_wh, c.factor_d = i["inv_wh"], i["factor_d"]
+        for n in STATE:
+            setattr(c, n, self.a[n].ctypes.data)
+        c.img0, c.img1 = self.img["img0"].ctypes.data, self.img["img1"].ctypes.data
+        for n in ("f0", "f1", "b0", "b1"):
+            setattr(c, n, self.flow[n].ctypes.data if n in self.flow else None)
+        self.c = c
+        lib().ref_setup_stencils(i["impmask_rowstride"])          # Morph::initialize_level, morph.cu:266-279
+
+    def zero_state(self):
+        """morph.cu:298-314: every per-level array except v is zero-filled (improving_mask is written by its kernel)."""
+        for n in STATE:
+            if n != "v":
+                self.a[n][...] = 0
+
+    def initialize_level(self, ssim_clamp):
+        lib().ref_initialize_level(C.byref(self.c), ssim_clamp)
+
+    def sweep_launch(self, frame, flag, offx, offy):
+        return bool(lib().ref_sweep_launch(C.byref(self.c), frame, int(flag), offx, offy))
+
+    def optimize_frame(self, frame, flag, max_iter):
+        return lib().ref_optimize_frame(C.byref(self.c), frame, int(flag), float(max_iter))
+
+    def initialize_temp(self, frame, direction):
+        lib().ref_initialize_temp(C.byref(self.c), frame, direction)
+
+    def infill_frame(self, frame):
+        lib().ref_infill_frame(C.byref(self.c), frame)
+
+
+def render_halfway(w, h, ex, color_fa, geo_fa, color_from, ext0, ext1, vec, qpath=None):
+    rowstride = (w + 31) // 32 * 32
+    out = np.zeros((h, rowstride, 3), np.uint8)
+    ext0 = np.ascontiguousarray(ext0, np.uint8)
+    ext1 = np.ascontiguousarray(ext1, np.uint8)
+    vec = np.ascontiguousarray(vec, np.float32)
+    qp = np.ascontiguousarray(qpath, np.float32) if qpath is not None else None
+    u8, fp = C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+    lib().ref_render_halfway(out.ctypes.data_as(u8), rowstride, w, h, ex, color_fa, geo_fa, color_from, ext0.ctypes.data_as(u8),
+                             ext1.ctypes.data_as(u8), vec.ctypes.data_as(fp), qp.ctypes.data_as(fp) if qp is not None else None)
+    return out

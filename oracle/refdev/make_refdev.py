@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""oracle/refdev/make_refdev.py -- builds oracle/_ref/libref_devfn.so: the REFERENCE's own CUDA device code for the hot
+path (Algorithm/morph.cu, upsample.cu, render.cu) and its stencils.cpp, compiled for the HOST behind the SIMT emulator of
+simt.h, so tests can check the oracle's restatement against reference code (tests/test_oracle_refdev.py).
+
+TEST INFRASTRUCTURE ONLY.  Nothing of the reference is copied into the repository: the device functions are cut out of
+the reference files where they lie (by the anchors below, not by line number) into a temporary translation unit that is
+deleted after compilation; only the shared library lands in oracle/_ref/ (git-ignored, travels to the GPU box).
+The reference's headers (util/dmath.h, util/linalg.h, stencils.h, Pyramid.h, parameters.h) are included in place;
+stubs/ only holds three stand-ins for things that do not exist on this machine (OpenCV-C++, CUDA's internal
+device_functions.h, and the case-insensitive "pyramid.h").
+
+    python oracle/refdev/make_refdev.py [--ref /root/reference] [--keep]
+"""
+import argparse
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT_DIR = os.path.join(HERE, "..", "_ref")
+OUT = os.path.join(OUT_DIR, "libref_devfn.so")
+
+# (file, regex of the first line taken, regex of the first line NOT taken, regex of trailing lines to drop or None)
+SPANS = [
+    # isignbit, calc_border, ssim                                   morph.cu:35-118
+    ("Algorithm/morph.cu", r"^__device__ int isignbit\(", r"^// Level processing", None),
+    # INIT_* constants, kernel_initialize_level, init_improving_mask  morph.cu:170-261
+    ("Algorithm/morph.cu", r"^const int INIT_BW", r"^void Morph::initialize_level", None),
+    # OPT_* constants ... kernel_optimize_level                     morph.cu:594-1345 (stops before the host helper addressof)
+    ("Algorithm/morph.cu", r"^const int OPT_BW", r"^T \*addressof\(", r"^template <class T>\s*$|^\s*$"),
+    # temp_ref, interpolate_temp_ref, smooth, fill_zeros_x/y, kernel_initialize_temp   upsample.cu:28-211
+    ("Algorithm/upsample.cu", r"^__global__ void temp_ref\(", r"^void initialize_temp\(", None),
+    # kernel_render_halfway_image                                   render.cu:16-60
+    ("Algorithm/render.cu", r"^__global__ void kernel_render_halfway_image\(", r"^void render_halfway_image\(", None),
+]
+
+
+def cut(text, first, stop, drop, fname):
+    lines = text.split("\n")
+    a = next((i for i, l in enumerate(lines) if re.search(first, l)), None)
+    if a is None:
+        raise SystemExit(f"{fname}: anchor {first!r} not found")
+    b = next((i for i in range(a + 1, len(lines)) if re.search(stop, lines[i])), None)
+    if b is None:
+        raise SystemExit(f"{fname}: stop anchor {stop!r} not found")
+    while drop and b > a and re.search(drop, lines[b - 1]):
+        b -= 1
+    return f"// ---- {fname}:{a + 1}-{b} (extracted at build time) ----\n" + "\n".join(lines[a:b]) + "\n"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default=os.environ.get("REF", "/root/reference"))
+    ap.add_argument("--keep", action="store_true", help="keep the temporary translation unit (prints its path)")
+    args = ap.parse_args()
+    ref = args.ref
+    if not os.path.isdir(os.path.join(ref, "Algorithm")):
+        print(f"reference tree absent ({ref}): keeping prebuilt oracle/_ref/libref_devfn.so")
+        return 0
+    os.makedirs(OUT_DIR, exist_ok=True)
+    parts = ['#include "simt.h"\n#include <util/dmath.h>\n#include <util/linalg.h>\n#include "stencils.h"\n#include "Pyramid.h"\n#include "prelude.h"\n']
+    for fname, first, stop, drop in SPANS:
+        with open(os.path.join(ref, fname), encoding="latin-1") as f:
+            parts.append(cut(f.read().replace("\r\n", "\n"), first, stop, drop, fname))
+    parts.append('#include "capi.inc"\n')
+    tmp = tempfile.mkdtemp(prefix="refdev_")
+    tu = os.path.join(tmp, "refdev_tu.cpp")
+    with open(tu, "w") as f:
+        f.write("\n".join(parts))
+    pre = os.path.join(tmp, "pre.h")
+    with open(pre, "w") as f:
+        # linalg.hpp:369 names an undeclared `mat` inside a template body MSVC never checks; __min / __max are MSVC macros
+        f.write("#include <cstring>\nstatic int mat;\n#define __min(a,b) ((a)<(b)?(a):(b))\n#define __max(a,b) ((a)>(b)?(a):(b))\n")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    inc = ["-I" + HERE, "-I" + os.path.join(HERE, "stubs"), "-I" + os.path.join(ref, "include"), "-I" + os.path.join(ref, "Algorithm"),
+           "-I/usr/local/cuda/include"]
+    # IEEE fp32, no contraction: the arithmetic contract of DESIGN.md section 2 (the reference binary itself was built with
+    # -use_fast_math, which no CPU can reproduce)
+    flags = ["-O2", "-std=c++17", "-fPIC", "-w", "-DNDEBUG", "-DCUDA_SM=35", "-ffp-contract=off", "-fno-fast-math", "-include", pre]
+    cmd = [cxx] + flags + inc + ["-shared", "-o", OUT, tu, os.path.join(ref, "Algorithm", "stencils.cpp")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-6000:])
+        print("temporary translation unit kept at", tu)
+        raise SystemExit("g++ failed building libref_devfn.so")
+    if args.keep:
+        print("translation unit:", tu)
+    else:
+        os.remove(tu); os.remove(pre); os.rmdir(tmp)
+    print(os.path.normpath(OUT))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -6,13 +6,22 @@
 // bench.py's cpu_baseline / --impl reference legs may use it, and only as the
 // checker / CPU baseline, never as the thing measured or shipped.
 //
-// Parity status: the reference ships no tests, golden vectors or fixtures for
-// this path and its optimizer (Algorithm/morph.cu) cannot be
-// compiled with CUDA 12 (texture references).  This oracle is therefore
-// "parity unpinned" for the optimizer/upsample/render/qpath parts; it is
-// pinned (a) for the resampler against the reference's own include/resample
-// sources compiled in place (oracle/_ref, see Makefile) and (b) by the
-// reference-internal cross-checks of SURVEY.md section 4.
+// Parity status.  The reference ships no tests, golden vectors or fixtures for this path and its CUDA
+// files cannot be built with CUDA 12 (texture references), so the oracle is pinned to reference CODE instead:
+//  (a) resampler: the reference's include/resample sources compiled in place (oracle/_ref/libref_resample.so,
+//      tests/test_oracle_resample.py) -- bit-equal;
+//  (b) stencil tables: the reference's Algorithm/stencils.cpp compiled in place -- equal (all 25 border classes);
+//  (c) calc_border, ssim, kernel_initialize_level, init_improving_mask, kernel_optimize_level with every device
+//      function under it (ssim_change, energy_change, compute_gradient, fold-over test, golden-section search,
+//      commit_pixel_motion, Load/Update/SaveSSIM), kernel_render_halfway_image: the reference's own text, cut out of
+//      morph.cu / render.cu at build time and run on the host by the SIMT emulator of oracle/refdev -- bit-equal for
+//      whole launches, frames and pyramids (sum_mode = 0), tests/test_oracle_refdev.py;
+//  (d) temp_ref / interpolate_temp_ref / kernel_initialize_temp / smooth / fill_zeros_x (upsample.cu): the same way,
+//      within 2e-5 (float atomics there, order-free fixed point here);
+//  (e) the reference-internal cross-checks of SURVEY.md section 4.
+// Still "parity unpinned" (host / third-party code of the reference that cannot run here): the coarse dense solve
+// (cv::Mat::inv, D4), rod::upsample's hardware-bilinear prolongation, the host UI splat, MatchingThread's Resize,
+// QuadraticPath (cuBLAS / cuSPARSE CG, D6).  The texture unit itself (D1) and -use_fast_math are not modelled.
 //
 // Each function cites the reference file:line it follows
 // (paths relative to /root/reference).

@@ -1,0 +1,218 @@
+"""The oracle's restatement against the REFERENCE's own code, executed on the host.
+
+oracle/refdev/make_refdev.py cuts the device functions out of /root/reference/Algorithm/{morph,upsample,render}.cu at
+build time (nothing is copied into the repository), compiles them -- together with the reference's stencils.cpp, against
+the reference's own headers -- behind the SIMT emulator of oracle/refdev/simt.h into oracle/_ref/libref_devfn.so.
+These tests run kernel_initialize_level, init_improving_mask, kernel_optimize_level (whole launches, whole frames, whole
+pyramids), temp_ref / interpolate_temp_ref / kernel_initialize_temp, the temporal in-fill kernels and
+kernel_render_halfway_image from that library and require the oracle to agree with them:
+
+  * bit for bit wherever the reference's arithmetic is deterministic (everything except the two float-atomic scatters);
+    the oracle runs with sum_mode=0 (the reference's sequential 25-term sum; tests/test_oracle_core.py shows that the
+    tree order the GPU uses, sum_mode=1, gives the same vectors), the emulator runs a block's threads in row-major order,
+    which is the accumulation order the oracle fixes for the commit atomics (deviation D2);
+  * within 2e-5 relative for the forward splat (temp_ref), where the oracle accumulates 2^-32 fixed point instead of
+    float atomics (order-independent by construction).
+
+The only thing both sides share by definition is the texture fetch (deviation D1: fp32 bilinear instead of the
+hardware's 9-bit weights); everything else on the reference side is the reference's text.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyrefdev as rd
+
+pytestmark = pytest.mark.skipif(rd.lib() is None, reason="oracle/_ref/libref_devfn.so not built (needs /root/reference)")
+
+OFFSETS = ((0, 0), (64, 0), (0, 16), (64, 16))            # morph.cu:1382-1385
+
+
+def _equal_state(R, o, l, what, skip=()):
+    for k in rd.STATE:
+        if k in skip:
+            continue
+        np.testing.assert_array_equal(R.a[k], o.get(l, k), err_msg=f"{what}: {k}")
+
+
+def test_stencil_tables_equal_reference_stencils_cpp(oracle_lib):
+    """calc_nb_io_stencil / calc_nb_improvmask_check_stencil / calc_tps_stencil of Algorithm/stencils.cpp (compiled from the
+    reference's source) == the oracle's tables == the product's own formulation (vm_stencils_get, host arithmetic)."""
+    from videomorphing_b200 import api
+    oio, oim, otps = oracle_lib.stencils()
+    pio, pim, ptps = api.stencils()
+    for irs in (4, 22, 258):
+        io, im, off, tps = rd.stencils(irs)
+        np.testing.assert_array_equal(io, oio)
+        np.testing.assert_array_equal(im, oim)
+        np.testing.assert_array_equal(tps, otps)
+        np.testing.assert_array_equal(io, pio)
+        np.testing.assert_array_equal(im, pim)
+        np.testing.assert_array_equal(tps, ptps)
+        # stencils.cpp:120-125: offsets of the 3x3 neighbouring mask cells
+        assert off.tolist() == [[(i - 1) * irs + (j - 1) for j in range(3)] for i in range(3)]
+
+
+def test_ssim_and_calc_border_equal_reference(oracle_lib):
+    L, R = oracle_lib.lib(), rd.lib()
+    rng = np.random.default_rng(7)
+    for k in range(3000):
+        n = float(rng.integers(0, 26))
+        x = rng.uniform(0, 255, (max(int(n), 1), 2)).astype(np.float32)
+        if k % 7 == 0:
+            x[:, 1] = x[:, 0]                              # perfectly correlated
+        if k % 11 == 0:
+            x[:] = x[0]                                    # zero variance (the max(0, var) clamp)
+        m = x.sum(0, dtype=np.float32); v = (x * x).sum(0, dtype=np.float32)
+        c = np.float32((x[:, 0] * x[:, 1]).sum(dtype=np.float32))
+        clampv = float(rng.choice([0.0, 0.0, 0.3]))
+        a = L.vo_ssim(m[0], m[1], v[0], v[1], c, n, clampv)
+        b = R.ref_ssim(m[0], m[1], v[0], v[1], c, n, clampv)
+        assert np.float32(a).tobytes() == np.float32(b).tobytes(), (n, m, v, c, a, b)
+    import ctypes as C
+    out4 = np.zeros(4, np.int32); out2 = np.zeros(2, np.int32)
+    ip = C.POINTER(C.c_int)
+    for w in (4, 5, 6, 9):
+        for h in (4, 7):
+            for px in range(w):
+                for py in range(h):
+                    L.vo_calc_border(px, py, w, h, out4.ctypes.data_as(ip))
+                    R.ref_calc_border(px, py, w, h, out2.ctypes.data_as(ip))
+                    assert (out4[0], out4[1]) == (out2[0], out2[1]) == (out4[2], out4[3])
+
+
+@pytest.mark.parametrize("w,h,bcond,npts,max_iter", [(96, 64, 0, 0, 24), (80, 56, 1, 5, 20), (70, 45, 2, 3, 16)])
+def test_whole_pyramid_equals_reference_kernels(oracle_lib, w, h, bcond, npts, max_iter):
+    """Coarse to fine over every optimised level: kernel_initialize_level + init_improving_mask, then the do / while of
+    Morph::optimize_level (morph.cu:1377-1391) with the reference's kernel_optimize_level -- all state arrays, the
+    improving masks and the iteration counts equal the oracle's, bit for bit, at every level.  (The coarse solve, the
+    prolongation and the UI splat are host / library code in the reference and stay restatements: the reference side
+    takes them from the oracle.)"""
+    from videomorphing_b200 import synth
+    rgb0, rgb1, field = synth.image_pair(w, h, 100 + w, 200 + h, 3.0)
+    o = oracle_lib.Oracle(dict(max_iter=max_iter, bcond=bcond), sum_mode=0)
+    n = o.build(rgb0, rgb1)
+    if npts:
+        o.set_constraints(*synth.point_pairs(npts, w, h, 7, field, margin=6))
+    rd.set_params(o.params)
+    o.coarse_solve()
+    mi = np.float32(max_iter)
+    for l in range(n - 2, 0, -1):
+        o.upsample(l)
+        R = rd.RefLevel(o, l)                      # v of this level after the prolongation
+        R.zero_state()
+        o.initialize_level(l)
+        R.initialize_level(o.params["ssim_clamp"])
+        R.a["ui_axy"][...] = o.get(l, "ui_axy")   # host UI splat (morph.cu:345-388) is not device code
+        R.a["ui_b"][...] = o.get(l, "ui_b")
+        _equal_state(R, o, l, f"initialize_level {l}")
+        it_o = o.optimize_frame(l, 0, False, float(mi))
+        it_r = R.optimize_frame(0, False, float(mi))
+        assert it_o == it_r, (l, it_o, it_r)
+        _equal_state(R, o, l, f"optimize level {l}")
+        mi = np.float32(mi / np.float32(2))
+
+
+def test_every_launch_equals_reference_kernel(oracle_lib):
+    """Launch by launch (4 offsets x 4 iterations) on a level with several tiles, incl. the improving flag."""
+    from videomorphing_b200 import synth
+    rgb0, rgb1, field = synth.image_pair(150, 50, 31, 32, 4.0)
+    o = oracle_lib.Oracle(dict(max_iter=8), sum_mode=0)
+    n = o.build(rgb0, rgb1)
+    rd.set_params(o.params)
+    o.coarse_solve()
+    for l in range(n - 2, 1, -1):
+        o.upsample(l); o.initialize_level(l); o.optimize_frame(l, 0, False, 8.0)
+    o.upsample(1)
+    R = rd.RefLevel(o, 1); R.zero_state()
+    o.initialize_level(1); R.initialize_level(0.0)
+    _equal_state(R, o, 1, "init")
+    for it in range(4):
+        for ox, oy in OFFSETS:
+            a, b = o.sweep_launch(1, 0, False, ox, oy), R.sweep_launch(0, False, ox, oy)
+            assert a == b, (it, ox, oy)
+            _equal_state(R, o, 1, f"iteration {it} offset {(ox, oy)}")
+
+
+@pytest.fixture(scope="module")
+def small_video(oracle_lib):
+    from videomorphing_b200 import synth
+    v0, v1, flows, field = synth.video_pair(64, 48, 5, 51, 52, 3.0)
+    return v0, v1, flows
+
+
+def test_video_chain_equals_reference_kernels(oracle_lib, small_video):
+    """The temporal path on the finest level of a 5-frame video: initialize_temp (temp_ref + interpolate_temp_ref +
+    kernel_initialize_temp, upsample.cu:214-258) within 2e-5 of the reference's float atomics, then the flagged sweep
+    (temporal energy term, morph.cu:752-760) bit for bit from the same temp.ref / temp.mask."""
+    v0, v1, flows = small_video
+    o = oracle_lib.Oracle(dict(max_iter=12), sum_mode=0)
+    n = o.build(v0, v1, flows=flows)
+    rd.set_params(o.params)
+    o.coarse_solve()
+    for l in range(n - 2, 1, -1):
+        o.upsample(l); o.initialize_level(l); o.optimize_level(l, 12.0)
+    l = 1
+    o.upsample(l)
+    R = rd.RefLevel(o, l); R.zero_state()
+    o.initialize_level(l); R.initialize_level(0.0)
+    _equal_state(R, o, l, "init (all frames)")
+    d = o.info(l)["d"]
+    mid = d // 2
+    assert o.optimize_frame(l, mid, False, 12.0) == R.optimize_frame(mid, False, 12.0)
+    _equal_state(R, o, l, "middle frame")
+    for i, direction in [(mid + 1, -1), (mid + 2, -1), (mid - 1, 1), (mid - 2, 1)]:
+        if i < 0 or i >= d:
+            continue
+        o.initialize_temp(l, i, direction)
+        R.initialize_temp(i, direction)
+        for k in ("temp_ref", "temp_mask"):
+            a, b = R.a[k][i], o.get(l, k)[i]
+            assert (b != 0).any(), k
+            np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-5, err_msg=f"initialize_temp frame {i}: {k}")
+            R.a[k][i] = b                                   # continue from identical inputs
+        assert o.optimize_frame(l, i, True, 12.0) == R.optimize_frame(i, True, 12.0)
+        _equal_state(R, o, l, f"frame {i}")
+
+
+def test_temporal_infill_equals_reference_kernels(oracle_lib):
+    """upsample()'s in-fill of the frames a temporally subsampled level does not have (upsample.cu:297-335: temp_ref from
+    both neighbours, interpolate_temp_ref, smooth, fill_zeros_x, fill_zeros_y) against the oracle's upsample_level."""
+    from videomorphing_b200 import synth
+    v0, v1, flows, _ = synth.video_pair(40, 32, 17, 61, 62, 2.0)
+    o = oracle_lib.Oracle(dict(max_iter=6), sum_mode=0)
+    n = o.build(v0, v1, flows=flows)
+    depths = [o.info(l)["d"] for l in range(n)]
+    dst = next(l for l in range(n - 2, 0, -1) if depths[l] > depths[l + 1])     # first level that doubles the depth
+    # a known smooth field on the coarser level (the optimizer is not under test here)
+    ic = o.info(dst + 1)
+    vc = np.zeros((ic["d"], ic["h"], ic["rowstride"], 2), np.float32)
+    for z in range(ic["d"]):
+        vc[z, :, :ic["w"]] = synth.smooth_warp(ic["w"], ic["h"], 600 + z, 1.5)
+    o.set(dst + 1, "v", vc)
+    o.upsample(dst)
+    want = o.get(dst, "v")
+    R = rd.RefLevel(o, dst)
+    d = depths[dst]
+    for i in range(1, d, 2):                                # upsample.cu:299-303
+        if i == d - 1:
+            continue
+        R.a["v"][i] = 0                                     # dest.v.fill(0) before the splat, upsample.cu:262-263
+        R.infill_frame(i)
+        assert np.abs(want[i]).max() > 0
+        np.testing.assert_allclose(R.a["v"][i], want[i], rtol=2e-5, atol=2e-5, err_msg=f"in-filled frame {i}")
+
+
+@pytest.mark.parametrize("color_from", [0, 1, 2])
+def test_render_equals_reference_kernel(oracle_lib, color_from):
+    """kernel_render_halfway_image (render.cu:16-60) incl. a non-zero quadratic path: byte-identical frames."""
+    from videomorphing_b200 import synth
+    w, h = 120, 70
+    ex = int(max(w, h) * 0.1)
+    rgb0, rgb1, field = synth.image_pair(w, h, 71, 72, 5.0)
+    e0, e1 = synth.extended_rgba(rgb0[0], ex), synth.extended_rgba(rgb1[0], ex)
+    vec = (field / 2).astype(np.float32)
+    qp = (0.3 * synth.smooth_warp(w, h, 73, 2.0)).astype(np.float32)
+    for fa, q in ((0.0, None), (0.37, None), (0.5, qp), (1.0, qp)):
+        a = rd.render_halfway(w, h, ex, fa, fa, color_from, e0, e1, vec, q)
+        b = oracle_lib.render_halfway(w, h, ex, fa, fa, color_from, e0, e1, vec, q)
+        np.testing.assert_array_equal(a[:, :w], b[:, :w])
