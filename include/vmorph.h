@@ -136,6 +136,14 @@ double vm_morph_executed_pixel_iters(const vm_morph *m);
  * and their count: the live measurement behind bench.py's roofline (no reference counterpart; the reference only
  * clocks the whole stage, MatchingThread.cpp:141-145) */
 double vm_morph_sweep_ms(const vm_morph *m, uint64_t *launches_out);
+/* attempted pixel updates of the sweep launches collected so far: active pixels x colour rounds, i.e. how many times
+ * optimize_pixel (morph.cu:1030-1083) got past its improving-mask and border tests -- the unit of the FP32 roofline
+ * (about 15 kFLOP each); and the length (ms) of the union of the sweep launches' device-time intervals
+ * (launches of concurrent frame chains overlap), i.e. the part of the run during which a sweep kernel was executing. */
+double vm_morph_attempted_updates(const vm_morph *m);
+double vm_morph_sweep_busy_ms(const vm_morph *m);
+/* attempted pixel updates of every logged sweep launch, in the order of vm_morph_iters_log; returns count */
+int vm_morph_updates_log(const vm_morph *m, int max_entries, uint32_t *out);
 /* device ms of every logged sweep launch, in the order of vm_morph_iters_log; returns count */
 int vm_morph_ms_log(const vm_morph *m, int max_entries, float *out);
 /* (level, frame, iterations) triples logged by optimize_level; returns count */
@@ -171,6 +179,17 @@ int vm_morph_get_vectors(vm_morph *m, float *host_out, void *stream);
  * size, x (w0/w_el, h0/h_el), frames written at min(i*factor, d0-1) and the frames in between filled by the temporal
  * lerp of MatchingThread.cpp:61-78; frames the reference leaves untouched are zero. */
 int vm_morph_get_vectors_level(vm_morph *m, int level, float *host_out, void *stream);
+/* update_result without the host copy: leaves the level-0 sized field of level `level` on the device (the buffer
+ * vm_morph_get_vectors_level downloads) for vm_morph_render_frames. */
+int vm_morph_extract(vm_morph *m, int level, void *stream);
+/* RenderWidget's playback / export loop over the frames of the video (UI/RenderWidget.cpp:85-166 -> RenderStage2, 229-266, once
+ * per frame): renders frames [frame0, frame0 + nframes) from the device-resident field of the last vm_morph_extract /
+ * vm_morph_get_vectors*.  ext0 / ext1 = nframes consecutive host RGBA8 extended frames (w+2ex) x (h+2ex) of those frames
+ * (Pyramid::_extends1/2), color_fa / geo_fa one value per frame, qpath = nframes x h*w float2 (host) or NULL, out =
+ * nframes x h*w*3 RGB8 (host).  Uploads, rendering and downloads of consecutive frames overlap (pinned host memory makes
+ * the copies asynchronous). */
+int vm_morph_render_frames(vm_morph *m, int frame0, int nframes, uint8_t *out, int ex, const float *color_fa, const float *geo_fa,
+                           int color_from, const uint8_t *ext0, const uint8_t *ext1, const float *qpath, void *stream);
 /* stencil tables (stencils.h:13-19): iomask[5][5][5][5], improvmask[5][5][3][3], tps[5][5][5][5]; host arithmetic */
 int vm_stencils_get(int32_t *iomask625, int32_t *improvmask225, float *tps625);
 

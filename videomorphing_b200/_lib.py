@@ -41,8 +41,8 @@ EXPORTS = [
     "vm_pyramid_create", "vm_pyramid_destroy", "vm_level_schedule", "vm_pyramid_alloc", "vm_pyramid_build",
     "vm_pyramid_num_levels", "vm_pyramid_level_info", "vm_level_get", "vm_level_set", "vm_morph_create", "vm_morph_destroy",
     "vm_morph_set_tracks", "vm_morph_set_constraints", "vm_morph_run", "vm_morph_progress", "vm_morph_executed_pixel_iters",
-    "vm_morph_sweep_ms", "vm_morph_ms_log", "vm_morph_iters_log", "vm_level_cpu_solve", "vm_level_upsample", "vm_level_initialize", "vm_level_init_temp", "vm_level_upsample_frames", "vm_level_initialize_frames",
-    "vm_level_optimize_frame", "vm_level_optimize", "vm_level_optimize_chains", "vm_level_dev_ptr", "vm_level_mark_v_valid", "vm_dev_copy", "vm_level_energy", "vm_morph_get_vectors", "vm_morph_get_vectors_level", "vm_stencils_get",
+    "vm_morph_sweep_ms", "vm_morph_attempted_updates", "vm_morph_sweep_busy_ms", "vm_morph_updates_log", "vm_morph_ms_log", "vm_morph_iters_log", "vm_level_cpu_solve", "vm_level_upsample", "vm_level_initialize", "vm_level_init_temp", "vm_level_upsample_frames", "vm_level_initialize_frames",
+    "vm_level_optimize_frame", "vm_level_optimize", "vm_level_optimize_chains", "vm_level_dev_ptr", "vm_level_mark_v_valid", "vm_dev_copy", "vm_level_energy", "vm_morph_get_vectors", "vm_morph_get_vectors_level", "vm_morph_extract", "vm_morph_render_frames", "vm_stencils_get",
     "vm_render_halfway_dev", "vm_render_halfway", "vm_render_sequence", "vm_qpath_optimize", "vm_qpath_optimize_frames", "vm_dev_alloc", "vm_dev_free", "vm_dev_upload",
     "vm_dev_download", "vm_stream_sync", "vm_kernel_launch_count", "vm_selftest_exact_arith",
 ]
@@ -85,6 +85,11 @@ def load():
     L.vm_morph_executed_pixel_iters.restype = C.c_double
     L.vm_morph_sweep_ms.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.vm_morph_sweep_ms.restype = C.c_double
+    L.vm_morph_attempted_updates.argtypes = [vp]
+    L.vm_morph_attempted_updates.restype = C.c_double
+    L.vm_morph_sweep_busy_ms.argtypes = [vp]
+    L.vm_morph_sweep_busy_ms.restype = C.c_double
+    L.vm_morph_updates_log.argtypes = [vp, i32, vp]
     L.vm_morph_ms_log.argtypes = [vp, i32, vp]
     L.vm_morph_iters_log.argtypes = [vp, i32, vp]
     L.vm_level_cpu_solve.argtypes = [vp, vp]
@@ -102,6 +107,8 @@ def load():
     L.vm_level_energy.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.vm_morph_get_vectors.argtypes = [vp, vp, vp]
     L.vm_morph_get_vectors_level.argtypes = [vp, i32, vp, vp]
+    L.vm_morph_extract.argtypes = [vp, i32, vp]
+    L.vm_morph_render_frames.argtypes = [vp, i32, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp]
     L.vm_stencils_get.argtypes = [vp, vp, vp]
     L.vm_render_halfway_dev.argtypes = [vp, i32, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, vp]
     L.vm_render_halfway.argtypes = [i32, vp, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, vp]

@@ -245,6 +245,21 @@ class Morph:
         ms = self.L.vm_morph_sweep_ms(self.h, C.byref(n))
         return ms, n.value
 
+    @property
+    def attempted_updates(self):
+        """Active pixels x colour rounds optimised by the sweep launches so far (FP32-roofline unit, ~15 kFLOP each)."""
+        return self.L.vm_morph_attempted_updates(self.h)
+
+    @property
+    def sweep_busy_ms(self):
+        """Length of the union of the sweep launches' device-time intervals (concurrent chains overlap)."""
+        return self.L.vm_morph_sweep_busy_ms(self.h)
+
+    def updates_log(self):
+        out = np.zeros(1 << 20, np.uint32)
+        n = check(self.L.vm_morph_updates_log(self.h, len(out), _vp(out)))
+        return out[:n].copy()
+
     def ms_log(self):
         """Device ms of every logged sweep launch (same order as iters_log)."""
         out = np.zeros(1 << 20, np.float32)
@@ -262,6 +277,29 @@ class Morph:
         out = np.zeros((i["d"], i["h"], i["w"], 2), np.float32)
         check(self.L.vm_morph_get_vectors_level(self.h, level, _vp(out), stream))
         return out
+
+
+def render_video_frames(morph, frame0, ext0, ext1, color_fa, geo_fa, color_from=1, qpath=None, out=None, stream=None, level=None):
+    """RenderWidget's per-frame loop (UI/RenderWidget.cpp:85-166, RenderStage2 229-266) over frames [frame0, frame0+n) of the
+    video from the vector field the optimizer left on the device.  ext0 / ext1: (n, h+2ex, w+2ex, 4) uint8 extended frames.
+    level: extract that level's field first (None = reuse the last extract / get_vectors).  Returns (n,h,w,3) uint8."""
+    L = _lib.load()
+    ext0 = np.ascontiguousarray(ext0, np.uint8)
+    ext1 = np.ascontiguousarray(ext1, np.uint8)
+    n = ext0.shape[0]
+    i0 = morph.pyramid.info(0)
+    w, h = i0["w"], i0["h"]
+    ex = (ext0.shape[2] - w) // 2
+    cf = np.ascontiguousarray(color_fa, np.float32)
+    gf = np.ascontiguousarray(geo_fa, np.float32)
+    assert len(cf) == n and len(gf) == n and ext0.shape == ext1.shape == (n, h + 2 * ex, w + 2 * ex, 4)
+    qp = np.ascontiguousarray(qpath, np.float32) if qpath is not None else None
+    if out is None:
+        out = np.zeros((n, h, w, 3), np.uint8)
+    if level is not None:
+        check(L.vm_morph_extract(morph.h, level, stream))
+    check(L.vm_morph_render_frames(morph.h, frame0, n, _vp(out), ex, _vp(cf), _vp(gf), int(color_from), _vp(ext0), _vp(ext1), _vp(qp), stream))
+    return out
 
 
 def render_halfway_image(w, h, ex, color_fa, geo_fa, color_from, ext0, ext1, vector, qpath=None, device=0, stream=None):

@@ -11,6 +11,7 @@
 
 namespace vm {
 
+constexpr int VM_MAX_ITER = 1 << 20;
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 
@@ -321,7 +322,8 @@ int vm_level_set(vm_pyramid *p, int level, int field, const void *host_in, size_
 int vm_morph_create(const vm_params *prm, vm_pyramid *pyr, volatile int *run_flag, vm_morph **out) {
     if (!prm || !pyr || !out) { set_error("null argument"); return VM_ERR_ARG; }
     if (pyr->lv.size() < 3) { set_error("pyramid not allocated"); return VM_ERR_STATE; }
-    if (prm->max_iter < 1 || prm->max_iter > 4000 || prm->max_iter_drop_factor <= 0 || prm->eps <= 0) { set_error("bad parameters (max_iter 1..4000, drop > 0, eps > 0)"); return VM_ERR_ARG; }
+    if (prm->max_iter < 1 || prm->max_iter > VM_MAX_ITER || prm->max_iter_drop_factor <= 0 || prm->eps <= 0) { set_error("bad parameters (max_iter 1..%d, drop > 0, eps > 0)", VM_MAX_ITER); return VM_ERR_ARG; }
+    sweep_reload_hooks();
     int rc = use_device(pyr->device); if (rc) return rc;
     vm_morph *m = new vm_morph();
     m->prm = *prm; m->pyr = pyr; m->run_flag = run_flag;
@@ -332,9 +334,9 @@ int vm_morph_create(const vm_params *prm, vm_pyramid *pyr, volatile int *run_fla
         } else cudaGetLastError();
     }
     cudaError_t e = cudaHostAlloc((void **)&m->progress_host, 64, cudaHostAllocMapped);
-    if (e == cudaSuccess) { m->progress_host[0] = 0; e = cudaHostGetDevicePointer((void **)&m->progress_dev, m->progress_host, 0); }
-    if (e == cudaSuccess) e = m->ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(prm->max_iter + 1, 8192));
-    if (e == cudaSuccess) e = m->ctrl2.ensure(sizeof(unsigned) * sweep_ctrl_words(prm->max_iter + 1, 8192));
+    if (e == cudaSuccess) { m->progress_host[0] = 0; m->progress_host[1] = 0; e = cudaHostGetDevicePointer((void **)&m->progress_dev, m->progress_host, 0); }
+    if (e == cudaSuccess) e = m->ctrl.ensure(sizeof(unsigned) * sweep_ctrl_words(std::min(prm->max_iter, 4096) + 1, 8192));
+    if (e == cudaSuccess) e = m->ctrl2.ensure(sizeof(unsigned) * sweep_ctrl_words(std::min(prm->max_iter, 4096) + 1, 8192));
     for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaStreamCreateWithFlags(&m->chain_stream[k], cudaStreamNonBlocking);
     for (int k = 0; k < 3 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&m->chain_ev[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { vm_morph_destroy(m); return cuda_fail(e, "morph_create"); }
@@ -354,6 +356,7 @@ void vm_morph_destroy(vm_morph *m) {
     cudaDeviceSynchronize();
     if (m->run_flag_registered) cudaHostUnregister((void *)m->run_flag);
     if (m->progress_host) cudaFreeHost(m->progress_host);
+    if (m->ev_base) cudaEventDestroy(m->ev_base);
     for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) if (m->chain_stream[k]) cudaStreamDestroy(m->chain_stream[k]);
     for (int k = 0; k < 3; k++) if (m->chain_ev[k]) cudaEventDestroy(m->chain_ev[k]);
@@ -399,6 +402,8 @@ int vm_morph_set_tracks(vm_morph *m, int n_left, const int32_t *left_len, const 
     return upload_cons(m);
 }
 
+// The reference has no iteration limit (int max_iter, morph.h:20); the sweep keeps one flag word per iteration in its
+// control block, so the library accepts up to 2^20 iterations per level (4 MB of flags) -- 1000x the reference default.
 static bool keep_running(vm_morph *m) { return !m->run_flag || *m->run_flag != 0; }
 
 int vm_level_cpu_solve(vm_morph *m, void *stream) {
@@ -522,50 +527,77 @@ static int init_temp_chain(vm_morph *m, int level, int frame, int dir, cudaStrea
     return VM_OK;
 }
 
-// enqueue one frame's optimisation; iterations land in log_dev[seq]
-static int enqueue_frame(vm_morph *m, int level, int frame, int flag, float max_iter, cudaStream_t s, int *seq_out, int chain = 0, int sm_budget = 0) {
-    vm_pyramid *p = m->pyr;
-    Level &L = p->lv[level];
-    int seq = (int)m->seqs.size();
-    if (seq >= (1 << 19)) { set_error("too many sweep launches"); return VM_ERR_STATE; }
-    size_t need = sizeof(unsigned) * (size_t)(seq + 1024);
+// enqueue one frame's optimisation; iterations and attempted updates land in log_dev[2 * seq], [2 * seq + 1]
+static int grow_log(vm_morph *m, size_t launches) {
+    size_t need = sizeof(unsigned) * 2 * (launches + 1024);
     if (m->log_dev.bytes < need) {
-        DevBuf nb; VM_CUDA(nb.ensure(need * 2));
+        vm::DevBuf nb; VM_CUDA(nb.ensure(need * 2));
         VM_CUDA(cudaDeviceSynchronize());
         if (m->log_dev.p) VM_CUDA(cudaMemcpy(nb.p, m->log_dev.p, m->log_dev.bytes, cudaMemcpyDeviceToDevice));
         std::swap(nb.p, m->log_dev.p); std::swap(nb.bytes, m->log_dev.bytes);
     }
+    return VM_OK;
+}
+static int enqueue_frame(vm_morph *m, int level, int frame, int flag, float max_iter, cudaStream_t s, int *seq_out, int chain = 0, int sm_budget = 0) {
+    vm_pyramid *p = m->pyr;
+    Level &L = p->lv[level];
+    int seq = (int)m->seqs.size();
+    if (seq >= (1 << 22)) { set_error("too many sweep launches in one call"); return VM_ERR_STATE; }
+    int rc = grow_log(m, (size_t)seq + 1); if (rc) return rc;
     int iters_cap = (int)ceilf(max_iter) + 1;
     if (iters_cap < 1) iters_cap = 1;
     DevBuf &ctrl = chain ? m->ctrl2 : m->ctrl;
     const size_t cwords = sweep_ctrl_words(iters_cap, sweep_num_tiles(L.w, L.h));
     if (ctrl.bytes < sizeof(unsigned) * cwords) { VM_CUDA(cudaDeviceSynchronize()); VM_CUDA(ctrl.ensure(sizeof(unsigned) * cwords)); }
     VM_CUDA(cudaMemsetAsync(ctrl.p, 0, sizeof(unsigned) * (8 + (size_t)iters_cap + 8), s));      // counters + flags (the tile lists need no clearing)
+    if (seq == 0) {                                       // time origin of this call's launch intervals
+        if (!m->ev_base) VM_CUDA(cudaEventCreate(&m->ev_base));
+        VM_CUDA(cudaEventRecord(m->ev_base, s));
+    }
     m->seqs.push_back({level, frame, (double)L.w * L.h, max_iter});
     while (m->ev.size() < 2 * (size_t)(seq + 1)) { cudaEvent_t e; VM_CUDA(cudaEventCreate(&e)); m->ev.push_back(e); }
     VM_CUDA(cudaEventRecord(m->ev[2 * seq], s));
     VM_CUDA(launch_sweep(make_view(p, level), kparams(m->prm), p->stencils.as<StencilTables>(), frame, flag, max_iter,
                          ctrl.as<unsigned>(), m->run_flag_dev, m->progress_dev, seq, p->sm_count, sm_budget, s));
     VM_CUDA(cudaEventRecord(m->ev[2 * seq + 1], s));
-    VM_CUDA(cudaMemcpyAsync(m->log_dev.as<unsigned>() + seq, ctrl.as<unsigned>() + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
+    VM_CUDA(cudaMemcpyAsync(m->log_dev.as<unsigned>() + 2 * seq, ctrl.as<unsigned>() + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
+    VM_CUDA(cudaMemcpyAsync(m->log_dev.as<unsigned>() + 2 * seq + 1, ctrl.as<unsigned>() + 3, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
     if (seq_out) *seq_out = seq;
     return VM_OK;
 }
 
-// fetch iteration counts of launches [from, seqs.size()) and fold them into the counters
-static int collect_log(vm_morph *m, size_t from, cudaStream_t s) {
+// Fetches the iteration counts of every launch enqueued since the last collection, folds them into the counters and logs,
+// and resets the launch table (events are kept for reuse): a long-lived vm_morph neither leaks events nor runs out of
+// launch numbers.
+static int collect_log(vm_morph *m, size_t /*from*/, cudaStream_t s) {
     size_t n = m->seqs.size();
-    if (from >= n) return VM_OK;
-    std::vector<unsigned> it(n - from);
+    if (!n) return VM_OK;
+    std::vector<unsigned> it(2 * n);
     VM_CUDA(cudaStreamSynchronize(s));
-    VM_CUDA(cudaMemcpy(it.data(), m->log_dev.as<unsigned>() + from, sizeof(unsigned) * (n - from), cudaMemcpyDeviceToHost));
-    for (size_t k = from; k < n; k++) {
-        float ms = 0.f;
+    VM_CUDA(cudaMemcpy(it.data(), m->log_dev.p, sizeof(unsigned) * 2 * n, cudaMemcpyDeviceToHost));
+    std::vector<std::pair<float, float>> iv;
+    iv.reserve(n);
+    for (size_t k = 0; k < n; k++) {
+        float ms = 0.f, t0 = 0.f;
         if (cudaEventElapsedTime(&ms, m->ev[2 * k], m->ev[2 * k + 1]) == cudaSuccess) { m->sweep_ms += ms; m->sweep_launches++; } else cudaGetLastError();
+        if (m->ev_base && cudaEventElapsedTime(&t0, m->ev_base, m->ev[2 * k]) == cudaSuccess) iv.push_back({t0, t0 + ms}); else cudaGetLastError();
         m->ms_log.push_back(ms);
-        m->executed_pixel_iters += m->seqs[k].wh * it[k - from];
-        m->iters_log.push_back(m->seqs[k].level); m->iters_log.push_back(m->seqs[k].frame); m->iters_log.push_back((int)it[k - from]);
+        m->executed_pixel_iters += m->seqs[k].wh * it[2 * k];
+        m->attempted_updates += (double)it[2 * k + 1];
+        m->done_iter += m->seqs[k].wh * m->seqs[k].max_iter;                                  // morph.cu:1391
+        m->iters_log.push_back(m->seqs[k].level); m->iters_log.push_back(m->seqs[k].frame); m->iters_log.push_back((int)it[2 * k]);
+        m->upd_log.push_back(it[2 * k + 1]);
     }
+    // union of the launch intervals: concurrent chains overlap, the union is the time during which a sweep was running
+    std::sort(iv.begin(), iv.end());
+    float lo = 0.f, hi = -1.f;
+    for (auto &x : iv) {
+        if (hi < lo || x.first > hi) { if (hi >= lo) m->sweep_busy_ms += hi - lo; lo = x.first; hi = x.second; }
+        else if (x.second > hi) hi = x.second;
+    }
+    if (hi >= lo) m->sweep_busy_ms += hi - lo;
+    m->seqs.clear();
+    if (m->progress_host) { m->progress_host[0] = 0; m->progress_host[1] = 0; }
     return VM_OK;
 }
 
@@ -573,7 +605,7 @@ int vm_level_optimize_frame(vm_morph *m, int level, int frame, int flag, float m
     if (!m) { set_error("null morph"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
     if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
-    if (frame < 0 || frame >= p->lv[level].d || !(max_iter > 0) || max_iter > 4000) { set_error("bad frame %d / max_iter %g", frame, max_iter); return VM_ERR_ARG; }
+    if (frame < 0 || frame >= p->lv[level].d || !(max_iter > 0) || max_iter > (float)VM_MAX_ITER) { set_error("bad frame %d / max_iter %g", frame, max_iter); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
     size_t from = m->seqs.size();
     rc = enqueue_frame(m, level, frame, flag, max_iter, s, nullptr); if (rc) return rc;
@@ -600,13 +632,7 @@ static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s,
     if (two) {
         sf = m->chain_stream[0]; sb = m->chain_stream[1]; budget = p->sm_count / 2;
         // reserve the launch log up front: growing it needs a device-wide synchronisation
-        size_t need = sizeof(unsigned) * (m->seqs.size() + (size_t)L.d + 1024);
-        if (m->log_dev.bytes < need) {
-            DevBuf nb; VM_CUDA(nb.ensure(need * 2));
-            VM_CUDA(cudaDeviceSynchronize());
-            if (m->log_dev.p) VM_CUDA(cudaMemcpy(nb.p, m->log_dev.p, m->log_dev.bytes, cudaMemcpyDeviceToDevice));
-            std::swap(nb.p, m->log_dev.p); std::swap(nb.bytes, m->log_dev.bytes);
-        }
+        rc = grow_log(m, m->seqs.size() + (size_t)L.d + 1); if (rc) return rc;
         VM_CUDA(cudaEventRecord(m->chain_ev[0], s));
         VM_CUDA(cudaStreamWaitEvent(sf, m->chain_ev[0], 0));
         VM_CUDA(cudaStreamWaitEvent(sb, m->chain_ev[0], 0));
@@ -637,7 +663,7 @@ int vm_level_optimize_chains(vm_morph *m, int level, float max_iter, int chains,
     if (!m) { set_error("null morph"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
     if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
-    if (!(max_iter > 0) || max_iter > 4000 || chains < 0 || chains > 3) { set_error("bad max_iter %g / chains %d", max_iter, chains); return VM_ERR_ARG; }
+    if (!(max_iter > 0) || max_iter > (float)VM_MAX_ITER || chains < 0 || chains > 3) { set_error("bad max_iter %g / chains %d", max_iter, chains); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
     size_t from = m->seqs.size();
     rc = enqueue_level(m, level, max_iter, s, chains); if (rc) return rc;
@@ -668,7 +694,7 @@ int vm_level_optimize(vm_morph *m, int level, float max_iter, void *stream) {
     if (!m) { set_error("null morph"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
     if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
-    if (!(max_iter > 0) || max_iter > 4000) { set_error("bad max_iter %g", max_iter); return VM_ERR_ARG; }
+    if (!(max_iter > 0) || max_iter > (float)VM_MAX_ITER) { set_error("bad max_iter %g", max_iter); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
     size_t from = m->seqs.size();
     rc = enqueue_level(m, level, max_iter, s); if (rc) return rc;
@@ -684,6 +710,8 @@ int vm_morph_run(vm_morph *m, void *stream) {
         if (!p->lv[l].img0.p) { set_error("level %d has no images: call vm_pyramid_build first", l); return VM_ERR_STATE; }
     size_t from = m->seqs.size();
     m->cancelled = false;
+    m->done_iter = 0;
+    m->total_l = (int)p->lv.size() - 1;
     float max_iter = (float)m->prm.max_iter;
     rc = vm_level_cpu_solve(m, s); if (rc) return rc;
     for (int l = m->total_l - 1; l > 0; l--) {
@@ -700,9 +728,9 @@ int vm_morph_run(vm_morph *m, void *stream) {
 
 int vm_morph_progress(const vm_morph *m, int *total_l, int *current_l, double *total_iter, double *current_iter, float *max_iter) {
     if (!m) { set_error("null morph"); return VM_ERR_ARG; }
-    int word = m->progress_host ? *(volatile int *)m->progress_host : 0;
-    size_t seq = (size_t)(word >> 12); int it = word & 4095;
-    double cur = 0; int lvl = m->total_l; float mi = m->max_iter_now;
+    size_t seq = m->progress_host ? (size_t)*(volatile int *)m->progress_host : 0;
+    int it = m->progress_host ? *(volatile int *)(m->progress_host + 1) : 0;
+    double cur = m->done_iter; int lvl = m->total_l; float mi = m->max_iter_now;
     size_t n = m->seqs.size();
     for (size_t k = 0; k < n && k < seq; k++) cur += m->seqs[k].wh * m->seqs[k].max_iter;      // morph.cu:1391
     if (seq < n) { cur += m->seqs[seq].wh * it; lvl = m->seqs[seq].level; mi = m->seqs[seq].max_iter; }
@@ -718,6 +746,14 @@ double vm_morph_sweep_ms(const vm_morph *m, uint64_t *launches_out) {
     if (!m) return 0.0;
     if (launches_out) *launches_out = m->sweep_launches;
     return m->sweep_ms;
+}
+double vm_morph_attempted_updates(const vm_morph *m) { return m ? m->attempted_updates : 0.0; }
+double vm_morph_sweep_busy_ms(const vm_morph *m) { return m ? m->sweep_busy_ms : 0.0; }
+int vm_morph_updates_log(const vm_morph *m, int max_entries, uint32_t *out) {
+    if (!m) return VM_ERR_ARG;
+    int n = (int)m->upd_log.size();
+    for (int i = 0; i < n && i < max_entries; i++) out[i] = m->upd_log[i];
+    return n;
 }
 int vm_morph_iters_log(const vm_morph *m, int max_triples, int32_t *out) {
     if (!m) return VM_ERR_ARG;
@@ -749,8 +785,9 @@ int vm_level_energy(vm_morph *m, int level, int frame, int flag, double *energy_
     return VM_OK;
 }
 
-int vm_morph_get_vectors_level(vm_morph *m, int level, float *host_out, void *stream) {
-    if (!m || !host_out) { set_error("null argument"); return VM_ERR_ARG; }
+// update_result (MatchingThread.cpp:22-84) into the device-resident level-0 sized buffer
+int vm_morph_extract(vm_morph *m, int level, void *stream) {
+    if (!m) { set_error("null argument"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
     if (level < 1 || level >= (int)p->lv.size()) { set_error("bad level %d", level); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
@@ -758,9 +795,20 @@ int vm_morph_get_vectors_level(vm_morph *m, int level, float *host_out, void *st
     if (!L1.v_valid) { set_error("level %d has no result yet", level); return VM_ERR_STATE; }
     int factor = (int)(L0.factor_d / L1.factor_d);                                // MatchingThread.cpp:29
     size_t bytes = sizeof(float2) * (size_t)L0.w * L0.h * L0.d;
-    DevBuf &out = m->extract_buf; VM_CUDA(out.ensure(bytes));
+    DevBuf &out = m->extract_buf;
+    if (out.bytes < bytes) VM_CUDA(cudaDeviceSynchronize());
+    VM_CUDA(out.ensure(bytes));
     VM_CUDA(launch_extract(make_view(p, level), out.as<float2>(), L0.w, L0.h, L0.d, factor, s));
-    VM_CUDA(cudaMemcpyAsync(host_out, out.p, bytes, cudaMemcpyDeviceToHost, s));
+    m->extract_valid = true;
+    return VM_OK;
+}
+
+int vm_morph_get_vectors_level(vm_morph *m, int level, float *host_out, void *stream) {
+    if (!m || !host_out) { set_error("null argument"); return VM_ERR_ARG; }
+    int rc = vm_morph_extract(m, level, stream); if (rc) return rc;
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    size_t bytes = sizeof(float2) * (size_t)p->lv[0].w * p->lv[0].h * p->lv[0].d;
+    VM_CUDA(cudaMemcpyAsync(host_out, m->extract_buf.p, bytes, cudaMemcpyDeviceToHost, s));
     VM_CUDA(cudaStreamSynchronize(s));
     return VM_OK;
 }
@@ -843,6 +891,62 @@ int vm_render_sequence(int device, uint8_t *out, int nframes, int w, int h, int 
         VM_CUDA(cudaEventRecord(Q.copied[b], Q.copy));
     }
     VM_CUDA(cudaStreamSynchronize(Q.copy));
+    VM_CUDA(cudaStreamSynchronize(s));
+    return VM_OK;
+}
+
+// RenderWidget's playback / export loop over the frames of the video (UI/RenderWidget.cpp:85-166 calls RenderStage2 once per
+// frame, each call allocating four cudaArrays and copying everything both ways).  Here the vector field stays where the
+// optimizer left it (vm_morph_extract), the extended frames of frame k+1 go up while frame k renders and frame k-1 comes
+// back: three streams, two sets of staging buffers.
+namespace { struct FrameScratch { cudaStream_t up = nullptr, down = nullptr; cudaEvent_t uploaded[2] = {}, rendered[2] = {}, downloaded[2] = {};
+                                  DevBuf e0[2], e1[2], q[2], o[2]; }; FrameScratch g_frames[16]; }
+
+int vm_morph_render_frames(vm_morph *m, int frame0, int nframes, uint8_t *out, int ex, const float *color_fa, const float *geo_fa,
+                           int color_from, const uint8_t *ext0, const uint8_t *ext1, const float *qpath, void *stream) {
+    if (!m || !out || !ext0 || !ext1 || !color_fa || !geo_fa || nframes < 1 || ex < 0 || color_from < 0 || color_from > 2) { set_error("bad render arguments"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr;
+    const int w = p->lv[0].w, h = p->lv[0].h, d = p->lv[0].d;
+    if (frame0 < 0 || frame0 + nframes > d) { set_error("bad frame range %d+%d of %d", frame0, nframes, d); return VM_ERR_ARG; }
+    if (!m->extract_valid) { set_error("no extracted vector field: call vm_morph_extract / vm_morph_get_vectors first"); return VM_ERR_STATE; }
+    int rc = use_device(p->device); if (rc) return rc;
+    if (p->device >= 16) { set_error("device %d: at most 16 devices", p->device); return VM_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int rowstride = (w + 31) / 32 * 32;                                     // UI/RenderWidget.cpp:235
+    const size_t eb = (size_t)(w + 2 * ex) * (h + 2 * ex) * 4, vb = sizeof(float2) * (size_t)w * h, ob = (size_t)rowstride * h * 3, fb = (size_t)w * h * 3;
+    std::lock_guard<std::mutex> lock(g_render_mu);
+    FrameScratch &F = g_frames[p->device];
+    if (!F.up) {
+        VM_CUDA(cudaStreamCreateWithFlags(&F.up, cudaStreamNonBlocking));
+        VM_CUDA(cudaStreamCreateWithFlags(&F.down, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            VM_CUDA(cudaEventCreateWithFlags(&F.uploaded[k], cudaEventDisableTiming)); VM_CUDA(cudaEventCreateWithFlags(&F.rendered[k], cudaEventDisableTiming));
+            VM_CUDA(cudaEventCreateWithFlags(&F.downloaded[k], cudaEventDisableTiming));
+        }
+    }
+    if (F.e0[0].bytes < eb || F.o[0].bytes < ob || (qpath && F.q[0].bytes < vb)) VM_CUDA(cudaDeviceSynchronize());
+    for (int k = 0; k < 2; k++) { VM_CUDA(F.e0[k].ensure(eb)); VM_CUDA(F.e1[k].ensure(eb)); VM_CUDA(F.o[k].ensure(ob)); if (qpath) VM_CUDA(F.q[k].ensure(vb)); }
+    // the staging buffers may still be in use by work the caller's stream has not reached yet
+    VM_CUDA(cudaEventRecord(F.rendered[0], s)); VM_CUDA(cudaStreamWaitEvent(F.up, F.rendered[0], 0)); VM_CUDA(cudaStreamWaitEvent(F.down, F.rendered[0], 0));
+    const float2 *vec = m->extract_buf.as<float2>();
+    for (int k = 0; k < nframes; k++) {
+        const int b = k & 1, z = frame0 + k;
+        if (k >= 2) VM_CUDA(cudaStreamWaitEvent(F.up, F.rendered[b], 0));                     // frame k-2 no longer reads these inputs
+        VM_CUDA(cudaMemcpyAsync(F.e0[b].p, ext0 + (size_t)k * eb, eb, cudaMemcpyHostToDevice, F.up));
+        VM_CUDA(cudaMemcpyAsync(F.e1[b].p, ext1 + (size_t)k * eb, eb, cudaMemcpyHostToDevice, F.up));
+        if (qpath) VM_CUDA(cudaMemcpyAsync(F.q[b].p, qpath + (size_t)k * w * h * 2, vb, cudaMemcpyHostToDevice, F.up));
+        VM_CUDA(cudaEventRecord(F.uploaded[b], F.up));
+        VM_CUDA(cudaStreamWaitEvent(s, F.uploaded[b], 0));
+        if (k >= 2) VM_CUDA(cudaStreamWaitEvent(s, F.downloaded[b], 0));                      // output buffer b has left the device
+        rc = vm_render_halfway_dev(F.o[b].as<uint8_t>(), rowstride, w, h, ex, color_fa[k], geo_fa[k], color_from, F.e0[b].as<uint8_t>(), F.e1[b].as<uint8_t>(),
+                                   reinterpret_cast<const float *>(vec + (size_t)z * w * h), qpath ? F.q[b].as<float>() : nullptr, stream);
+        if (rc) return rc;
+        VM_CUDA(cudaEventRecord(F.rendered[b], s));
+        VM_CUDA(cudaStreamWaitEvent(F.down, F.rendered[b], 0));
+        VM_CUDA(cudaMemcpy2DAsync(out + (size_t)k * fb, (size_t)w * 3, F.o[b].p, (size_t)rowstride * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, F.down));
+        VM_CUDA(cudaEventRecord(F.downloaded[b], F.down));
+    }
+    VM_CUDA(cudaStreamSynchronize(F.down));
     VM_CUDA(cudaStreamSynchronize(s));
     return VM_OK;
 }

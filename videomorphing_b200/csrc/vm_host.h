@@ -86,7 +86,7 @@ struct vm_morph {
     volatile int *run_flag = nullptr;     // caller's flag (host memory); registered as mapped memory when possible
     int *run_flag_dev = nullptr;          // device alias of run_flag (NULL: polled on the host between launches only)
     bool run_flag_registered = false;
-    int *progress_host = nullptr;         // cudaHostAllocMapped word written by the sweep kernel: (seq << 12) | iteration
+    int *progress_host = nullptr;         // cudaHostAllocMapped words written by the sweep kernel: [0] launch number, [1] iteration
     int *progress_dev = nullptr;
     std::vector<vm::Conn> cons;
     vm::DevBuf cons_dev;
@@ -94,23 +94,29 @@ struct vm_morph {
     vm::DevBuf ctrl2;                     // control block of the backward frame chain (runs concurrently with the forward chain)
     cudaStream_t chain_stream[2] = {nullptr, nullptr};
     cudaEvent_t chain_ev[3] = {nullptr, nullptr, nullptr};
-    vm::DevBuf log_dev;                   // iterations executed per sweep launch (one word per launch)
+    vm::DevBuf log_dev;                   // per sweep launch: iterations executed, attempted pixel updates (two words per launch)
     // launch table for progress reporting: seq -> (level, frame, w*h, max_iter)
     struct Seq { int level, frame; double wh; float max_iter; };
-    std::vector<Seq> seqs;
+    std::vector<Seq> seqs;                // launches enqueued since the last collect_log (reset by every collecting call)
+    double done_iter = 0;                 // morph.cu:1391 progress of the launches already collected
     // morph.h:17-20 progress fields
     int total_l = 0;
     double total_iter = 0;
     float max_iter_now = 0;
     double executed_pixel_iters = 0;
     std::vector<int32_t> iters_log;
+    std::vector<uint32_t> upd_log;        // attempted pixel updates of each logged sweep launch
     std::vector<float> ms_log;            // device ms of each logged sweep launch (same order as iters_log)
     bool cancelled = false;
     // device time of the sweep launches (CUDA events on the launching stream around every k_sweep launch)
     std::vector<cudaEvent_t> ev;          // 2 per launch: ev[2*seq], ev[2*seq+1]
+    bool extract_valid = false;           // extract_buf holds the field of the last vm_morph_extract
     vm::DevBuf extract_buf;               // level-0 sized vector field staged for vm_morph_get_vectors (kept between calls)
     double sweep_ms = 0;                  // accumulated by collect_log
     uint64_t sweep_launches = 0;
+    double attempted_updates = 0;         // active pixels x colour rounds the sweep launches optimised (FP32 roofline unit)
+    double sweep_busy_ms = 0;             // length of the union of the sweep launches' [start, end] intervals (concurrent chains overlap)
+    cudaEvent_t ev_base = nullptr;        // time origin of the intervals of one collecting call
 };
 
 namespace vm {
@@ -123,6 +129,7 @@ void free_resample_cache(vm_pyramid *p);
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
                          unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, int sm_budget, cudaStream_t stream);
 size_t sweep_ctrl_words(int max_iter_ceil, int ntiles);
+void sweep_reload_hooks();      // re-reads the VMORPH_* experiment hooks from the environment (called by vm_morph_create)
 int sweep_num_tiles(int w, int h);
 
 cudaError_t launch_initialize_level(const LevelView &L, const StencilTables *st, float ssim_clamp, cudaStream_t s);

@@ -13,6 +13,7 @@
 // binary tree over the 128 group sums, f64), which makes the solve bit-reproducible and equal to the CPU oracle.
 #include "vm_device.cuh"
 #include "vm_host.h"
+#include <atomic>
 #include <cstring>
 #include <cstdlib>
 
@@ -451,11 +452,13 @@ cudaError_t launch_qpath(const float2 *vec, float2 *out, int cols, int rows, int
     const char *eq = getenv("VMORPH_QPATH");
     const bool resident = N <= (size_t)QP_MAXK * QP_LANES && !(eq && !strcmp(eq, "global"));
     if (resident) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        // per device: the attribute belongs to the current device's context
+        static std::atomic<bool> attr_set[64];
+        int dev = 0; cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
             e = cudaFuncSetAttribute(k_qpath_cg_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QpResSmem));
             if (e != cudaSuccess) return e;
-            attr_set = true;
+            if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
         }
         void *args[] = {&X0, &X1, &R0, &R1, &P00, &P01, &P10, &P11, &cols, &rows, &max_iter, &tol, &part, &bar, &iters_dev};
         e = cudaLaunchCooperativeKernel((const void *)k_qpath_cg_res, dim3(QP_BLOCKS), dim3(QP_THREADS), args, sizeof(QpResSmem), s);

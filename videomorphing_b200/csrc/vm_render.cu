@@ -7,6 +7,7 @@
 // vector field stay in L1/L2 (8 B/px field); HBM traffic is the compulsory 8 + 8 + 2x4 + 3 B per output pixel.
 #include "vm_device.cuh"
 #include "vm_host.h"
+#include <atomic>
 #include <cuda.h>
 #include <cstring>
 #include <cstdlib>
@@ -298,11 +299,13 @@ cudaError_t launch_render(uint8_t *out, int rowstride, int w, int h, int ex, flo
         if (!qpath) mq = mv;
         dim3 b(RT_W, RT_H), g((w + RT_W - 1) / RT_W, (h + RT_H - 1) / RT_H);
         size_t smem = (size_t)RT_WW * RT_WH * 8 * (qpath ? 2 : 1) + (size_t)RT_H * RT_W * 3;
-        static bool attr_set = false;
-        if (!attr_set) {
+        // per device: the attribute belongs to the current device's context
+        static std::atomic<bool> attr_set[64];
+        int dev = 0; cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
             cudaFuncSetAttribute(k_render_halfway_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_WW * RT_WH * 16 + RT_H * RT_W * 3);
             cudaFuncSetAttribute(k_render_halfway_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_WW * RT_WH * 8 + RT_H * RT_W * 3);
-            attr_set = true;
+            if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
         }
         if (qpath)
             k_render_halfway_tma<true><<<g, b, smem, s>>>(out, rowstride, w, h, ex, color_fa, geo_fa, color_from, reinterpret_cast<const uchar4 *>(ext0),

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 namespace cg = cooperative_groups;
 
 namespace vm {
@@ -323,9 +324,6 @@ __device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float ep
 // One tile of one offset step (one block of one launch of the reference, morph.cu:1281-1345), executed by a
 // cluster of R CTAs (R == 1: a single CTA).  Everything that decides control flow is computed redundantly and
 // deterministically by every CTA of the cluster, so the cluster barriers are always reached by all of them.
-// One tile of one offset step (one block of one launch of the reference, morph.cu:1281-1345), executed by a
-// cluster of R CTAs (R == 1: a single CTA).  Everything that decides control flow is computed redundantly and
-// deterministically by every CTA of the cluster, so the cluster barriers are always reached by all of them.
 //
 // Improving mask: the words around the tile are replicated in shared memory for the duration of the step.  Only bits
 // of pixels inside the tile extent are ever looked at (5-pixel tile spacing: the 5x5 window of an own pixel reaches
@@ -334,7 +332,7 @@ __device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float ep
 // the mask as it was before the sub-phase; set / clear (morph.cu:1320-1332) happen at commit, like the reference.
 template <int NW, bool LAT>
 __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, const StencilTables *__restrict__ st,
-                          int page, bool flag, int ox, int oy, int R, int rank, unsigned int &phase) {
+                          int page, bool flag, int ox, int oy, int R, int rank, unsigned int &phase, unsigned int *attempted) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NT = NW * 32;
     const size_t poff = (size_t)page * L.ps;
@@ -446,12 +444,14 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
 #pragma unroll
             for (int k = 0; k < NPIX / 32; k++) { qn += S.warp_cnt[fb][k]; stat_any |= S.stat_any[fb][k]; }
             TR(2);
+            // attempted pixel updates of this launch (one per active pixel and colour): the unit of bench.py's FP32 roofline
+            if (tid == 0 && rank == 0 && qn) atomicAdd(attempted, (unsigned)qn);
 #ifdef VM_TRACE
             if (threadIdx.x == 0 && rank == 0) { atomicAdd(&g_trace[15], (unsigned long long)qn); atomicAdd(&g_trace[31], 1ull); }   // active pixels / sub-phases
 #endif
             // speculative line search only while the SM has issue slots to spare (at most ~1.5 busy warps per scheduler);
             // qn, R are the same in every CTA of the cluster, so the choice is uniform (and does not change results)
-            const bool spec = LAT && qn <= 6 * R;
+            const bool spec = LAT && qn * 16 <= 6 * R * NW;
             // ---- compute: one warp per active pixel, all from the pre-sub-phase state; the owning warp commits the
             //      pixel's own cells at once (nobody else reads them in this sub-phase) and broadcasts the deltas
             //      (queue entry q goes to CTA q % R, warp q / R: the active pixels spread over all SMs of the cluster)
@@ -660,6 +660,7 @@ __device__ __forceinline__ bool tile_active_warp(const LevelView &L, const unsig
 }
 
 // ctrl layout (unsigned ints): [0] barrier counter, [1] iterations executed (out), [2] cancelled (out),
+// [3] attempted pixel updates (out),
 // [4 + par] number of active tiles, [6 + par] next list entry to hand out (par = parity of the non-empty step count),
 // [8 + it] per-iteration flags: bit0 = improving, bit1 = cancel requested; then (dynamic mode) two tile lists.
 //
@@ -669,7 +670,7 @@ __device__ __forceinline__ bool tile_active_warp(const LevelView &L, const unsig
 // SM idles behind a converged tile while another one has several active tiles queued.  Tiles of a step are independent,
 // the order in which they are processed does not change the result.
 template <int NW, bool LAT>
-__global__ void __launch_bounds__(NW * 32, (LAT ? 1 : (NW <= 8 ? 3 : 2)))
+__global__ void __launch_bounds__(NW * 32, (LAT ? (NW <= 8 ? 2 : 1) : (NW <= 8 ? 3 : 2)))
 k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, int flag, float max_iter,
         unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int dyn, int list_off) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -704,7 +705,7 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
                     int by = t / gx, bx = t - by * gx;
                     int ox = bx * (OPT_BW * 2 + SPACING) + offx - 2, oy = by * (OPT_BH * 2 + SPACING) + offy - 2;
                     if (ox + 2 >= L.w || oy + 2 >= L.h) continue;
-                    tile_step<NW, LAT>(S, L, P, st, page, flag != 0, ox, oy, R, rank, phase);
+                    tile_step<NW, LAT>(S, L, P, st, page, flag != 0, ox, oy, R, rank, phase, &ctrl[3]);
                 }
             } else if (!empty) {
                 const unsigned par = nstep & 1u;
@@ -739,7 +740,7 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
                     int t = (int)__ldcg(list + k);
                     int by = t / gx, bx = t - by * gx;
                     int ox = bx * (OPT_BW * 2 + SPACING) + offx - 2, oy = by * (OPT_BH * 2 + SPACING) + offy - 2;
-                    tile_step<NW, LAT>(S, L, P, st, page, flag != 0, ox, oy, R, rank, phase);
+                    tile_step<NW, LAT>(S, L, P, st, page, flag != 0, ox, oy, R, rank, phase, &ctrl[3]);
                 }
                 nstep++;
             }
@@ -756,7 +757,7 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
         }
         unsigned f = __ldcg(&ctrl[8 + iter]);
         iter++;
-        if (blockIdx.x == 0 && tid == 0 && progress) *progress = (seq << 12) | iter;
+        if (blockIdx.x == 0 && tid == 0 && progress) { progress[1] = iter; progress[0] = seq; }
         go = ((float)iter < max_iter) && (f & 1u) && !(f & 2u);          // morph.cu:1390
         if (!go && blockIdx.x == 0 && tid == 0) { ctrl[1] = (unsigned)iter; ctrl[2] = (f & 2u) ? 1u : 0u; }
     } while (go);
@@ -764,18 +765,46 @@ k_sweep(LevelView L, KParams P, const StencilTables *__restrict__ st, int page, 
 }
 
 // ------------------------------------------------------------------ host launcher
+// Per-device launch configuration (cudaFuncSetAttribute and the occupancy answers belong to the current device's
+// context: a process that drives several GPUs needs one copy per device), created under a mutex on first use.
+constexpr int MAX_DEVICES = 64;
+constexpr int NVARIANTS = 4;
 struct SweepCfg { bool init = false; int per_sm = 0; int max_clusters[17] = {0}; bool queried[17] = {false}; };   // index = cluster size R
-static SweepCfg g_cfg[3];
+static SweepCfg g_cfg[MAX_DEVICES][NVARIANTS];
+static std::mutex g_cfg_mu;
+
+// Test / experiment hooks, read from the environment when a vm_morph is created (sweep_reload_hooks), not on every launch:
+// VMORPH_CLUSTER=1..16 caps the cluster size, VMORPH_DYNAMIC=0|1 forces the tile schedule, VMORPH_R_DYN=n forces clusters
+// of n CTAs pulling from the tile list, VMORPH_VARIANT=lat|lat8|thr16|thr8 selects the kernel, VMORPH_LOG_LAUNCH=1 prints
+// every launch's decision.
+struct SweepHooks { int want_r = 16, r_dyn = 0, dynamic = -1, variant = -1, log = 0; };
+static SweepHooks g_hooks;
+void sweep_reload_hooks() {
+    std::lock_guard<std::mutex> lock(g_cfg_mu);
+    SweepHooks h;
+    const char *e;
+    if ((e = getenv("VMORPH_CLUSTER")) && atoi(e) > 0) h.want_r = atoi(e) > 16 ? 16 : atoi(e);
+    if ((e = getenv("VMORPH_R_DYN")) && atoi(e) > 1 && atoi(e) <= 16) h.r_dyn = atoi(e);
+    if ((e = getenv("VMORPH_DYNAMIC"))) h.dynamic = atoi(e) != 0;
+    if ((e = getenv("VMORPH_VARIANT"))) h.variant = !strcmp(e, "lat") ? 0 : (!strcmp(e, "thr16") ? 1 : (!strcmp(e, "thr8") ? 2 : (!strcmp(e, "lat8") ? 3 : -1)));
+    if ((e = getenv("VMORPH_LOG_LAUNCH"))) h.log = atoi(e);
+    g_hooks = h;
+}
 
 template <int NW, bool LAT>
 static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag,
                                   float max_iter, unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq,
-                                  int ntiles, int sm_count, int sm_budget, cudaStream_t stream, int slot, int want_r) {
+                                  int ntiles, int sm_count, int sm_budget, cudaStream_t stream, int slot, const SweepHooks &hk) {
     size_t smem = sizeof(SweepSmem);
     auto kern = k_sweep<NW, LAT>;
-    SweepCfg &cfg = g_cfg[slot];
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    if (device < 0 || device >= MAX_DEVICES) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(g_cfg_mu);
+    SweepCfg &cfg = g_cfg[device][slot];
     if (!cfg.init) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.per_sm, kern, NW * 32, smem);
         if (e != cudaSuccess) return e;
@@ -797,8 +826,8 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
             if (cudaOccupancyMaxActiveClusters(&nc, kern, &qc) != cudaSuccess) { cudaGetLastError(); nc = 0; }
             cfg.max_clusters[R] = nc; cfg.queried[R] = true;
         }
-        // a launch that was given part of the GPU (two frame chains side by side) takes the same part of the clusters that
-        // can be co-resident: GPC boundaries make that fewer than SMs / R, and two launches that together ask for more
+        // a launch that was given part of the GPU (several launches side by side) takes the same part of the clusters that
+        // can be co-resident: GPC boundaries make that fewer than SMs / R, and launches that together ask for more
         // than the GPU can hold run one after the other
         int by_budget = cfg.per_sm * sm_budget / R;
         int share = (int)((long long)cfg.max_clusters[R] * sm_budget / (sm_count > 0 ? sm_count : 1));
@@ -812,27 +841,27 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
     //    active tile's chain of pixels; a cluster finishes such a tile R times faster, and while every tile is still active
     //    the clusters simply take several tiles each.  R = 2 + 2 * budget / ntiles, clamped to [2, 6]: 52 tiles -> 6,
     //    91 -> 5, 200 -> 3, >= 296 -> 2 (best or within 3 % of the best measured size at every level).
+    const int want_r = hk.want_r;
+    const int slots = sm_budget * cfg.per_sm;            // CTA slots of this launch's share of the GPU
     int R, dyn = 0;
     const int nt = ntiles > 0 ? ntiles : 1;
-    if (6 * nt <= sm_budget) {
-        R = sm_budget / nt;
+    if (6 * nt <= slots) {
+        R = slots / nt;
         if (R > want_r) R = want_r;
         if (R > 16) R = 16;
         if (R < 1) R = 1;
         while (R > 1 && cap(R) < ntiles) R--;
     } else {
-        R = 2 + 2 * sm_budget / nt;
+        R = 2 + 2 * slots / nt;
         if (R > 6) R = 6;
         if (R > want_r) R = want_r;
         if (R < 1) R = 1;
         while (R > 1 && cap(R) < 1) R--;
         dyn = ntiles > cap(R) ? 1 : 0;
-        if (!dyn) { R = sm_budget / nt; if (R > want_r) R = want_r; if (R < 1) R = 1; while (R > 1 && cap(R) < ntiles) R--; }
+        if (!dyn) { R = slots / nt; if (R > want_r) R = want_r; if (R < 1) R = 1; while (R > 1 && cap(R) < ntiles) R--; }
     }
-    const char *er = getenv("VMORPH_R_DYN");          // experiment hook: clusters of this size pulling from the tile list
-    if (er && atoi(er) > 1 && atoi(er) <= 16 && cap(atoi(er)) >= 1 && ntiles > cap(atoi(er))) { R = atoi(er); dyn = 1; }
-    const char *ed = getenv("VMORPH_DYNAMIC");
-    if (ed) { int f = atoi(ed) != 0; if (f != dyn) { dyn = f; if (!dyn) { while (R > 1 && cap(R) < ntiles) R--; } } }
+    if (hk.r_dyn > 1 && cap(hk.r_dyn) >= 1 && ntiles > cap(hk.r_dyn)) { R = hk.r_dyn; dyn = 1; }
+    if (hk.dynamic >= 0 && hk.dynamic != dyn) { dyn = hk.dynamic; if (!dyn) { while (R > 1 && cap(R) < ntiles) R--; } }
     int nclusters = ntiles < cap(R) ? ntiles : cap(R);
     if (nclusters < 1) nclusters = 1;
     if (!dyn && nclusters < ntiles && R > 1) { R = 1; nclusters = ntiles < cap(1) ? ntiles : cap(1); }   // static: tiles loop over clusters
@@ -845,15 +874,18 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
     at[1].id = cudaLaunchAttributeClusterDimension; at[1].val.clusterDim.x = R; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = (R > 1) ? 2 : 1;
     count_launch();
-    if (getenv("VMORPH_LOG_LAUNCH"))
-        fprintf(stderr, "[vmorph] sweep %dx%d page %d: %d tiles, budget %d SMs -> %d clusters of %d, %s tiles\n", L.w, L.h, page, ntiles, sm_budget, nclusters, R, dyn ? "pulled" : "static");
-    cudaError_t e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq, dyn, list_off);
+    if (hk.log)
+        fprintf(stderr, "[vmorph] sweep %dx%d page %d: %d tiles, budget %d SMs x %d -> %d clusters of %d, %s tiles\n", L.w, L.h, page, ntiles, sm_budget, cfg.per_sm, nclusters, R, dyn ? "pulled" : "static");
+    // The kernel spins in a hand-written grid barrier, which is only safe when every CTA is co-resident: the launch stays
+    // cooperative.  Should the driver reject cooperative + cluster, fall back to single-CTA "clusters" (still cooperative)
+    // rather than to a plain cluster grid that could hang next to another resident kernel.
+    e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq, dyn, list_off);
     if (e != cudaSuccess && R > 1) {
-        // cooperative + cluster attribute combination rejected: the grid is sized to be co-resident
-        // (<= cudaOccupancyMaxActiveClusters), launch it as a plain cluster grid.
         cudaGetLastError();
-        lc.attrs = at + 1; lc.numAttrs = 1;
-        e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq, dyn, list_off);
+        int n1 = ntiles < cap(1) ? ntiles : cap(1);
+        if (n1 < 1) n1 = 1;
+        lc.gridDim = dim3(n1); lc.numAttrs = 1;
+        e = cudaLaunchKernelEx(&lc, kern, Lc, Pc, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles > n1 ? 1 : 0, list_off);
     }
     return e;
 }
@@ -862,24 +894,22 @@ static cudaError_t launch_sweep_t(const LevelView &L, const KParams &P, const St
 //   lat   16 warps, 1 CTA / SM (up to 128 registers): batched + speculative energy evaluations; a cluster of up to 16
 //         CTAs per tile.  For levels with at most one tile per SM, where the dependent chain of one pixel's line
 //         search, not throughput, bounds the step.
-//   thr16 16 warps, 2 CTAs / SM;  thr8  8 warps, 3 CTAs / SM: sequential line search, for levels with many tiles.
-// Test hooks (read on every launch): VMORPH_CLUSTER=1..16 caps the cluster size, VMORPH_DYNAMIC=0|1 forces the tile schedule, VMORPH_VARIANT=lat|thr16|thr8.
+//   lat8  the same code with 8 warps per CTA, 2 CTAs / SM: twice as many co-resident clusters of half the width, for
+//         launches that share the GPU with other launches (level wavefront of a video).
+//   thr16 16 warps, 2 CTAs / SM;  thr8  8 warps, 3 CTAs / SM: sequential line search (test hooks).
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
                          unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, int sm_budget, cudaStream_t stream) {
     const int gx = (L.w + OPT_BW * 2 + SPACING - 1) / (OPT_BW * 2 + SPACING);
     const int gy = (L.h + OPT_BH * 2 + SPACING - 1) / (OPT_BH * 2 + SPACING);
     const int ntiles = gx * gy;
-    const char *ec = getenv("VMORPH_CLUSTER"), *ev = getenv("VMORPH_VARIANT");
-    int want_r = (ec && atoi(ec) > 0) ? atoi(ec) : 16;
-    if (want_r > 16) want_r = 16;
+    SweepHooks hk;
+    { std::lock_guard<std::mutex> lock(g_cfg_mu); hk = g_hooks; }
     if (sm_budget <= 0 || sm_budget > sm_count) sm_budget = sm_count;
-    // levels with more tiles than SMs: the latency variant with dynamic tile hand-out (VMORPH_VARIANT=thr16|thr8 keep
-    // the static many-CTAs-per-SM schedule for comparison)
-    int variant = 0;
-    if (ev) variant = !strcmp(ev, "lat") ? 0 : (!strcmp(ev, "thr16") ? 1 : (!strcmp(ev, "thr8") ? 2 : variant));
-    if (variant == 0) return launch_sweep_t<16, true>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 0, want_r);
-    if (variant == 1) return launch_sweep_t<16, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 1, want_r);
-    return launch_sweep_t<8, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 2, want_r);
+    int variant = hk.variant >= 0 ? hk.variant : 0;
+    if (variant == 0) return launch_sweep_t<16, true>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 0, hk);
+    if (variant == 1) return launch_sweep_t<16, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 1, hk);
+    if (variant == 3) return launch_sweep_t<8, true>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 3, hk);
+    return launch_sweep_t<8, false>(L, P, st, page, flag, max_iter, ctrl, run_flag, progress, seq, ntiles, sm_count, sm_budget, stream, 2, hk);
 }
 
 size_t sweep_ctrl_words(int max_iter_ceil, int ntiles) { return 8 + (size_t)max_iter_ceil + 8 + 2 * (size_t)ntiles; }

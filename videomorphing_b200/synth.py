@@ -85,6 +85,37 @@ def smoothstep(t):
     return np.float32(t * t * (np.float32(3) - np.float32(2) * t))
 
 
+def video_offset_fn(seed_warp, vel=1.5, wobble=1.0):
+    """Camera offset (x, y) of frame t - d/2 of video_pair's synthetic motion."""
+    rng = np.random.Generator(np.random.PCG64(seed_warp + 11))
+    ph = rng.uniform(0, 2 * np.pi)
+
+    def offset(t):
+        return np.float32(vel * t + wobble * np.sin(0.2 * t + ph)), np.float32(wobble * np.cos(0.15 * t + ph))
+    return offset
+
+
+def video_tracks(w, h, d, seed, seed_warp, field, ntracks=4, margin=96, vel=1.5, wobble=1.0):
+    """`ntracks` UI point tracks propagated by the analytic motion of video_pair, all frames connected.
+    Track k follows one scene point: left point in video 0 at frame t, right point = left + warp (rounded), weight 1.
+    Returns the resolved connections (lp, lw, rp, rw): (ntracks*d, 4) int32 [x, y, frame, keyflag] and weights."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    offset = video_offset_fn(seed_warp, vel, wobble)
+    bx = rng.integers(margin, w - margin, ntracks)
+    by = rng.integers(margin, h - margin, ntracks)
+    lp, rp = [], []
+    for k in range(ntracks):
+        fx, fy = field[by[k], bx[k]]
+        for t in range(d):
+            ox, oy = offset(t - d / 2)
+            ox0, oy0 = offset(0 - d / 2 + d // 2)                      # the point is picked in the middle frame
+            x = int(np.clip(np.rint(bx[k] + (ox - ox0)), 0, w - 1)); y = int(np.clip(np.rint(by[k] + (oy - oy0)), 0, h - 1))
+            lp.append((x, y, t, 1 if t == d // 2 else 0))
+            rp.append((int(np.clip(np.rint(x + fx), 0, w - 1)), int(np.clip(np.rint(y + fy), 0, h - 1)), t, 1 if t == d // 2 else 0))
+    n = len(lp)
+    return np.asarray(lp, np.int32), np.ones(n, np.float32), np.asarray(rp, np.int32), np.ones(n, np.float32)
+
+
 def video_pair(w, h, d, seed_img, seed_warp, amp, vel=1.5, wobble=1.0):
     """Two videos (d,h,w,3) u8 plus analytic forward/backward flows (d,h,w,2) float32 for each.
 
@@ -95,11 +126,7 @@ def video_pair(w, h, d, seed_img, seed_warp, amp, vel=1.5, wobble=1.0):
     base0 = _noise_image(w + 2 * 64, h + 2 * 64, seed_img)
     field = smooth_warp(w + 128, h + 128, seed_warp, amp)
     base1 = warp_image(base0, field)
-    rng = np.random.Generator(np.random.PCG64(seed_warp + 11))
-    ph = rng.uniform(0, 2 * np.pi)
-
-    def offset(t):
-        return np.float32(vel * t + wobble * np.sin(0.2 * t + ph)), np.float32(wobble * np.cos(0.15 * t + ph))
+    offset = video_offset_fn(seed_warp, vel, wobble)
 
     v0 = np.zeros((d, h, w, 3), np.uint8)
     v1 = np.zeros((d, h, w, 3), np.uint8)
