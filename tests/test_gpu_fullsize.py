@@ -209,3 +209,62 @@ def test_four_gpu_level_pipeline_is_bit_identical_to_one_gpu(vm):
             assert one[(int(l), int(f))] == int(i)
             allr[(int(l), int(f))] = int(i)
     assert allr == one                                     # together the four ranks ran every (level, frame) of the one-GPU log
+
+
+def _one_gpu_pipeline_worker(rank, port, q, world):
+    """Rank of the exact multi-GPU schedule with EVERY rank on cuda:0 (gloo carries the hand-offs through pinned host
+    memory): the real kernels and the real run_pipeline / chain-split code on a one-GPU lease."""
+    import os
+    os.environ.update(RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VMORPH_DIST_TIMEOUT_S="240")
+    import torch
+    import torch.distributed as dist
+    import videomorphing_b200 as vm
+    from videomorphing_b200 import dist as vd, synth
+    torch.cuda.set_device(0)
+    vd.init("gloo")
+    v0, v1, flows, _ = synth.video_pair(96, 64, 9, 41, 42, 3.0)
+    prm = vm.Parameters(max_iter=24, start_res=4)
+    pyr = vm.Pyramid(0); pyr.build(v0, v1, flows, start_res=4)
+    m = vm.Morph(prm, pyr)
+    vd.optimize_video(m, pyr, prm, device=0)
+    vec = m.get_vectors() if rank < 2 else None            # the level-1 owners hold the result
+    dist.barrier()
+    q.put((rank, vec, m.iters_log().copy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_exact_multi_rank_schedules_on_one_gpu_are_bit_identical(vm, world):
+    """dist.optimize_video at world 2 / 3 (one frame chain per rank, v halves swapped per level, extra ranks by broadcast),
+    4 (2-stage level pipeline) and 8 (4-stage level pipeline), all ranks sharing ONE GPU: bit-identical to vm_morph_run,
+    and the union of the ranks' iteration logs is the one-GPU log.  (The same schedules on 2 / 4 real GPUs over NCCL:
+    test_two_gpu_chain_split_*, test_four_gpu_level_pipeline_*.)"""
+    import socket
+    import torch.multiprocessing as mp
+    from videomorphing_b200 import dist as vd, synth
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_one_gpu_pipeline_worker, args=(r, port, q, world)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict((r, (v, it)) for r, v, it in (q.get(timeout=600) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    v0, v1, flows, _ = synth.video_pair(96, 64, 9, 41, 42, 3.0)
+    prm = vm.Parameters(max_iter=24, start_res=4)
+    pyr = vm.Pyramid(0); n = pyr.build(v0, v1, flows, start_res=4)
+    if world == 8:
+        assert vd.pipeline_plan([pyr.info(l)["d"] for l in range(n)], world)["nstages"] == 4
+    m = vm.Morph(prm, pyr); m.run()
+    ref = m.get_vectors()
+    np.testing.assert_array_equal(res[0][0], ref)          # the two level-1 owners end with the whole field
+    np.testing.assert_array_equal(res[1][0], ref)
+    one = {(int(l), int(f)): int(i) for l, f, i in m.iters_log()}
+    allr = {}
+    for r in range(world):
+        for l, f, i in res[r][1]:
+            assert one[(int(l), int(f))] == int(i)
+            allr[(int(l), int(f))] = int(i)
+    assert allr == one

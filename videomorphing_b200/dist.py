@@ -122,31 +122,6 @@ def quadratic_path_sharded(vectors, max_iter=10000, tol=1e-12, device=0, gather=
 
 
 # ------------------------------------------------------------------------------------------ optimizer, exact mode
-def _exchange_pages(pyramid, level, my_pages, peer_pages, peer, device, stream=None):
-    """Send this rank's `v` pages [a, b) of a level to `peer` and receive the peer's pages: NCCL send / recv over NVLink.
-    The pages are contiguous in the level array (pagestride float2 each), staged through torch tensors."""
-    from . import _lib
-    L = _lib.load()
-    info = pyramid.info(level)
-    page_bytes = info["pagestride"] * 8
-    base, _ = pyramid.dev_ptr(level, "v")
-    ops, recv_t = [], None
-    (a, b), (c, e) = my_pages, peer_pages
-    if b > a:
-        send_t = torch.empty((b - a) * page_bytes, dtype=torch.uint8, device=f"cuda:{device}")
-        _lib.check(L.vm_dev_copy(device, send_t.data_ptr(), base + a * page_bytes, (b - a) * page_bytes, stream))
-        ops.append(dist.P2POp(dist.isend, send_t, peer))
-    if e > c:
-        recv_t = torch.empty((e - c) * page_bytes, dtype=torch.uint8, device=f"cuda:{device}")
-        ops.append(dist.P2POp(dist.irecv, recv_t, peer))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    if recv_t is not None:
-        _lib.check(L.vm_dev_copy(device, base + c * page_bytes, recv_t.data_ptr(), (e - c) * page_bytes, stream))
-        torch.cuda.current_stream().synchronize()
-
-
 def _optimize_video_two_chains(morph, pyramid, params, device=0):
     """Morph::calculate_halfway_parametrization (morph.cu:150-168) for a video with the two frame chains of every level on
     two GPUs (exact mode: the same arithmetic as one GPU, bit-identical result on ranks 0 and 1).
@@ -160,8 +135,9 @@ def _optimize_video_two_chains(morph, pyramid, params, device=0):
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     n = pyramid.num_levels
+    eng = MorphEngine(morph, pyramid, device)
     morph.cpu_optimize_level()
-    max_iter = float(params.max_iter)
+    max_iter = np.float32(params.max_iter)
     for l in range(n - 2, 0, -1):
         morph.upsample(l)
         morph.initialize_level(l)
@@ -169,28 +145,20 @@ def _optimize_video_two_chains(morph, pyramid, params, device=0):
         plan = chain_plan(d, world)
         mid = plan["mid"]
         if world == 1:
-            morph.optimize_chains(l, max_iter, 3)
+            morph.optimize_chains(l, float(max_iter), 3)
         else:
             chains = (1 if rank == plan["forward"][0] else 0) | (2 if rank == plan["backward"][0] else 0)
+            fwd, bwd = (mid + 1, d), (0, mid)
             if rank <= 1:
-                morph.optimize_chains(l, max_iter, chains)
-                fwd, bwd = (mid + 1, d), (0, mid)
-                if rank == 0:
-                    _exchange_pages(pyramid, l, fwd, bwd, 1, device)
-                else:
-                    _exchange_pages(pyramid, l, bwd, fwd, 0, device)
+                morph.optimize_chains(l, float(max_iter), chains)
+                _swap_pages(eng, l, fwd if rank == 0 else bwd, bwd if rank == 0 else fwd, rank ^ 1)
             if world > 2:
-                from . import _lib
-                base, nbytes = pyramid.dev_ptr(l, "v")
-                t = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{device}")
-                if rank == 0:
-                    _lib.check(_lib.load().vm_dev_copy(device, t.data_ptr(), base, nbytes, None))
+                t = eng.get_pages(l, 0, d) if rank == 0 else eng.new_pages(l, d)
                 dist.broadcast(t, 0)
                 if rank > 1:
-                    _lib.check(_lib.load().vm_dev_copy(device, base, t.data_ptr(), nbytes, None))
-                    _lib.check(_lib.load().vm_level_mark_v_valid(pyramid.h, l))
-                torch.cuda.current_stream().synchronize()
-        max_iter /= params.max_iter_drop_factor
+                    eng.set_pages(l, 0, t)
+                eng.sync()
+        max_iter = np.float32(max_iter / np.float32(params.max_iter_drop_factor))     # float like the reference (morph.cu:163)
     return morph
 
 
@@ -255,23 +223,42 @@ class MorphEngine:
         base, _ = self.p.dev_ptr(l, "v")
         return base, self.p.info(l)["pagestride"] * 8
 
+    @property
+    def staging(self):
+        """Where hand-off buffers live: on this GPU for NCCL (send / recv over NVLink), in pinned host memory for gloo
+        (the CPU tests and the several-ranks-on-one-GPU test: gloo has no CUDA send / recv)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_backend() != "nccl":
+            return "cpu"
+        return f"cuda:{self.device}"
+
     def new_pages(self, l, n=1):
-        return torch.empty(n * self._page(l)[1], dtype=torch.uint8, device=f"cuda:{self.device}")
+        st = self.staging
+        return torch.empty(n * self._page(l)[1], dtype=torch.uint8, device=st, pin_memory=(st == "cpu" and torch.cuda.is_available()))
 
     def get_pages(self, l, a, b):
-        """Copy of the `v` pages [a, b) of level l (one contiguous byte tensor on this GPU)."""
+        """Copy of the `v` pages [a, b) of level l (one contiguous byte tensor on this GPU, or in host memory under gloo)."""
         base, pb = self._page(l)
         t = self.new_pages(l, b - a)
-        self._lib.check(self.L.vm_dev_copy(self.device, t.data_ptr(), base + a * pb, (b - a) * pb, None))
+        if t.is_cuda:
+            self._lib.check(self.L.vm_dev_copy(self.device, t.data_ptr(), base + a * pb, (b - a) * pb, None))
+        else:
+            self._lib.check(self.L.vm_dev_download(self.device, t.data_ptr(), base + a * pb, (b - a) * pb, None))
+            self._lib.check(self.L.vm_stream_sync(self.device, None))
         return t
 
     def set_pages(self, l, a, t):
         base, pb = self._page(l)
-        self._lib.check(self.L.vm_dev_copy(self.device, base + a * pb, t.data_ptr(), t.numel(), None))
+        if t.is_cuda:
+            self._lib.check(self.L.vm_dev_copy(self.device, base + a * pb, t.data_ptr(), t.numel(), None))
+        else:
+            self._lib.check(self.L.vm_dev_upload(self.device, base + a * pb, t.data_ptr(), t.numel(), None))
+            self._lib.check(self.L.vm_stream_sync(self.device, None))
         self._lib.check(self.L.vm_level_mark_v_valid(self.p.h, l))
 
     def sync(self):
-        torch.cuda.current_stream().synchronize()
+        self._lib.check(self.L.vm_stream_sync(self.device, None))
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()
 
 
 def _swap_pages(eng, l, mine, theirs, peer):
