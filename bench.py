@@ -8,7 +8,8 @@ Default workload = the configuration the metric is quoted on (BASELINE.json conf
 pair x 120 frames with analytic optical flows and 4 UI point tracks, voxel cap lifted.  A "step" is one pass of the hot path
 over that video: Morph::calculate_halfway_parametrization (coarse solve + upsample / initialise / optimise every level and
 frame, morph.cu:150-168).  ONE video is optimised by ALL N GPUs together in exact mode (videomorphing_b200.dist
-.optimize_video: the same arithmetic as one GPU, bit-identical result) => "scaling": "strong".
+.optimize_video: the direction x level wavefront split over the ranks, the same arithmetic as one GPU, bit-identical result
+on every rank) => "scaling": "strong".
 
   value      halfway-opt Mpixel-iters/s of the one video with the pyramid resident in HBM: sum over levels and frames of
              w*h*iterations executed (the reference's own _current_iter increments) / device time (CUDA events on the
@@ -374,14 +375,14 @@ def run_ours_video(args):
     m.set_constraints(*V["cons"])
     depths = [pyr.info(l)["d"] for l in range(pyr.num_levels)]
     dims = {l: (pyr.info(l)["w"], pyr.info(l)["h"]) for l in range(pyr.num_levels)}
-    plan = vd.pipeline_plan(depths, world)
     if world == 1:
-        sched = "one GPU: vm_morph_run"
-    elif plan["nstages"] > 1:
-        sched = "direction x level pipeline, %d stages: " % plan["nstages"] + "; ".join(
-            "rank %d %s levels %s" % (r, "fwd" if e["dir"] == 0 else "bwd", e["levels"]) for r, e in sorted(plan["ranks"].items()))
+        sched = "one GPU: vm_morph_run (direction x level wavefront, one multi-job launch per tick)"
     else:
-        sched = "one frame chain per rank (ranks 0 / 1), v halves swapped per level over NCCL"
+        mi = vd.level_max_iters(prm.max_iter, prm.max_iter_drop_factor, len(depths))
+        plan = vd.wavefront_plan(depths, dims, mi, world)
+        sched = f"wavefront of levels {plan['K']}..1 split by direction and level group: " + "; ".join(
+            "rank %d %s levels %s" % (r, "fwd" if g[0][0] == 0 else "bwd", g[0][1]) for r, g in sorted(plan["groups"].items())) + \
+            "; the levels above run redundantly on every rank"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
 
     def optimize():
@@ -474,15 +475,6 @@ def run_ours_video(args):
         optimize()
         torch.cuda.synchronize()
         t2 = time.perf_counter()
-        if world > 1:                                                           # the frame-parallel render needs the field on every rank
-            base, nbytes = pyr.dev_ptr(1, "v")
-            t = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                _lib.check(L.vm_dev_copy(local, t.data_ptr(), base, nbytes, sh))
-            dist.broadcast(t, 0)
-            if rank != 0:
-                _lib.check(L.vm_dev_copy(local, base, t.data_ptr(), nbytes, sh))
-                _lib.check(L.vm_level_mark_v_valid(pyr.h, 1))
         if rank == 0:
             _lib.check(L.vm_morph_get_vectors(m.h, vp(vec_pin), sh))           # update_result: D2H of the whole field
         else:

@@ -165,6 +165,20 @@ int vm_level_optimize_chains(vm_morph *m, int level, float max_iter, int chains,
  * requires depth(l) == depth(l+1) (no temporal in-fill, upsample.cu:286-339); VM_ERR_STATE otherwise. */
 int vm_level_upsample_frames(vm_morph *m, int dest_level, int frame0, int nframes, void *stream);
 int vm_level_initialize_frames(vm_morph *m, int level, int frame0, int nframes, void *stream);
+/* The direction x level wavefront of a video, in pieces (vm_morph_run drives them on one GPU; videomorphing_b200/dist.py
+ * drives the same schedule over several GPUs, one process each):
+ *   vm_morph_wavefront_prepare  runs everything above the wavefront -- the coarse dense solve and the temporally
+ *       subsampled levels, each whole (morph.cu:150-168 for those levels) -- then prolongs and initialises the head level
+ *       K (the coarsest level whose finer levels all have its depth) and gives the levels 2 .. K their own state arenas.
+ *       Returns K (>= 1) or a negative status.  Asynchronous on `stream`.
+ *   vm_level_enqueue_jobs       ONE persistent launch that optimises n <= 16 independent (level, frame) jobs in lock-step
+ *       (the do / while of morph.cu:1377-1391 for each); the jobs' levels must be initialised (and, with flag = 1,
+ *       vm_level_init_temp must have run for the frame).  Asynchronous: results are folded into the logs by
+ *   vm_morph_collect            which waits for `stream` and collects every launch enqueued since the last collecting call
+ *       (vm_morph_run, vm_level_optimize* collect by themselves). */
+int vm_morph_wavefront_prepare(vm_morph *m, void *stream);
+int vm_level_enqueue_jobs(vm_morph *m, int n, const int32_t *levels, const int32_t *frames, const int32_t *flags, const float *max_iters, void *stream);
+int vm_morph_collect(vm_morph *m, void *stream);
 /* Device pointer + size of a level array (fields / layouts of vm_level_get) for P2P / NCCL exchanges done by the caller;
  * vm_level_mark_v_valid tells the library that level's v has been written that way (PyramidLevel::v is public in the
  * reference, Pyramid.h:78). */
@@ -224,6 +238,11 @@ int vm_qpath_optimize_frames(int device, const float *vectors, float *qpaths, in
  * the device: mismatches3[0] = sqrt over every float in [2^-100, FLT_MAX] and +0, [1] = n_div pseudo-random quotients,
  * [2] = every float in [2^-60, 2^40] (both signs) divided by each window count 4..25.  All three must be 0. */
 int vm_selftest_exact_arith(int device, uint64_t n_div, uint64_t *mismatches3);
+
+/* Diagnostics of the multi-job sweep kernel (no reference counterpart): clock cycles one CTA spent per phase of the rounds
+ * since the last reset -- out8 = compute, barrier after compute, schedule advance + commit gather, filter, barrier after
+ * filter, then the number of rounds, queued pixels and accepted moves.  Feeds the phase tables under profiles/. */
+int vm_debug_sweep_phases(int device, uint64_t *out8, int reset);
 
 /* device memory helpers for callers that keep inputs resident (bench, multi-frame render) */
 int vm_dev_alloc(int device, size_t nbytes, void **out_dev);

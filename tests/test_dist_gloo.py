@@ -49,7 +49,6 @@ def test_frame_blocks_and_chain_plan():
             assert plan["mid"] == mid
             assert plan["forward"][1] == list(range(mid + 1, d)) and plan["backward"][1] == list(range(mid - 1, -1, -1))
             assert sorted(plan["forward"][1] + plan["backward"][1] + [mid]) == list(range(d))
-            assert plan["forward"][0] == 0 and plan["backward"][0] == (1 if world > 1 else 0)
 
 
 def test_world2_gloo_gather_and_reduce():
@@ -69,27 +68,25 @@ def test_world2_gloo_gather_and_reduce():
         assert units == 30.0 and secs == 1.5
 
 
-# ------------------------------------------------------------------------------------------ level pipeline (dist.run_pipeline)
+# ------------------------------------------------------------------------------------------ wavefront over ranks (dist.run_wavefront)
 class _FakeEngine:
     """Stand-in for dist.MorphEngine on CPU tensors: every operation is a cheap deterministic function of exactly the
     inputs the real one reads (the coarser level's frame, the chain neighbour's final frame), and asserts that those
     inputs are final when it runs -- so a wrong hand-off order or a missing exchange changes the result or trips."""
     P = 5
 
-    def __init__(self, depths):
+    def __init__(self, depths, max_iter0=1000.0, drop=1.5):
         import torch
+        from videomorphing_b200 import dist as vd
         self.depths = list(depths)
         n = len(depths)
+        self.dims = {l: (16 << (n - l), 9 << (n - l)) for l in range(n)}
+        self.max_iters = vd.level_max_iters(max_iter0, drop, n)
         self.v = [torch.full((depths[l], self.P), float("nan"), dtype=torch.float64) for l in range(n)]
         self.final = [set() for _ in range(n)]          # frames of level l whose v is final
         self.ready = [set() for _ in range(n)]          # frames prolonged + initialised
         self.temp = {}
-
-    def coarse_solve(self):
-        import torch
-        l = len(self.depths) - 1
-        self.v[l] = torch.arange(self.depths[l] * self.P, dtype=torch.float64).reshape(self.depths[l], self.P) * 0.25 + 1
-        self.final[l] = set(range(self.depths[l]))
+        self.launches = []
 
     def _up(self, l, i):
         dc, df = self.depths[l + 1], self.depths[l]
@@ -104,33 +101,55 @@ class _FakeEngine:
         self.v[l][i] = val
         self.ready[l].add(i)
 
-    def upsample(self, l):
-        for i in range(self.depths[l]):
-            dc, df = self.depths[l + 1], self.depths[l]
-            need = [i] if dc == df else [i // 2, min((i + 1) // 2, dc - 1)]
-            if all(f in self.final[l + 1] for f in need):
-                self._up(l, i)                           # frames of the other chain may be missing on this rank: never used
-    def initialize(self, l): pass
-    def upsample_frames(self, l, i): self._up(l, i)
-    def initialize_frames(self, l, i): assert i in self.ready[l]
-
-    def init_temp(self, l, i, direction):
+    def _init_temp(self, l, i, direction):
         assert (i + direction) in self.final[l], f"level {l} frame {i}: neighbour {i + direction} not final"
         self.temp[(l, i)] = self.v[l][i + direction] * 3 + 0.125
 
-    def optimize_frame(self, l, i, flag, max_iter):
-        assert i in self.ready[l] and i not in self.final[l]
+    def _optimize(self, l, i, flag, max_iter):
+        assert i in self.ready[l] and i not in self.final[l], (l, i)
         self.v[l][i] = self.v[l][i] * 1.5 + (self.temp.pop((l, i)) if flag else 0.0) + max_iter * 0.001 + l
         self.final[l].add(i)
-        return 1
 
-    def optimize_chains(self, l, max_iter, chains):
+    def _whole_level(self, l):
         d = self.depths[l]; mid = d // 2
-        self.optimize_frame(l, mid, False, max_iter)
-        for i in (range(mid + 1, d) if chains & 1 else []):
-            self.init_temp(l, i, -1); self.optimize_frame(l, i, True, max_iter)
-        for i in (range(mid - 1, -1, -1) if chains & 2 else []):
-            self.init_temp(l, i, 1); self.optimize_frame(l, i, True, max_iter)
+        for i in range(d):
+            self._up(l, i)
+        self._optimize(l, mid, False, self.max_iters[l])
+        for i in range(mid + 1, d):
+            self._init_temp(l, i, -1); self._optimize(l, i, True, self.max_iters[l])
+        for i in range(mid - 1, -1, -1):
+            self._init_temp(l, i, 1); self._optimize(l, i, True, self.max_iters[l])
+
+    def prepare(self):
+        import torch
+        from videomorphing_b200 import dist as vd
+        n = len(self.depths)
+        l = n - 1
+        self.v[l] = torch.arange(self.depths[l] * self.P, dtype=torch.float64).reshape(self.depths[l], self.P) * 0.25 + 1
+        self.final[l] = set(range(self.depths[l]))
+        K = vd.wavefront_head(self.depths)
+        for l in range(n - 2, K, -1):
+            self._whole_level(l)
+        for i in range(self.depths[K]):
+            self._up(K, i)
+        return K
+
+    def prep_frame(self, l, i, head, first, tdir):
+        if not head:
+            self._up(l, i)
+        assert i in self.ready[l]
+        if not first:
+            self._init_temp(l, i, tdir)
+
+    def enqueue_jobs(self, jobs):
+        assert len({(l, f) for l, f, _, _ in jobs}) == len(jobs) <= 16
+        for l, f, flag, mi in jobs:                      # the jobs of a launch are independent of each other
+            assert not flag or (l, f) in self.temp
+        for l, f, flag, mi in jobs:
+            self._optimize(l, f, flag, mi)
+        self.launches.append(len(jobs))
+
+    def collect(self): pass
 
     def new_pages(self, l, n=1):
         import torch
@@ -146,67 +165,74 @@ class _FakeEngine:
     def sync(self): pass
 
 
-def _pipeline_reference(depths, max_iter0, drop):
+def _sequential_reference(depths):
     e = _FakeEngine(depths)
-    n = len(depths)
-    e.coarse_solve()
-    mi = np.float32(max_iter0)
-    for l in range(n - 2, 0, -1):
-        e.upsample(l); e.initialize(l); e.optimize_chains(l, float(mi), 3)
-        mi = np.float32(mi / np.float32(drop))
+    K = e.prepare()
+    for l in range(K, 0, -1):
+        if l < K:
+            for i in range(depths[l]):
+                e._up(l, i)
+        d = depths[l]; mid = d // 2
+        e._optimize(l, mid, False, e.max_iters[l])
+        for i in range(mid + 1, d):
+            e._init_temp(l, i, -1); e._optimize(l, i, True, e.max_iters[l])
+        for i in range(mid - 1, -1, -1):
+            e._init_temp(l, i, 1); e._optimize(l, i, True, e.max_iters[l])
     return e.v[1].numpy().copy()
 
 
-def _pipeline_worker(rank, world, port, depths, q):
+def _wavefront_worker(rank, world, port, depths, q):
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
     from videomorphing_b200 import dist as vd
     vd.init(backend="gloo")
     e = _FakeEngine(depths)
-    plan = vd.run_pipeline(e, 1000.0, 1.5, rank, world)
+    plan = vd.run_wavefront(e, rank, world)
     dist.barrier()
-    q.put((rank, plan["nstages"], e.v[1].numpy().copy() if rank in (0, 1) else None))
+    q.put((rank, plan["K"], e.v[1].numpy().copy(), e.launches))
     dist.destroy_process_group()
 
 
-def test_pipeline_plan_shapes():
+def test_wavefront_plan_shapes():
     from videomorphing_b200 import dist as vd
     cfg4 = [120, 120, 120, 120, 120, 120, 61, 31, 16]                 # 720p x 120, cap lifted
-    p8 = vd.pipeline_plan(cfg4, 8)
-    assert p8["nstages"] == 4 and sorted(p8["ranks"]) == list(range(8))
-    assert [p8["ranks"][r]["levels"] for r in (0, 2, 4, 6)] == [[1], [2], [3], [7, 6, 5, 4]]
-    assert all(p8["ranks"][r]["send_to"] == (r - 2 if r >= 2 else None) for r in range(8))
-    assert all(p8["ranks"][r]["recv_from"] == (r + 2 if r < 6 else None) for r in range(8))
-    assert vd.pipeline_plan(cfg4, 4)["nstages"] == 2 and vd.pipeline_plan(cfg4, 2)["nstages"] == 1 and vd.pipeline_plan(cfg4, 1)["nstages"] == 1
-    # every optimised level is owned by exactly one pair, for any world size
-    for world in (1, 2, 3, 4, 6, 8, 16):
-        for depths in (cfg4, [9, 9, 9, 9, 5], [16, 16, 16, 9, 5, 3], [1, 1, 1, 1], [5, 5, 3]):
-            pl = vd.pipeline_plan(depths, world)
-            owned = sorted(l for r, e in pl["ranks"].items() if e["dir"] == 0 for l in e["levels"])
-            assert owned == list(range(1, len(depths) - 1))
-            for r, e in pl["ranks"].items():
-                if e["recv_from"] is not None:           # streamed-into levels have the depth of the level above
-                    assert len(e["levels"]) == 1 and depths[e["levels"][0]] == depths[e["levels"][0] + 1]
-    assert vd.chain_frames(7, 0) == [3, 4, 5, 6] and vd.chain_frames(7, 1) == [3, 2, 1, 0] and vd.chain_frames(1, 0) == [0]
+    dims = {l: (1280 >> (l - 1), 720 >> (l - 1)) for l in range(1, 9)}
+    mi = vd.level_max_iters(1000, 2, 9)
+    assert vd.wavefront_head(cfg4) == 5 and vd.wavefront_head([1, 1, 1, 1]) == 2 and vd.wavefront_head([9, 9, 9, 9, 5]) == 3
+    assert [mi[l] for l in (7, 6, 5, 4, 3, 2, 1)] == [1000.0, 500.0, 250.0, 125.0, 62.5, 31.25, 15.625]
+    for world in (2, 3, 4, 6, 8):
+        for depths in (cfg4, [9, 9, 9, 9, 5], [16, 16, 16, 9, 5, 3], [5, 5, 3]):
+            dm = {l: (64 << (len(depths) - l), 36 << (len(depths) - l)) for l in range(len(depths))}
+            pl = vd.wavefront_plan(depths, dm, vd.level_max_iters(1000, 2, len(depths)), world)
+            K = pl["K"]
+            assert sorted(pl["owner"]) == sorted((l, dr) for l in range(1, K + 1) for dr in (0, 1))     # every chain has exactly one owner
+            g0 = (world + 1) // 2
+            assert all((r < g0) == (dr == 0) for (l, dr), r in pl["owner"].items())                     # a rank serves one direction
+            assert pl["owner"][(1, 0)] == 0 and pl["owner"][(1, 1)] == g0                                # level 1 on the directions' first ranks
+            for dr in (0, 1):                                                                            # contiguous level groups, finest first
+                owners = [pl["owner"][(l, dr)] for l in range(1, K + 1)]
+                assert owners == sorted(owners)
+    p8 = vd.wavefront_plan(cfg4, dims, mi, 8)
+    assert sorted(p8["groups"]) == list(range(8))                                                        # 720p x 120 on 8 GPUs: nobody idles
+    assert vd.chain_plan(7, 2)["mid"] == 3
 
 
-@pytest.mark.parametrize("world,depths", [(4, [9, 9, 9, 9, 5]), (6, [16, 16, 16, 16, 9, 5, 3]), (4, [6, 6, 6, 4, 3])])
-def test_level_pipeline_hand_offs_on_gloo(world, depths):
-    """dist.run_pipeline on `world` CPU ranks with a stand-in engine: the frames each stage reads are final when it reads
-    them, and ranks 0 and 1 end with exactly the level-1 field of the sequential schedule."""
+@pytest.mark.parametrize("world,depths", [(2, [9, 9, 9, 9, 5]), (4, [9, 9, 9, 9, 5]), (6, [16, 16, 16, 16, 9, 5, 3]), (3, [6, 6, 6, 4, 3]), (8, [7, 7, 7, 7, 7, 7, 4])])
+def test_wavefront_hand_offs_on_gloo(world, depths):
+    """dist.run_wavefront on `world` CPU ranks with a stand-in engine: the frames each chain reads are final when it reads
+    them, every launch holds independent jobs only, and EVERY rank ends with exactly the level-1 field of the sequential
+    schedule."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_pipeline_worker, args=(r, world, port, depths, q)) for r in range(world)]
+    procs = [ctx.Process(target=_wavefront_worker, args=(r, world, port, depths, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    want = _pipeline_reference(depths, 1000.0, 1.5)
+    want = _sequential_reference(depths)
     assert np.isfinite(want).all()
-    for rank, nst, v1 in res:
-        assert nst == world // 2
-        if rank in (0, 1):
-            np.testing.assert_array_equal(v1, want)
+    for rank, K, v1, launches in res:
+        np.testing.assert_array_equal(v1, want)

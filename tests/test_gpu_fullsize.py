@@ -91,14 +91,14 @@ def _two_gpu_worker(rank, port, q, world=2):
     pyr = vm.Pyramid(rank); pyr.build(v0, v1, flows, start_res=4)
     m = vm.Morph(prm, pyr)
     vd.optimize_video(m, pyr, prm, device=rank)
-    vec = m.get_vectors() if rank < 2 else None            # the level-1 owners hold the result
+    vec = m.get_vectors()                                  # every rank ends with the whole level-1 field
     dist.barrier()
     q.put((rank, vec, m.iters_log().copy()))
     dist.destroy_process_group()
 
 
 def test_two_gpu_chain_split_is_bit_identical_to_one_gpu(vm):
-    # exact multi-GPU mode: forward chain on GPU 0, backward chain on GPU 1, v pages swapped per level over NCCL
+    # exact multi-GPU mode: the forward half of the wavefront on GPU 0, the backward half on GPU 1 (dist.run_wavefront over NCCL)
     import socket
     import torch
     import torch.multiprocessing as mp
@@ -133,8 +133,8 @@ def test_two_gpu_chain_split_is_bit_identical_to_one_gpu(vm):
 
 
 def test_frame_by_frame_level_ops_match_the_whole_level_run(vm):
-    """vm_level_upsample_frames / vm_level_initialize_frames (the level pipeline's per-frame prolongation + initialisation)
-    in chain order on ONE GPU give the bits of the ordinary run: the schedule dist.run_pipeline spreads over GPUs."""
+    """vm_level_upsample_frames / vm_level_initialize_frames / vm_level_init_temp / vm_level_optimize_frame (the wavefront's
+    per-frame operators) called one frame at a time in chain order give the bits of vm_morph_run."""
     from videomorphing_b200 import dist as vd, synth
     v0, v1, flows, field = synth.video_pair(96, 64, 9, 41, 42, 3.0)
     prm = vm.Parameters(max_iter=24, start_res=4)
@@ -156,29 +156,29 @@ def test_frame_by_frame_level_ops_match_the_whole_level_run(vm):
     assert K >= 3                                         # levels 1 .. K-1 take the frame-by-frame path (level K is prolonged as a whole)
     m2 = vm.Morph(prm, pyr)
     m2.set_constraints(*cons)
-    eng = vd.MorphEngine(m2, pyr, 0)
-    eng.coarse_solve()
+    m2.cpu_optimize_level()
     mi = np.float32(24)
+    chain = lambda d, dr: [d // 2] + (list(range(d // 2 + 1, d)) if dr == 0 else list(range(d // 2 - 1, -1, -1)))
     for l in range(n - 2, 0, -1):
         if l >= K:
-            eng.upsample(l); eng.initialize(l); eng.optimize_chains(l, float(mi), 3)
+            m2.upsample(l); m2.initialize_level(l); m2.optimize_chains(l, float(mi), 3)
         else:
             mid = depths[l] // 2
             for dr in (0, 1):
-                for i in vd.chain_frames(depths[l], dr):
+                for i in chain(depths[l], dr):
                     if dr == 1 and i == mid:
                         continue
-                    eng.upsample_frames(l, i); eng.initialize_frames(l, i)
+                    m2.upsample_frames(l, i); m2.initialize_frames(l, i)
                     if i != mid:
-                        eng.init_temp(l, i, -1 if dr == 0 else 1)
-                    eng.optimize_frame(l, i, i != mid, float(mi))
+                        m2.initialize_temp(l, i, -1 if dr == 0 else 1)
+                    m2.optimize_frame(l, i, i != mid, float(mi))
         mi = np.float32(mi / np.float32(2))
     np.testing.assert_array_equal(m2.get_vectors(), ref)
     assert {(int(l), int(f)): int(i) for l, f, i in m2.iters_log()} == ref_log
 
 
 def test_four_gpu_level_pipeline_is_bit_identical_to_one_gpu(vm):
-    # exact multi-GPU mode on 4 GPUs: direction x level pipeline (dist.pipeline_plan), frames handed on over NCCL
+    # exact multi-GPU mode on 4 GPUs: two level groups per direction (dist.wavefront_plan), frames handed on over NCCL
     import socket
     import torch
     import torch.multiprocessing as mp
@@ -200,8 +200,8 @@ def test_four_gpu_level_pipeline_is_bit_identical_to_one_gpu(vm):
     pyr = vm.Pyramid(0); pyr.build(v0, v1, flows, start_res=4)
     m = vm.Morph(prm, pyr); m.run()
     ref = m.get_vectors()
-    np.testing.assert_array_equal(res[0][0], ref)          # the two level-1 owners end with the whole field
-    np.testing.assert_array_equal(res[1][0], ref)
+    for r in range(4):
+        np.testing.assert_array_equal(res[r][0], ref)      # every rank ends with the whole field
     one = {(int(l), int(f)): int(i) for l, f, i in m.iters_log()}
     allr = {}
     for r in range(4):
@@ -227,7 +227,7 @@ def _one_gpu_pipeline_worker(rank, port, q, world):
     pyr = vm.Pyramid(0); pyr.build(v0, v1, flows, start_res=4)
     m = vm.Morph(prm, pyr)
     vd.optimize_video(m, pyr, prm, device=0)
-    vec = m.get_vectors() if rank < 2 else None            # the level-1 owners hold the result
+    vec = m.get_vectors()                                  # every rank ends with the whole level-1 field
     dist.barrier()
     q.put((rank, vec, m.iters_log().copy()))
     dist.destroy_process_group()
@@ -235,10 +235,10 @@ def _one_gpu_pipeline_worker(rank, port, q, world):
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_exact_multi_rank_schedules_on_one_gpu_are_bit_identical(vm, world):
-    """dist.optimize_video at world 2 / 3 (one frame chain per rank, v halves swapped per level, extra ranks by broadcast),
-    4 (2-stage level pipeline) and 8 (4-stage level pipeline), all ranks sharing ONE GPU: bit-identical to vm_morph_run,
-    and the union of the ranks' iteration logs is the one-GPU log.  (The same schedules on 2 / 4 real GPUs over NCCL:
-    test_two_gpu_chain_split_*, test_four_gpu_level_pipeline_*.)"""
+    """dist.optimize_video (the wavefront split by direction and level group, dist.run_wavefront) at world 2, 3, 4 and 8 with
+    all ranks sharing ONE GPU: every rank ends with the bits of vm_morph_run, and the union of the ranks' iteration logs is
+    the one-GPU log (the middle frames are optimised by both directions' owners and must agree).  (The same schedules on
+    2 / 4 real GPUs over NCCL: test_two_gpu_chain_split_*, test_four_gpu_level_pipeline_*.)"""
     import socket
     import torch.multiprocessing as mp
     from videomorphing_b200 import dist as vd, synth
@@ -255,12 +255,13 @@ def test_exact_multi_rank_schedules_on_one_gpu_are_bit_identical(vm, world):
     v0, v1, flows, _ = synth.video_pair(96, 64, 9, 41, 42, 3.0)
     prm = vm.Parameters(max_iter=24, start_res=4)
     pyr = vm.Pyramid(0); n = pyr.build(v0, v1, flows, start_res=4)
-    if world == 8:
-        assert vd.pipeline_plan([pyr.info(l)["d"] for l in range(n)], world)["nstages"] == 4
+    if world == 8:                                         # 4 equal-depth levels: each of the 8 ranks owns one (level, direction) chain
+        eng = vd.MorphEngine(vm.Morph(prm, pyr), pyr, 0, prm)
+        assert sorted(vd.wavefront_plan(eng.depths, eng.dims, eng.max_iters, world)["groups"]) == list(range(8))
     m = vm.Morph(prm, pyr); m.run()
     ref = m.get_vectors()
-    np.testing.assert_array_equal(res[0][0], ref)          # the two level-1 owners end with the whole field
-    np.testing.assert_array_equal(res[1][0], ref)
+    for r in range(world):
+        np.testing.assert_array_equal(res[r][0], ref)      # every rank ends with the whole field
     one = {(int(l), int(f)): int(i) for l, f, i in m.iters_log()}
     allr = {}
     for r in range(world):

@@ -426,3 +426,44 @@ def test_qpath_resident_and_streaming_kernels_agree(vm, oracle_lib, w, h, max_it
     qo, ito = oracle_lib.qpath_optimize(v, max_iter, 1e-12)
     assert list(it_auto) == list(ito)
     np.testing.assert_array_equal(q_auto, qo)
+
+
+@pytest.mark.parametrize("sweep,wavefront", [("tile", "1"), ("mj", "1"), ("mj", "0")])
+def test_both_sweep_kernels_and_the_wavefront_equal_the_oracle(vm, oracle_lib, sweep, wavefront, monkeypatch):
+    """VMORPH_SWEEP=tile: one tile per CTA cluster, state replicated in shared memory (vm_sweep.cu); =mj: several frames in
+    lock-step, state in L2, one global pixel queue (vm_sweep_mj.cu); VMORPH_WAVEFRONT=0: a video level by level instead of
+    the direction x level wavefront.  Every combination gives the oracle's bits and the reference-ordered iteration log."""
+    from videomorphing_b200 import synth
+    monkeypatch.setenv("VMORPH_SWEEP", sweep)
+    monkeypatch.setenv("VMORPH_WAVEFRONT", wavefront)
+    # image pair: UI constraints, locked border (BCOND_BORDER), several tiles, a partial tile row
+    rgb0, rgb1, field = synth.image_pair(150, 70, 250, 270, 3.0)
+    cons = synth.point_pairs(6, 150, 70, 7, field, margin=6)
+    o, pyr, m, n = _setup(vm, oracle_lib, rgb0, rgb1, dict(max_iter=30, bcond=2), cons=cons)
+    o.run(); m.run()
+    np.testing.assert_array_equal(m.iters_log(), o.iters_log())
+    _assert_vec(m.get_vectors(), o.extract_vectors(), f"image pair ({sweep})")
+    for f in STATE:
+        np.testing.assert_array_equal(pyr.get(1, f), o.get(1, f), err_msg=f"{sweep}: {f}")
+    # video: 13 frames, 4 equal-depth levels (a 4-stage wavefront) under one temporally subsampled level, UI points on several frames
+    v0, v1, flows, _ = synth.video_pair(96, 64, 13, 41, 42, 3.0)
+    rng = np.random.Generator(np.random.PCG64(43))
+    k = 12
+    lp = np.stack([rng.integers(8, 88, k), rng.integers(8, 56, k), rng.integers(0, 13, k), np.ones(k, np.int64)], 1).astype(np.int32)
+    rp = lp.copy(); rp[:, 0] += rng.integers(-3, 4, k).astype(np.int32); rp[:, 1] += rng.integers(-3, 4, k).astype(np.int32)
+    cons = (lp, np.ones(k, np.float32), rp, np.ones(k, np.float32))
+    o, pyr, m, n = _setup(vm, oracle_lib, v0, v1, dict(max_iter=24, start_res=4), flows=flows, cons=cons)
+    depths = [pyr.info(l)["d"] for l in range(n)]
+    assert depths[1] == depths[2] == depths[3] and len(set(depths)) > 1
+    o.run(); m.run()
+    np.testing.assert_array_equal(m.iters_log(), o.iters_log())
+    assert m.executed_pixel_iters == o.executed_pixel_iters
+    _assert_vec(m.get_vectors(), o.extract_vectors(), f"video ({sweep}, wavefront {wavefront})")
+    for f in ("temp_ref", "temp_mask", "value", "mean", "tps_b", "impmask"):
+        np.testing.assert_array_equal(pyr.get(1, f), o.get(1, f), err_msg=f"{sweep}: {f}")
+    eo, _ = o.energy(1, 0, True); eg, _ = m.energy(1, 0, True)
+    assert abs(eo - eg) <= TOL_ENERGY * abs(eo)
+    # a second run on the same objects (buffers, arenas and logs are reused) gives the same result
+    v_first = m.get_vectors()
+    m.run()
+    np.testing.assert_array_equal(m.get_vectors(), v_first)

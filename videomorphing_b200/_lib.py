@@ -42,9 +42,9 @@ EXPORTS = [
     "vm_pyramid_num_levels", "vm_pyramid_level_info", "vm_level_get", "vm_level_set", "vm_morph_create", "vm_morph_destroy",
     "vm_morph_set_tracks", "vm_morph_set_constraints", "vm_morph_run", "vm_morph_progress", "vm_morph_executed_pixel_iters",
     "vm_morph_sweep_ms", "vm_morph_attempted_updates", "vm_morph_sweep_busy_ms", "vm_morph_updates_log", "vm_morph_ms_log", "vm_morph_iters_log", "vm_level_cpu_solve", "vm_level_upsample", "vm_level_initialize", "vm_level_init_temp", "vm_level_upsample_frames", "vm_level_initialize_frames",
-    "vm_level_optimize_frame", "vm_level_optimize", "vm_level_optimize_chains", "vm_level_dev_ptr", "vm_level_mark_v_valid", "vm_dev_copy", "vm_level_energy", "vm_morph_get_vectors", "vm_morph_get_vectors_level", "vm_morph_extract", "vm_morph_render_frames", "vm_stencils_get",
+    "vm_level_optimize_frame", "vm_level_optimize", "vm_level_optimize_chains", "vm_morph_wavefront_prepare", "vm_level_enqueue_jobs", "vm_morph_collect", "vm_level_dev_ptr", "vm_level_mark_v_valid", "vm_dev_copy", "vm_level_energy", "vm_morph_get_vectors", "vm_morph_get_vectors_level", "vm_morph_extract", "vm_morph_render_frames", "vm_stencils_get",
     "vm_render_halfway_dev", "vm_render_halfway", "vm_render_sequence", "vm_qpath_optimize", "vm_qpath_optimize_frames", "vm_dev_alloc", "vm_dev_free", "vm_dev_upload",
-    "vm_dev_download", "vm_stream_sync", "vm_kernel_launch_count", "vm_selftest_exact_arith",
+    "vm_dev_download", "vm_stream_sync", "vm_kernel_launch_count", "vm_selftest_exact_arith", "vm_debug_sweep_phases",
 ]
 
 _lib = None
@@ -101,6 +101,9 @@ def load():
     L.vm_level_upsample_frames.argtypes = [vp, i32, i32, i32, vp]
     L.vm_level_initialize_frames.argtypes = [vp, i32, i32, i32, vp]
     L.vm_level_optimize_chains.argtypes = [vp, i32, f32, i32, vp]
+    L.vm_morph_wavefront_prepare.argtypes = [vp, vp]
+    L.vm_level_enqueue_jobs.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.vm_morph_collect.argtypes = [vp, vp]
     L.vm_level_dev_ptr.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.vm_level_mark_v_valid.argtypes = [vp, i32]
     L.vm_dev_copy.argtypes = [i32, vp, vp, C.c_size_t, vp]
@@ -120,6 +123,7 @@ def load():
     L.vm_dev_upload.argtypes = [i32, vp, vp, C.c_size_t, vp]
     L.vm_dev_download.argtypes = [i32, vp, vp, C.c_size_t, vp]
     L.vm_stream_sync.argtypes = [i32, vp]
+    L.vm_debug_sweep_phases.argtypes = [i32, vp, i32]
     L.vm_selftest_exact_arith.argtypes = [i32, C.c_uint64, C.POINTER(C.c_uint64)]
     _lib = L
     return L

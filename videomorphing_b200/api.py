@@ -222,6 +222,21 @@ class Morph:
         """Middle frame + the selected chains of Morph::optimize_level (1 forward, 2 backward, 3 both)."""
         check(self.L.vm_level_optimize_chains(self.h, level, float(max_iter), int(chains), stream))
 
+    def wavefront_prepare(self, stream=None):
+        """Everything above the wavefront (coarse solve, temporally subsampled levels) + head level prolonged and initialised;
+        returns the head level K.  Asynchronous."""
+        return check(self.L.vm_morph_wavefront_prepare(self.h, stream))
+
+    def enqueue_jobs(self, jobs, stream=None):
+        """ONE persistent launch over independent (level, frame, flag, max_iter) jobs in lock-step.  Asynchronous; collect()."""
+        n = len(jobs)
+        lv = (C.c_int32 * n)(*[int(j[0]) for j in jobs]); fr = (C.c_int32 * n)(*[int(j[1]) for j in jobs])
+        fl = (C.c_int32 * n)(*[int(bool(j[2])) for j in jobs]); mi = (C.c_float * n)(*[float(j[3]) for j in jobs])
+        check(self.L.vm_level_enqueue_jobs(self.h, n, lv, fr, fl, mi, stream))
+
+    def collect(self, stream=None):
+        check(self.L.vm_morph_collect(self.h, stream))
+
     def energy(self, level, frame=0, flag=False):
         e = C.c_double(0)
         t = (C.c_double * 4)()

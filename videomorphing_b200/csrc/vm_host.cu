@@ -104,17 +104,22 @@ std::vector<SchedEntry> level_schedule(int w, int h, int d, int start_res, int64
 }
 
 // ------------------------------------------------------------------ views
+Arena &arena_of(vm_pyramid *p, int level) {
+    return (level >= 0 && level < (int)p->own.size() && p->own[level]) ? *p->own[level] : p->shared;
+}
+
 LevelView make_view(vm_pyramid *p, int level) {
     const Level &l = p->lv[level];
+    const Arena &A = arena_of(p, level);
     LevelView V;
     V.w = l.w; V.h = l.h; V.d = l.d; V.rs = l.rs; V.ps = l.ps; V.irs = l.irs; V.ips = l.ips;
     V.inv_wh = l.inv_wh; V.factor_d = l.factor_d;
     V.v = l.v.as<float2>();
-    V.mean = p->mean.as<float2>(); V.var = p->var.as<float2>(); V.luma = p->luma.as<float2>();
-    V.tps_b = p->tps_b.as<float2>(); V.ui_b = p->ui_b.as<float2>(); V.temp_ref = p->temp_ref.as<float2>();
-    V.cross = p->cross.as<float>(); V.value = p->value.as<float>(); V.counter = p->counter.as<float>();
-    V.tps_axy = p->tps_axy.as<float>(); V.ui_axy = p->ui_axy.as<float>(); V.temp_mask = p->temp_mask.as<float>();
-    V.impmask = p->impmask.as<unsigned int>();
+    V.mean = A.mean.as<float2>(); V.var = A.var.as<float2>(); V.luma = A.luma.as<float2>();
+    V.tps_b = A.tps_b.as<float2>(); V.ui_b = A.ui_b.as<float2>(); V.temp_ref = A.temp_ref.as<float2>();
+    V.cross = A.cross.as<float>(); V.value = A.value.as<float>(); V.counter = A.counter.as<float>();
+    V.tps_axy = A.tps_axy.as<float>(); V.ui_axy = A.ui_axy.as<float>(); V.temp_mask = A.temp_mask.as<float>();
+    V.impmask = A.impmask.as<unsigned int>();
     V.img0 = l.img0.as<float>(); V.img1 = l.img1.as<float>();
     V.f0 = l.f0.as<float2>(); V.f1 = l.f1.as<float2>(); V.b0 = l.b0.as<float2>(); V.b1 = l.b1.as<float2>();
     return V;
@@ -217,11 +222,13 @@ int vm_pyramid_alloc(vm_pyramid *p, int w, int h, int d, int start_res, int64_t 
             VM_CUDA(cudaMemset(L.v.p, 0, sizeof(float2) * (size_t)L.ps * L.d));
             L.v_valid = false; L.flows_valid = false;
         }
-        p->state_level = -1;
+        p->shared.level = -1;
+        for (auto &a : p->own) if (a) a->level = -1;
         return (int)s.size();
     }
     p->lv.clear(); p->lv.resize(s.size());
-    p->w0 = w; p->h0 = h; p->d0 = d; p->state_level = -1; p->a_start_res = start_res; p->a_cap = voxel_cap;
+    p->own.clear();
+    p->w0 = w; p->h0 = h; p->d0 = d; p->shared.level = -1; p->a_start_res = start_res; p->a_cap = voxel_cap;
     size_t max_state = 0, max_ps = 0, max_imp = 0;
     for (size_t i = 0; i < s.size(); i++) {
         Level &L = p->lv[i];
@@ -243,11 +250,7 @@ int vm_pyramid_alloc(vm_pyramid *p, int w, int h, int d, int start_res, int64_t 
             max_imp = std::max(max_imp, (size_t)L.ips * L.d);
         }
     }
-    VM_CUDA(p->mean.ensure(8 * max_state)); VM_CUDA(p->var.ensure(8 * max_state)); VM_CUDA(p->luma.ensure(8 * max_state));
-    VM_CUDA(p->tps_b.ensure(8 * max_state)); VM_CUDA(p->ui_b.ensure(8 * max_state)); VM_CUDA(p->temp_ref.ensure(8 * max_state));
-    VM_CUDA(p->cross.ensure(4 * max_state)); VM_CUDA(p->value.ensure(4 * max_state)); VM_CUDA(p->counter.ensure(4 * max_state));
-    VM_CUDA(p->tps_axy.ensure(4 * max_state)); VM_CUDA(p->ui_axy.ensure(4 * max_state)); VM_CUDA(p->temp_mask.ensure(4 * max_state));
-    VM_CUDA(p->impmask.ensure(4 * max_imp));
+    VM_CUDA(p->shared.ensure(max_state, max_imp));
     VM_CUDA(p->tmp_a.ensure(sizeof(long long) * 3 * max_ps)); VM_CUDA(p->tmp_b.ensure(sizeof(float2) * max_ps)); VM_CUDA(p->tmp_c.ensure(sizeof(float) * max_ps));
     if (d > 2) VM_CUDA(p->tmp_a2.ensure(sizeof(long long) * 3 * max_ps));
     return (int)s.size();
@@ -270,22 +273,22 @@ static int field_ptr(vm_pyramid *p, int level, int field, void **ptr, size_t *by
     size_t n = (size_t)L.ps * L.d, fs = (size_t)L.w * L.h * L.d;
     bool state = field >= VM_FIELD_SSIM_MEAN && field <= VM_FIELD_IMPROVING_MASK;
     if (state && !(L.has_images)) { set_error("level %d has no optimizer state", level); return VM_ERR_STATE; }
-    if (state && p->state_level != level && p->state_level != -1) { /* arena describes another level: still addressable with this level's strides */ }
+    Arena &A = arena_of(p, level);      // (an arena that describes another level is still addressable with this level's strides)
     switch (field) {
     case VM_FIELD_V: *ptr = L.v.p; *bytes = 8 * n; break;
-    case VM_FIELD_SSIM_MEAN: *ptr = p->mean.p; *bytes = 8 * n; break;
-    case VM_FIELD_SSIM_VAR: *ptr = p->var.p; *bytes = 8 * n; break;
-    case VM_FIELD_SSIM_LUMA: *ptr = p->luma.p; *bytes = 8 * n; break;
-    case VM_FIELD_SSIM_CROSS: *ptr = p->cross.p; *bytes = 4 * n; break;
-    case VM_FIELD_SSIM_VALUE: *ptr = p->value.p; *bytes = 4 * n; break;
-    case VM_FIELD_SSIM_COUNTER: *ptr = p->counter.p; *bytes = 4 * n; break;
-    case VM_FIELD_TPS_AXY: *ptr = p->tps_axy.p; *bytes = 4 * n; break;
-    case VM_FIELD_TPS_B: *ptr = p->tps_b.p; *bytes = 8 * n; break;
-    case VM_FIELD_UI_AXY: *ptr = p->ui_axy.p; *bytes = 4 * n; break;
-    case VM_FIELD_UI_B: *ptr = p->ui_b.p; *bytes = 8 * n; break;
-    case VM_FIELD_TEMP_REF: *ptr = p->temp_ref.p; *bytes = 8 * n; break;
-    case VM_FIELD_TEMP_MASK: *ptr = p->temp_mask.p; *bytes = 4 * n; break;
-    case VM_FIELD_IMPROVING_MASK: *ptr = p->impmask.p; *bytes = 4 * (size_t)L.ips * L.d; break;
+    case VM_FIELD_SSIM_MEAN: *ptr = A.mean.p; *bytes = 8 * n; break;
+    case VM_FIELD_SSIM_VAR: *ptr = A.var.p; *bytes = 8 * n; break;
+    case VM_FIELD_SSIM_LUMA: *ptr = A.luma.p; *bytes = 8 * n; break;
+    case VM_FIELD_SSIM_CROSS: *ptr = A.cross.p; *bytes = 4 * n; break;
+    case VM_FIELD_SSIM_VALUE: *ptr = A.value.p; *bytes = 4 * n; break;
+    case VM_FIELD_SSIM_COUNTER: *ptr = A.counter.p; *bytes = 4 * n; break;
+    case VM_FIELD_TPS_AXY: *ptr = A.tps_axy.p; *bytes = 4 * n; break;
+    case VM_FIELD_TPS_B: *ptr = A.tps_b.p; *bytes = 8 * n; break;
+    case VM_FIELD_UI_AXY: *ptr = A.ui_axy.p; *bytes = 4 * n; break;
+    case VM_FIELD_UI_B: *ptr = A.ui_b.p; *bytes = 8 * n; break;
+    case VM_FIELD_TEMP_REF: *ptr = A.temp_ref.p; *bytes = 8 * n; break;
+    case VM_FIELD_TEMP_MASK: *ptr = A.temp_mask.p; *bytes = 4 * n; break;
+    case VM_FIELD_IMPROVING_MASK: *ptr = A.impmask.p; *bytes = 4 * (size_t)L.ips * L.d; break;
     case VM_FIELD_IMG0: *ptr = L.img0.p; *bytes = 4 * fs; break;
     case VM_FIELD_IMG1: *ptr = L.img1.p; *bytes = 4 * fs; break;
     case VM_FIELD_F0: *ptr = L.f0.p; *bytes = 8 * fs; break;
@@ -324,9 +327,17 @@ int vm_morph_create(const vm_params *prm, vm_pyramid *pyr, volatile int *run_fla
     if (pyr->lv.size() < 3) { set_error("pyramid not allocated"); return VM_ERR_STATE; }
     if (prm->max_iter < 1 || prm->max_iter > VM_MAX_ITER || prm->max_iter_drop_factor <= 0 || prm->eps <= 0) { set_error("bad parameters (max_iter 1..%d, drop > 0, eps > 0)", VM_MAX_ITER); return VM_ERR_ARG; }
     sweep_reload_hooks();
+    sweep_mj_reload_hooks();
     int rc = use_device(pyr->device); if (rc) return rc;
     vm_morph *m = new vm_morph();
     m->prm = *prm; m->pyr = pyr; m->run_flag = run_flag;
+    {   // VMORPH_SWEEP=tile|mj selects the sweep kernel for every launch (default: multi-job kernel for videos, tile kernel for
+        // image pairs); VMORPH_WAVEFRONT=0 runs a video level by level instead of as a direction x level wavefront
+        const char *e = getenv("VMORPH_SWEEP");
+        m->sweep_mode = !e ? 0 : (!strcmp(e, "tile") ? 1 : (!strcmp(e, "mj") ? 2 : 0));
+        const char *wv = getenv("VMORPH_WAVEFRONT");
+        m->no_wavefront = wv && atoi(wv) == 0;
+    }
     if (run_flag) {
         if (cudaHostRegister((void *)run_flag, sizeof(int), cudaHostRegisterMapped) == cudaSuccess) {
             m->run_flag_registered = true;
@@ -455,17 +466,18 @@ int vm_level_initialize(vm_morph *m, int level, void *stream) {
     if (!L.img0.p || !L.img1.p) { set_error("level %d has no images", level); return VM_ERR_STATE; }
     size_t n = (size_t)L.ps * L.d;
     // morph.cu:280-314: (re)size + zero-fill of every per-level array (the arena is reused across levels)
-    VM_CUDA(cudaMemsetAsync(p->mean.p, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(p->var.p, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(p->luma.p, 0, 8 * n, s));
-    VM_CUDA(cudaMemsetAsync(p->cross.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(p->value.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(p->counter.p, 0, 4 * n, s));
-    VM_CUDA(cudaMemsetAsync(p->tps_axy.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(p->tps_b.p, 0, 8 * n, s));
-    VM_CUDA(cudaMemsetAsync(p->ui_axy.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(p->ui_b.p, 0, 8 * n, s));
-    VM_CUDA(cudaMemsetAsync(p->temp_ref.p, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(p->temp_mask.p, 0, 4 * n, s));
-    VM_CUDA(cudaMemsetAsync(p->impmask.p, 0, 4 * (size_t)L.ips * L.d, s));
+    Arena &A = arena_of(p, level);
+    VM_CUDA(cudaMemsetAsync(A.mean.p, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(A.var.p, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(A.luma.p, 0, 8 * n, s));
+    VM_CUDA(cudaMemsetAsync(A.cross.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(A.value.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(A.counter.p, 0, 4 * n, s));
+    VM_CUDA(cudaMemsetAsync(A.tps_axy.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(A.tps_b.p, 0, 8 * n, s));
+    VM_CUDA(cudaMemsetAsync(A.ui_axy.p, 0, 4 * n, s)); VM_CUDA(cudaMemsetAsync(A.ui_b.p, 0, 8 * n, s));
+    VM_CUDA(cudaMemsetAsync(A.temp_ref.p, 0, 8 * n, s)); VM_CUDA(cudaMemsetAsync(A.temp_mask.p, 0, 4 * n, s));
+    VM_CUDA(cudaMemsetAsync(A.impmask.p, 0, 4 * (size_t)L.ips * L.d, s));
     LevelView V = make_view(p, level);
     VM_CUDA(launch_initialize_level(V, p->stencils.as<StencilTables>(), m->prm.ssim_clamp, s));
     int factor = (int)(p->lv[0].factor_d / L.factor_d);                          // morph.cu:350
     VM_CUDA(launch_ui_splat(V, m->cons_dev.as<Conn>(), (int)m->cons.size(), factor, p->lv[0].w, p->lv[0].h, p->lv[0].d, s));
-    p->state_level = level;
+    A.level = level;
     return VM_OK;
 }
 
@@ -507,7 +519,7 @@ int vm_level_initialize_frames(vm_morph *m, int level, int frame0, int nframes, 
     VM_CUDA(launch_initialize_level(V, p->stencils.as<StencilTables>(), m->prm.ssim_clamp, s));
     int factor = (int)(p->lv[0].factor_d / L.factor_d);
     VM_CUDA(launch_ui_splat(V, m->cons_dev.as<Conn>(), (int)m->cons.size(), factor, p->lv[0].w, p->lv[0].h, p->lv[0].d, s, frame0));
-    p->state_level = level;
+    arena_of(p, level).level = level;
     return VM_OK;
 }
 
@@ -516,7 +528,7 @@ int vm_level_init_temp(vm_morph *m, int level, int frame, int dir, void *stream)
 static int init_temp_chain(vm_morph *m, int level, int frame, int dir, cudaStream_t stream, int chain) {
     if (!m) { set_error("null morph"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
-    if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
+    if (level < 1 || level + 1 >= (int)p->lv.size() || arena_of(p, level).level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
     Level &L = p->lv[level];
     if ((dir != 1 && dir != -1) || frame < 0 || frame >= L.d || frame + dir < 0 || frame + dir >= L.d) { set_error("bad frame/dir %d/%d", frame, dir); return VM_ERR_ARG; }
     if (!L.f0.p) { set_error("level %d has no optical flows", level); return VM_ERR_STATE; }
@@ -538,7 +550,20 @@ static int grow_log(vm_morph *m, size_t launches) {
     }
     return VM_OK;
 }
+struct JobSpec { int level, frame, flag; float max_iter; };
+static int enqueue_jobs(vm_morph *m, const JobSpec *js, int n, cudaStream_t s);
+static bool use_mj(const vm_morph *m) { return m->sweep_mode == 2 || (m->sweep_mode == 0 && m->pyr->d0 > 1); }
+
+static int enqueue_frame_tile(vm_morph *m, int level, int frame, int flag, float max_iter, cudaStream_t s, int *seq_out, int chain = 0, int sm_budget = 0);
 static int enqueue_frame(vm_morph *m, int level, int frame, int flag, float max_iter, cudaStream_t s, int *seq_out, int chain = 0, int sm_budget = 0) {
+    if (use_mj(m)) {
+        JobSpec j{level, frame, flag, max_iter};
+        if (seq_out) *seq_out = (int)m->seqs.size();
+        return enqueue_jobs(m, &j, 1, s);
+    }
+    return enqueue_frame_tile(m, level, frame, flag, max_iter, s, seq_out, chain, sm_budget);
+}
+static int enqueue_frame_tile(vm_morph *m, int level, int frame, int flag, float max_iter, cudaStream_t s, int *seq_out, int chain, int sm_budget) {
     vm_pyramid *p = m->pyr;
     Level &L = p->lv[level];
     int seq = (int)m->seqs.size();
@@ -554,7 +579,7 @@ static int enqueue_frame(vm_morph *m, int level, int frame, int flag, float max_
         if (!m->ev_base) VM_CUDA(cudaEventCreate(&m->ev_base));
         VM_CUDA(cudaEventRecord(m->ev_base, s));
     }
-    m->seqs.push_back({level, frame, (double)L.w * L.h, max_iter});
+    m->seqs.push_back({level, frame, (double)L.w * L.h, max_iter, seq});
     while (m->ev.size() < 2 * (size_t)(seq + 1)) { cudaEvent_t e; VM_CUDA(cudaEventCreate(&e)); m->ev.push_back(e); }
     VM_CUDA(cudaEventRecord(m->ev[2 * seq], s));
     VM_CUDA(launch_sweep(make_view(p, level), kparams(m->prm), p->stencils.as<StencilTables>(), frame, flag, max_iter,
@@ -577,14 +602,35 @@ static int collect_log(vm_morph *m, size_t /*from*/, cudaStream_t s) {
     VM_CUDA(cudaMemcpy(it.data(), m->log_dev.p, sizeof(unsigned) * 2 * n, cudaMemcpyDeviceToHost));
     std::vector<std::pair<float, float>> iv;
     iv.reserve(n);
+    // the logs keep the reference's order -- levels coarse to fine, within a level the middle frame, the forward chain, the
+    // backward chain (morph.cu:1374-1439) -- whatever order the wavefront / the two chains were enqueued in
+    std::vector<size_t> order(n);
+    for (size_t k = 0; k < n; k++) order[k] = k;
+    auto key = [&](size_t k) {
+        const vm_morph::Seq &q = m->seqs[k];
+        const int dd = m->pyr->lv[q.level].d, mid = dd / 2;
+        const long long pos = q.frame >= mid ? q.frame - mid : (dd - mid) + (mid - 1 - q.frame);
+        return (long long)(1000 - q.level) * 100000000LL + pos;
+    };
+    bool sorted = true;
+    for (size_t k = 1; k < n && sorted; k++) sorted = key(k - 1) <= key(k);
+    if (!sorted && m->sort_log) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key(a) < key(b); });
+    std::vector<float> ms_of(n, 0.f);
     for (size_t k = 0; k < n; k++) {
         float ms = 0.f, t0 = 0.f;
-        if (cudaEventElapsedTime(&ms, m->ev[2 * k], m->ev[2 * k + 1]) == cudaSuccess) { m->sweep_ms += ms; m->sweep_launches++; } else cudaGetLastError();
-        if (m->ev_base && cudaEventElapsedTime(&t0, m->ev_base, m->ev[2 * k]) == cudaSuccess) iv.push_back({t0, t0 + ms}); else cudaGetLastError();
-        m->ms_log.push_back(ms);
+        const int ek = m->seqs[k].ev;                       // -1: the job shared the previous job's launch (its time is logged there)
+        if (ek >= 0) {
+            if (cudaEventElapsedTime(&ms, m->ev[2 * ek], m->ev[2 * ek + 1]) == cudaSuccess) { m->sweep_ms += ms; m->sweep_launches++; } else cudaGetLastError();
+            if (m->ev_base && cudaEventElapsedTime(&t0, m->ev_base, m->ev[2 * ek]) == cudaSuccess) iv.push_back({t0, t0 + ms}); else cudaGetLastError();
+        }
+        ms_of[k] = ms;
         m->executed_pixel_iters += m->seqs[k].wh * it[2 * k];
         m->attempted_updates += (double)it[2 * k + 1];
         m->done_iter += m->seqs[k].wh * m->seqs[k].max_iter;                                  // morph.cu:1391
+    }
+    for (size_t o = 0; o < n; o++) {
+        const size_t k = order[o];
+        m->ms_log.push_back(ms_of[k]);
         m->iters_log.push_back(m->seqs[k].level); m->iters_log.push_back(m->seqs[k].frame); m->iters_log.push_back((int)it[2 * k]);
         m->upd_log.push_back(it[2 * k + 1]);
     }
@@ -601,10 +647,165 @@ static int collect_log(vm_morph *m, size_t /*from*/, cudaStream_t s) {
     return VM_OK;
 }
 
+
+// ---- multi-job sweep (vm_sweep_mj.cu): n independent (level, frame) jobs advance in lock-step in ONE persistent launch
+static int enqueue_jobs(vm_morph *m, const JobSpec *js, int n, cudaStream_t s) {
+    vm_pyramid *p = m->pyr;
+    if (n < 1 || n > MJ_MAX_JOBS) { set_error("bad job count %d", n); return VM_ERR_ARG; }
+    const int seq0 = (int)m->seqs.size();
+    if (seq0 + n >= (1 << 22)) { set_error("too many sweep launches in one call"); return VM_ERR_STATE; }
+    int rc = grow_log(m, (size_t)seq0 + n); if (rc) return rc;
+    const size_t gw = sweep_mj_gctrl_words(), jw = sweep_mj_job_ctrl_words();
+    size_t cand = 0;
+    for (int k = 0; k < n; k++) cand += (size_t)sweep_num_tiles(p->lv[js[k].level].w, p->lv[js[k].level].h) * 256;
+    bool grow = m->mj_ctrl.bytes < 4 * (gw + MJ_MAX_JOBS * jw) || m->mj_jobs.bytes < sizeof(SweepJob) * MJ_MAX_JOBS || m->mj_queue.bytes < 4 * cand || m->mj_acc.bytes < 4 * cand;
+    for (int k = 0; k < n; k++) grow = grow || m->mj_scratch[k].bytes < 32 * (size_t)p->lv[js[k].level].ps;
+    if (grow) {
+        VM_CUDA(cudaDeviceSynchronize());
+        VM_CUDA(m->mj_ctrl.ensure(4 * (gw + MJ_MAX_JOBS * jw))); VM_CUDA(m->mj_jobs.ensure(sizeof(SweepJob) * MJ_MAX_JOBS));
+        VM_CUDA(m->mj_queue.ensure(4 * cand + 4096)); VM_CUDA(m->mj_acc.ensure(4 * cand + 4096));
+        for (int k = 0; k < n; k++) VM_CUDA(m->mj_scratch[k].ensure(32 * (size_t)p->lv[js[k].level].ps));
+    }
+    if (seq0 == 0) {                                      // time origin of this call's launch intervals
+        if (!m->ev_base) VM_CUDA(cudaEventCreate(&m->ev_base));
+        VM_CUDA(cudaEventRecord(m->ev_base, s));
+    }
+    SweepJob host[MJ_MAX_JOBS];
+    unsigned *ctrl = m->mj_ctrl.as<unsigned>();
+    VM_CUDA(cudaMemsetAsync(ctrl, 0, 4 * (gw + (size_t)n * jw), s));
+    for (int k = 0; k < n; k++) {
+        const Level &L = p->lv[js[k].level];
+        if (arena_of(p, js[k].level).level != js[k].level) { set_error("level %d is not initialised", js[k].level); return VM_ERR_STATE; }
+        SweepJob &J = host[k];
+        J.L = make_frames_view(p, js[k].level, js[k].frame, 1);
+        J.flag = js[k].flag; J.max_iter = js[k].max_iter;
+        J.gx = (L.w + 68) / 69; J.gy = (L.h + 20) / 21;                           // morph.cu:1369-1371
+        J.seq = seq0 + k; J.pad = 0;
+        J.ctrl = ctrl + gw + (size_t)k * jw;
+        unsigned char *sc = m->mj_scratch[k].as<unsigned char>();
+        const size_t ps = (size_t)L.ps;
+        J.stamp = reinterpret_cast<unsigned *>(sc); J.sd = reinterpret_cast<float2 *>(sc + 4 * ps); J.sdm = reinterpret_cast<float2 *>(sc + 12 * ps);
+        J.sdv = reinterpret_cast<float2 *>(sc + 20 * ps); J.sdc = reinterpret_cast<float *>(sc + 28 * ps);
+        VM_CUDA(cudaMemsetAsync(J.stamp, 0, 4 * ps, s));
+        m->seqs.push_back({js[k].level, js[k].frame, (double)L.w * L.h, js[k].max_iter, k == 0 ? seq0 : -1});
+    }
+    VM_CUDA(cudaMemcpyAsync(m->mj_jobs.p, host, sizeof(SweepJob) * n, cudaMemcpyHostToDevice, s));
+    while (m->ev.size() < 2 * (size_t)(seq0 + 1)) { cudaEvent_t e; VM_CUDA(cudaEventCreate(&e)); m->ev.push_back(e); }
+    VM_CUDA(cudaEventRecord(m->ev[2 * seq0], s));
+    VM_CUDA(launch_sweep_jobs(m->mj_jobs.as<SweepJob>(), host, n, kparams(m->prm), p->stencils.as<StencilTables>(), ctrl, m->mj_queue.as<unsigned>(),
+                              m->mj_acc.as<unsigned>(), m->run_flag_dev, m->progress_dev, p->sm_count, 0, s));
+    VM_CUDA(cudaEventRecord(m->ev[2 * seq0 + 1], s));
+    // per job: iterations -> log[2 seq], attempted updates -> log[2 seq + 1] (control words 0 and 2 of the job)
+    for (int k = 0; k < n; k++) {
+        VM_CUDA(cudaMemcpyAsync(m->log_dev.as<unsigned>() + 2 * (seq0 + k), host[k].ctrl + 0, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
+        VM_CUDA(cudaMemcpyAsync(m->log_dev.as<unsigned>() + 2 * (seq0 + k) + 1, host[k].ctrl + 2, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
+    }
+    return VM_OK;
+}
+
+// Morph::optimize_level (morph.cu:1353-1441) of one level with the multi-job kernel: the forward and the backward chain
+// advance together, one launch per chain position with (up to) two jobs.
+static int enqueue_level_mj(vm_morph *m, int level, float max_iter, cudaStream_t s, int chains) {
+    vm_pyramid *p = m->pyr; Level &L = p->lv[level];
+    const int mid = L.d / 2, nf = L.d - mid, nb = mid;
+    for (int c = 0; c < std::max(nf, nb + 1); c++) {
+        if (!keep_running(m)) break;
+        JobSpec js[2]; int n = 0;
+        if (c == 0) js[n++] = {level, mid, 0, max_iter};
+        else if (c < nf && (chains & 1)) { int rc = init_temp_chain(m, level, mid + c, -1, s, 0); if (rc) return rc; js[n++] = {level, mid + c, 1, max_iter}; }
+        if (c >= 1 && c - 1 < nb && (chains & 2)) { int rc = init_temp_chain(m, level, mid - c, 1, s, 0); if (rc) return rc; js[n++] = {level, mid - c, 1, max_iter}; }
+        if (n) { int rc = enqueue_jobs(m, js, n, s); if (rc) return rc; }
+    }
+    return VM_OK;
+}
+
+// Morph::calculate_halfway_parametrization (morph.cu:150-168) of a video as a direction x level WAVEFRONT on one GPU.
+// Frame i of level l needs frame i of level l+1 (prolongation) and frame i -/+ 1 of level l (temporal reference,
+// morph.cu:1392-1439), so while level l works on chain position c, level l-1 can work on position c-1, and the forward
+// and backward chains are independent.  Levels 1 .. K (K = head: the coarsest level whose finer levels all have its depth,
+// i.e. no temporal in-fill between them, upsample.cu:297-338) run as K stages one chain position behind each other; every
+// tick is ONE multi-job launch with up to 2 K jobs.  The coarser levels (temporally subsampled) run whole, one after the other.
+// Same arithmetic as the level-by-level order: bit-identical vectors, identical iteration counts.
+static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s, int chains, bool allow_mj);
+static int wavefront_head(vm_morph *m) {
+    vm_pyramid *p = m->pyr;
+    const int n = (int)p->lv.size();
+    int K = 1;
+    while (K + 1 <= n - 2 && p->lv[K].d == p->lv[K + 1].d) K++;
+    if (2 * K > MJ_MAX_JOBS) K = MJ_MAX_JOBS / 2;                                                 // deeper pyramids: the coarsest equal-depth levels run whole
+    return K;
+}
+// the levels in flight together own their arenas (level 1 keeps the shared one)
+static int wavefront_arenas(vm_morph *m, int K) {
+    vm_pyramid *p = m->pyr;
+    const int n = (int)p->lv.size();
+    if (p->own.size() < (size_t)n) p->own.resize(n);
+    for (int l = 2; l <= K; l++)
+        if (!p->own[l]) {
+            VM_CUDA(cudaDeviceSynchronize());
+            p->own[l].reset(new Arena());
+            VM_CUDA(p->own[l]->ensure((size_t)p->lv[l].ps * p->lv[l].d, (size_t)p->lv[l].ips * p->lv[l].d));
+        }
+    return VM_OK;
+}
+// the temporally subsampled levels above the wavefront, whole and one after the other; they have 1 - 2 tiles, where a
+// cluster per tile (tile kernel, both chains side by side on two streams) has the shorter round
+static int wavefront_coarse(vm_morph *m, int K, const std::vector<float> &mi, cudaStream_t s) {
+    vm_pyramid *p = m->pyr;
+    const int n = (int)p->lv.size();
+    int rc = vm_level_cpu_solve(m, s); if (rc) return rc;
+    for (int l = n - 2; l > K; l--) {
+        if (!keep_running(m)) { m->cancelled = true; return VM_OK; }
+        m->max_iter_now = mi[l];
+        rc = vm_level_upsample(m, l, s); if (rc) return rc;
+        rc = vm_level_initialize(m, l, s); if (rc) return rc;
+        rc = enqueue_level(m, l, mi[l], s, 3, m->sweep_mode == 2); if (rc) return rc;
+    }
+    if (!keep_running(m)) { m->cancelled = true; return VM_OK; }
+    rc = vm_level_upsample(m, K, s); if (rc) return rc;
+    return vm_level_initialize(m, K, s);
+}
+
+static int run_wavefront(vm_morph *m, cudaStream_t s) {
+    vm_pyramid *p = m->pyr;
+    const int n = (int)p->lv.size();
+    std::vector<float> mi(n, 0.f);
+    float cur = (float)m->prm.max_iter;
+    for (int l = n - 2; l >= 1; l--) { mi[l] = cur; cur /= m->prm.max_iter_drop_factor; }        // morph.cu:163
+    const int K = wavefront_head(m);
+    int rc = wavefront_arenas(m, K); if (rc) return rc;
+    rc = wavefront_coarse(m, K, mi, s); if (rc) return rc;
+    if (m->cancelled) return VM_OK;
+    const int d = p->lv[K].d, mid = d / 2, nf = d - mid, nb = mid;
+    const int nticks = K - 1 + std::max(nf, nb + 1);
+    for (int T = 0; T < nticks; T++) {
+        if (!keep_running(m)) { m->cancelled = true; break; }
+        JobSpec js[MJ_MAX_JOBS]; int nj = 0;
+        for (int st = 0; st < K; st++) {
+            const int l = K - st;
+            for (int dr = 0; dr < 2; dr++) {
+                const int c = T - st - dr;                       // the backward chain starts one tick after the middle frame
+                if (c < 0 || c >= (dr == 0 ? nf : nb)) continue;
+                const int i = dr == 0 ? mid + c : mid - 1 - c;
+                if (st > 0) {
+                    rc = vm_level_upsample_frames(m, l, i, 1, s); if (rc) return rc;
+                    rc = vm_level_initialize_frames(m, l, i, 1, s); if (rc) return rc;
+                }
+                const bool first = dr == 0 && c == 0;            // the middle frame has no temporal term (morph.cu:1377-1391)
+                if (!first) { rc = init_temp_chain(m, l, i, dr == 0 ? -1 : 1, s, 0); if (rc) return rc; }
+                js[nj++] = {l, i, first ? 0 : 1, mi[l]};
+            }
+        }
+        if (nj) { m->max_iter_now = js[nj - 1].max_iter; rc = enqueue_jobs(m, js, nj, s); if (rc) return rc; }
+    }
+    for (int l = 1; l <= K; l++) p->lv[l].v_valid = true;
+    return VM_OK;
+}
+
 int vm_level_optimize_frame(vm_morph *m, int level, int frame, int flag, float max_iter, int *iters_out, void *stream) {
     if (!m) { set_error("null morph"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
-    if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
+    if (level < 1 || level + 1 >= (int)p->lv.size() || arena_of(p, level).level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
     if (frame < 0 || frame >= p->lv[level].d || !(max_iter > 0) || max_iter > (float)VM_MAX_ITER) { set_error("bad frame %d / max_iter %g", frame, max_iter); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
     size_t from = m->seqs.size();
@@ -619,10 +820,11 @@ int vm_level_optimize_frame(vm_morph *m, int level, int frame, int flag, float m
 // frame's result, so they are enqueued on two streams and run CONCURRENTLY, each with half of the SMs as its budget
 // (coarse levels occupy a fraction of the GPU anyway).  Same arithmetic, same results as the sequential order; the
 // iteration log keeps the reference's order.  VMORPH_CHAINS=1 forces the sequential schedule (test hook).
-static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s, int chains = 3) {
+static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s, int chains = 3, bool allow_mj = true) {
     vm_pyramid *p = m->pyr; Level &L = p->lv[level];
+    if (allow_mj && use_mj(m)) return enqueue_level_mj(m, level, max_iter, s, chains);
     int mid = L.d / 2, rc;
-    rc = enqueue_frame(m, level, mid, 0, max_iter, s, nullptr); if (rc) return rc;
+    rc = enqueue_frame_tile(m, level, mid, 0, max_iter, s, nullptr); if (rc) return rc;
     const char *ec = getenv("VMORPH_CHAINS");
     // (measured on 720p x 48: side by side 2.46 s, taking turns with the whole GPU 3.26 s, a per-level mix 2.81 s -- the
     //  overlap wins even at tile counts where half a GPU needs two waves of clusters; profiles/r1_video.md)
@@ -640,12 +842,12 @@ static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s,
     for (int i = mid + 1; i < L.d && (chains & 1); i++) {
         if (!keep_running(m)) break;
         rc = init_temp_chain(m, level, i, -1, sf, 0); if (rc) return rc;
-        rc = enqueue_frame(m, level, i, 1, max_iter, sf, nullptr, 0, budget); if (rc) return rc;
+        rc = enqueue_frame_tile(m, level, i, 1, max_iter, sf, nullptr, 0, budget); if (rc) return rc;
     }
     for (int i = mid - 1; i >= 0 && (chains & 2); i--) {
         if (!keep_running(m)) break;
         rc = init_temp_chain(m, level, i, 1, sb, two ? 1 : 0); if (rc) return rc;
-        rc = enqueue_frame(m, level, i, 1, max_iter, sb, nullptr, two ? 1 : 0, budget); if (rc) return rc;
+        rc = enqueue_frame_tile(m, level, i, 1, max_iter, sb, nullptr, two ? 1 : 0, budget); if (rc) return rc;
     }
     if (two) {
         VM_CUDA(cudaEventRecord(m->chain_ev[1], sf));
@@ -662,7 +864,7 @@ static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s,
 int vm_level_optimize_chains(vm_morph *m, int level, float max_iter, int chains, void *stream) {
     if (!m) { set_error("null morph"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
-    if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
+    if (level < 1 || level + 1 >= (int)p->lv.size() || arena_of(p, level).level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
     if (!(max_iter > 0) || max_iter > (float)VM_MAX_ITER || chains < 0 || chains > 3) { set_error("bad max_iter %g / chains %d", max_iter, chains); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
     size_t from = m->seqs.size();
@@ -693,12 +895,51 @@ int vm_dev_copy(int device, void *dst_dev, const void *src_dev, size_t nbytes, v
 int vm_level_optimize(vm_morph *m, int level, float max_iter, void *stream) {
     if (!m) { set_error("null morph"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
-    if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
+    if (level < 1 || level + 1 >= (int)p->lv.size() || arena_of(p, level).level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
     if (!(max_iter > 0) || max_iter > (float)VM_MAX_ITER) { set_error("bad max_iter %g", max_iter); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
     size_t from = m->seqs.size();
     rc = enqueue_level(m, level, max_iter, s); if (rc) return rc;
     return collect_log(m, from, s);
+}
+
+// ---- building blocks of the multi-GPU wavefront (videomorphing_b200/dist.py drives the same schedule over several ranks)
+int vm_morph_wavefront_prepare(vm_morph *m, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr; cudaStream_t s = (cudaStream_t)stream;
+    int rc = use_device(p->device); if (rc) return rc;
+    for (int l = 1; l + 1 < (int)p->lv.size(); l++)
+        if (!p->lv[l].img0.p) { set_error("level %d has no images: call vm_pyramid_build first", l); return VM_ERR_STATE; }
+    const int n = (int)p->lv.size();
+    std::vector<float> mi(n, 0.f);
+    float cur = (float)m->prm.max_iter;
+    for (int l = n - 2; l >= 1; l--) { mi[l] = cur; cur /= m->prm.max_iter_drop_factor; }
+    const int K = wavefront_head(m);
+    rc = wavefront_arenas(m, K); if (rc) return rc;
+    m->cancelled = false; m->done_iter = 0; m->total_l = n - 1;
+    rc = wavefront_coarse(m, K, mi, s); if (rc) return rc;
+    return K;
+}
+
+int vm_level_enqueue_jobs(vm_morph *m, int n, const int32_t *levels, const int32_t *frames, const int32_t *flags, const float *max_iters, void *stream) {
+    if (!m || n < 1 || n > MJ_MAX_JOBS || !levels || !frames || !flags || !max_iters) { set_error("bad job list"); return VM_ERR_ARG; }
+    vm_pyramid *p = m->pyr;
+    int rc = use_device(p->device); if (rc) return rc;
+    JobSpec js[MJ_MAX_JOBS];
+    for (int k = 0; k < n; k++) {
+        const int l = levels[k];
+        if (l < 1 || l + 1 >= (int)p->lv.size() || frames[k] < 0 || frames[k] >= p->lv[l].d || !(max_iters[k] > 0) || max_iters[k] > (float)VM_MAX_ITER) {
+            set_error("bad job %d: level %d frame %d max_iter %g", k, l, frames[k], max_iters[k]); return VM_ERR_ARG; }
+        for (int q = 0; q < k; q++) if (levels[q] == l && frames[q] == frames[k]) { set_error("job %d repeats level %d frame %d", k, l, frames[k]); return VM_ERR_ARG; }
+        js[k] = {l, frames[k], flags[k], max_iters[k]};
+    }
+    return enqueue_jobs(m, js, n, (cudaStream_t)stream);
+}
+
+int vm_morph_collect(vm_morph *m, void *stream) {
+    if (!m) { set_error("null morph"); return VM_ERR_ARG; }
+    int rc = use_device(m->pyr->device); if (rc) return rc;
+    return collect_log(m, 0, (cudaStream_t)stream);
 }
 
 // Morph::calculate_halfway_parametrization (morph.cu:150-168)
@@ -713,6 +954,10 @@ int vm_morph_run(vm_morph *m, void *stream) {
     m->done_iter = 0;
     m->total_l = (int)p->lv.size() - 1;
     float max_iter = (float)m->prm.max_iter;
+    if (use_mj(m) && p->d0 > 1 && !m->no_wavefront) {
+        rc = run_wavefront(m, s); if (rc) return rc;
+        return collect_log(m, from, s);
+    }
     rc = vm_level_cpu_solve(m, s); if (rc) return rc;
     for (int l = m->total_l - 1; l > 0; l--) {
         if (!keep_running(m)) { m->cancelled = true; continue; }                // morph.cu:156
@@ -772,7 +1017,7 @@ int vm_morph_ms_log(const vm_morph *m, int max_entries, float *out) {
 int vm_level_energy(vm_morph *m, int level, int frame, int flag, double *energy_out, double *terms_out) {
     if (!m) { set_error("null morph"); return VM_ERR_ARG; }
     vm_pyramid *p = m->pyr;
-    if (level < 1 || level + 1 >= (int)p->lv.size() || p->state_level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
+    if (level < 1 || level + 1 >= (int)p->lv.size() || arena_of(p, level).level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
     if (frame < 0 || frame >= p->lv[level].d) { set_error("bad frame"); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
     VM_CUDA(cudaDeviceSynchronize());
@@ -960,6 +1205,14 @@ int vm_selftest_exact_arith(int device, uint64_t n_div, uint64_t *mismatches3) {
     unsigned long long h[3];
     VM_CUDA(cudaMemcpy(h, out.p, sizeof(h), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 3; k++) mismatches3[k] = h[k];
+    return VM_OK;
+}
+
+int vm_debug_sweep_phases(int device, uint64_t *out8, int reset) {
+    int rc = use_device(device); if (rc) return rc;
+    unsigned long long t[8] = {0};
+    VM_CUDA(sweep_mj_trace(t, reset));
+    if (out8) for (int k = 0; k < 8; k++) out8[k] = t[k];
     return VM_OK;
 }
 

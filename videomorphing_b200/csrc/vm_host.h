@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include <atomic>
+#include <memory>
 #include "vm_device.cuh"
 #include "../../include/vmorph.h"
 
@@ -62,6 +63,35 @@ struct Level {
 
 struct Conn { vm_conp l, r; };
 
+// The optimizer's per-level scratch state (Pyramid.h:67-89 minus v): 72 B per pixel and frame + the improving mask.  One
+// arena sized for the largest level is shared by the levels that are optimised one after the other; the levels of a
+// video's direction x level wavefront are in flight together and own theirs.
+struct Arena {
+    DevBuf mean, var, luma, tps_b, ui_b, temp_ref, cross, value, counter, tps_axy, ui_axy, temp_mask, impmask;
+    int level = -1;                       // which level the arena currently describes
+    cudaError_t ensure(size_t px, size_t imp) {
+        cudaError_t e;
+        DevBuf *f2[] = {&mean, &var, &luma, &tps_b, &ui_b, &temp_ref}, *f1[] = {&cross, &value, &counter, &tps_axy, &ui_axy, &temp_mask};
+        for (DevBuf *b : f2) if ((e = b->ensure(8 * px)) != cudaSuccess) return e;
+        for (DevBuf *b : f1) if ((e = b->ensure(4 * px)) != cudaSuccess) return e;
+        return impmask.ensure(4 * imp);
+    }
+};
+
+// One (level, frame) job of the multi-job sweep (vm_sweep_mj.cu), passed to the kernel by value in an array.
+constexpr int MJ_MAX_JOBS = 16;
+struct SweepJob {
+    LevelView L;                          // view of ONE frame: every per-frame pointer starts at the frame's page (page index 0)
+    int flag;                             // temporal term on (morph.cu:1407-1410) / off
+    float max_iter;
+    int gx, gy;                           // tile grid of a launch (morph.cu:1369-1371)
+    int seq, pad;
+    unsigned int *ctrl;                   // per-job control words
+    unsigned int *stamp;                  // per pixel: round in which the pixel last moved
+    float2 *sd, *sdm, *sdv;               // per pixel: accepted step and SSIM-sum deltas of that round
+    float *sdc;
+};
+
 }  // namespace vm
 
 struct vm_pyramid {
@@ -69,9 +99,8 @@ struct vm_pyramid {
     int sm_count = 148;
     std::vector<vm::Level> lv;
     int w0 = 0, h0 = 0, d0 = 0;
-    // optimizer scratch arena, sized for the largest optimised level
-    vm::DevBuf mean, var, luma, tps_b, ui_b, temp_ref, cross, value, counter, tps_axy, ui_axy, temp_mask, impmask;
-    int state_level = -1;                 // which level the arena currently describes
+    vm::Arena shared;                     // optimizer scratch arena, sized for the largest optimised level
+    std::vector<std::unique_ptr<vm::Arena>> own;   // [level]: arenas of the levels a video wavefront keeps in flight together (else null)
     vm::DevBuf stencils;                  // StencilTables on the device
     vm::DevBuf tmp_a, tmp_b, tmp_c;       // transient scratch (splat accumulators, coarse solve, resampler planes)
     vm::DevBuf tmp_a2;                    // splat accumulators of the second (backward) frame chain
@@ -92,11 +121,17 @@ struct vm_morph {
     vm::DevBuf cons_dev;
     vm::DevBuf ctrl;                      // sweep control block
     vm::DevBuf ctrl2;                     // control block of the backward frame chain (runs concurrently with the forward chain)
+    // multi-job sweep (vm_sweep_mj.cu): global + per-job control words, pixel queue, accepted list, job descriptors, per-job scratch
+    vm::DevBuf mj_ctrl, mj_queue, mj_acc, mj_jobs;
+    vm::DevBuf mj_scratch[vm::MJ_MAX_JOBS];
+    bool sort_log = true;                 // collect_log orders a batch of launches like the reference (level, middle, forward, backward)
+    bool no_wavefront = false;            // VMORPH_WAVEFRONT=0
+    int sweep_mode = 0;                   // 0 auto (videos: multi-job kernel, image pairs: tile kernel), 1 tile kernel, 2 multi-job kernel (VMORPH_SWEEP)
     cudaStream_t chain_stream[2] = {nullptr, nullptr};
     cudaEvent_t chain_ev[3] = {nullptr, nullptr, nullptr};
     vm::DevBuf log_dev;                   // per sweep launch: iterations executed, attempted pixel updates (two words per launch)
     // launch table for progress reporting: seq -> (level, frame, w*h, max_iter)
-    struct Seq { int level, frame; double wh; float max_iter; };
+    struct Seq { int level, frame; double wh; float max_iter; int ev; };   // ev: index of the launch's event pair, -1 = shares the previous job's launch
     std::vector<Seq> seqs;                // launches enqueued since the last collect_log (reset by every collecting call)
     double done_iter = 0;                 // morph.cu:1391 progress of the launches already collected
     // morph.h:17-20 progress fields
@@ -121,6 +156,7 @@ struct vm_morph {
 
 namespace vm {
 
+Arena &arena_of(vm_pyramid *p, int level);
 LevelView make_view(vm_pyramid *p, int level);
 LevelView make_frames_view(vm_pyramid *p, int level, int frame0, int nframes);   // pages [frame0, frame0+nframes) as a level of depth nframes
 void free_resample_cache(vm_pyramid *p);
@@ -128,6 +164,13 @@ void free_resample_cache(vm_pyramid *p);
 // kernels (launchers) -- vm_kernels.cu / vm_sweep.cu / vm_render.cu / vm_resample.cu
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
                          unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, int sm_budget, cudaStream_t stream);
+cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_host, int njobs, const KParams &P, const StencilTables *st,
+                              unsigned int *gctrl, unsigned int *queue, unsigned int *acclist, volatile int *run_flag, volatile int *progress,
+                              int sm_count, int sm_budget, cudaStream_t stream);
+size_t sweep_mj_gctrl_words();
+size_t sweep_mj_job_ctrl_words();
+void sweep_mj_reload_hooks();
+cudaError_t sweep_mj_trace(unsigned long long *out8, int reset);
 size_t sweep_ctrl_words(int max_iter_ceil, int ntiles);
 void sweep_reload_hooks();      // re-reads the VMORPH_* experiment hooks from the environment (called by vm_morph_create)
 int sweep_num_tiles(int w, int h);

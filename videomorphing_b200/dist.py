@@ -5,10 +5,12 @@ What shards on this path:
   * the frame-parallel stages of a video (pyramid image levels, render, QuadraticPath) split into contiguous frame
     blocks, no exchange; results are gathered only when one host wants all frames;
   * the optimizer is two sequential frame chains per level (forward / backward from the middle frame,
-    morph.cu:1374-1439).  Exact mode (same arithmetic as one GPU): with 2-3 ranks each chain gets a rank and the ranks swap
-    their halves of `v` once per level; with 4+ ranks the levels of a chain additionally run as a wavefront on different
-    ranks (pipeline_plan / run_pipeline): frame i of level l+1 is handed to the rank that owns level l as soon as it is
-    final -- NCCL send / recv of one `v` page per frame and link, no collective.
+    morph.cu:1374-1439).  Exact mode (same arithmetic as one GPU, bit-identical result): the direction x level WAVEFRONT that
+    vm_morph_run executes on one GPU (frame i of level l needs frame i of level l+1 and frame i -/+ 1 of level l, so the
+    levels work one chain position behind each other and the two directions are independent) is split over the ranks by
+    (direction, contiguous group of levels); every tick each rank runs ONE multi-job launch over its chains and hands the
+    frames it finished to the rank that owns the next finer level of the same direction -- NCCL send / recv of one `v`
+    page per frame and link, stream-ordered, no collective on the path (wavefront_plan / run_wavefront).
 No collective is used unless a stage really exchanges data; timing reductions are scalar (MAX of seconds, SUM of units).
 """
 import datetime
@@ -122,102 +124,98 @@ def quadratic_path_sharded(vectors, max_iter=10000, tol=1e-12, device=0, gather=
 
 
 # ------------------------------------------------------------------------------------------ optimizer, exact mode
-def _optimize_video_two_chains(morph, pyramid, params, device=0):
-    """Morph::calculate_halfway_parametrization (morph.cu:150-168) for a video with the two frame chains of every level on
-    two GPUs (exact mode: the same arithmetic as one GPU, bit-identical result on ranks 0 and 1).
-
-    Every rank holds the whole pyramid (built from the same frames).  Per level: upsample + initialise all frames (cheap,
-    redundant), rank 0 optimises the middle frame and the forward chain, rank 1 the middle frame and the backward chain
-    (the middle frame is deterministic, so both get the same bits), then they swap the `v` pages of their chains -- the
-    only exchange on the path: one frame's vector field per frame and level, handed to the rank that needs it for the
-    next level's prolongation.  Ranks >= 2 own no chain (the chain is sequential) and receive the level by broadcast.
-    With one rank this is the ordinary run (both chains concurrently on two streams)."""
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    n = pyramid.num_levels
-    eng = MorphEngine(morph, pyramid, device)
-    morph.cpu_optimize_level()
-    max_iter = np.float32(params.max_iter)
-    for l in range(n - 2, 0, -1):
-        morph.upsample(l)
-        morph.initialize_level(l)
-        d = pyramid.info(l)["d"]
-        plan = chain_plan(d, world)
-        mid = plan["mid"]
-        if world == 1:
-            morph.optimize_chains(l, float(max_iter), 3)
-        else:
-            chains = (1 if rank == plan["forward"][0] else 0) | (2 if rank == plan["backward"][0] else 0)
-            fwd, bwd = (mid + 1, d), (0, mid)
-            if rank <= 1:
-                morph.optimize_chains(l, float(max_iter), chains)
-                _swap_pages(eng, l, fwd if rank == 0 else bwd, bwd if rank == 0 else fwd, rank ^ 1)
-            if world > 2:
-                t = eng.get_pages(l, 0, d) if rank == 0 else eng.new_pages(l, d)
-                dist.broadcast(t, 0)
-                if rank > 1:
-                    eng.set_pages(l, 0, t)
-                eng.sync()
-        max_iter = np.float32(max_iter / np.float32(params.max_iter_drop_factor))     # float like the reference (morph.cu:163)
-    return morph
-
-
-# ------------------------------------------------------------------------------------------ optimizer, level pipeline
-def pipeline_plan(depths, world):
-    """Exact-mode plan for `world` ranks (direction x level wavefront).
-
-    depths[l] = number of frames of pyramid level l (l = 0 .. n-1; levels 1 .. n-2 are optimised, n-1 is the dense solve).
-    Ranks come in pairs: rank = 2*pair + direction (0 = forward chain mid+1.., 1 = backward chain mid-1..0).
-    Pair 0 owns level 1, pair 1 level 2, ..., the last pair ("coarse") owns every remaining level: it runs them level by
-    level as on two GPUs (pages swapped with its partner per level) and streams the frames of its finest level out one
-    by one.  A pair that owns a single level receives frame i of the coarser level from the pair above (same
-    direction), prolongs + initialises + optimises its own frame i, and hands it on: level l of frame i only needs level
-    l+1 of frame i and level l of frame i -/+ 1, so the levels run as a wavefront behind each other.  A level can only be
-    streamed into when it has the depth of the level above (no temporal in-fill between them); that bounds the number
-    of stages.  Returns {"nstages", "ranks": {rank: {"pair", "dir", "levels", "recv_from", "send_to"}}}; ranks that
-    own nothing are absent."""
+def wavefront_head(depths):
+    """Head level K of the wavefront: the coarsest level whose finer levels all have its depth (no temporal in-fill between
+    them, upsample.cu:297-338); at most 8 stages.  depths[l] = frames of pyramid level l (l = 0 .. n-1)."""
     n = len(depths)
-    nopt = n - 2                                     # optimised levels 1 .. n-2
-    nst = 1
-    while nst < world // 2 and nst < nopt and depths[nst] == depths[nst + 1]:
-        nst += 1                                     # level `nst` may be streamed into from level nst+1
-    if world < 2 or nopt < 1:
-        nst = 1
-    ranks = {}
-    ndir = 2 if world >= 2 else 1
-    for pair in range(nst):
-        levels = [pair + 1] if pair < nst - 1 else list(range(nopt, pair, -1))       # coarse pair: n-2 .. nst
-        for dr in range(ndir):
-            r = 2 * pair + dr
-            ranks[r] = {"pair": pair, "dir": dr, "levels": levels,
-                        "recv_from": (r + 2) if pair < nst - 1 else None,
-                        "send_to": (r - 2) if pair > 0 else None}
-    return {"nstages": nst, "ranks": ranks}
+    K = 1
+    while K + 1 <= n - 2 and depths[K] == depths[K + 1]:
+        K += 1
+    return min(K, 8)
 
 
-def chain_frames(d, direction):
-    """Frames of one chain in processing order, the middle frame first (morph.cu:1374-1439)."""
-    mid = d // 2
-    return [mid] + (list(range(mid + 1, d)) if direction == 0 else list(range(mid - 1, -1, -1)))
+def level_max_iters(max_iter0, drop, n):
+    """_max_iter of every optimised level (morph.cu:131,163): float32 like the reference."""
+    out, mi = {}, np.float32(max_iter0)
+    for l in range(n - 2, 0, -1):
+        out[l] = float(mi)
+        mi = np.float32(mi / np.float32(drop))
+    return out
+
+
+def _group_cost(levels, dims, max_iters):
+    """Relative cost of one tick of a lock-step launch over `levels` (one frame each): the throughput terms add up, the
+    latency terms (rounds of the slowest level) overlap.  Fitted to the 720p measurements (profiles/r2_wavefront.md)."""
+    thr = sum(dims[l][0] * dims[l][1] * min(max_iters[l], 16.0) * 1e-6 for l in levels)
+    lat = max(min(max_iters[l], 50.0) * 16 * 0.02 for l in levels)
+    return thr + lat
+
+
+def wavefront_plan(depths, dims, max_iters, world):
+    """Who runs what.  Chains are (level, direction) for the levels K .. 1; direction 0 = the middle frame and the frames
+    after it, 1 = the frames before it.  Direction 0 goes to the first ceil(world / 2) ranks, direction 1 to the others
+    (one rank: both); within a direction the levels are split into contiguous groups, one per rank, minimising the most
+    expensive group (_group_cost).  Returns {"K", "owner": {(level, dir): rank}, "groups": {rank: (dir, [levels])}}."""
+    K = wavefront_head(depths)
+    levels = list(range(K, 0, -1))
+    g0 = (world + 1) // 2
+    ranks_of = {0: list(range(g0)), 1: list(range(g0, world)) if world > 1 else [0]}
+
+    def split(g):                                   # best contiguous partition of `levels` into at most g groups
+        g = max(1, min(g, len(levels)))
+        best = None
+
+        def rec(start, left, acc):
+            nonlocal best
+            if left == 1:
+                cand = acc + [levels[start:]]
+                cost = max(_group_cost(c, dims, max_iters) for c in cand)
+                if best is None or cost < best[0]:
+                    best = (cost, cand)
+                return
+            for end in range(start + 1, len(levels) - left + 2):
+                rec(end, left - 1, acc + [levels[start:end]])
+        rec(0, g, [])
+        return best[1]
+    owner, groups = {}, {}
+    for dr in (0, 1):
+        rk = ranks_of[dr]
+        parts = split(len(rk))
+        # the finest group goes to the direction's first rank: ranks 0 and ceil(world / 2) end up owning level 1
+        for r, part in zip(rk, reversed(parts)):
+            for l in part:
+                owner[(l, dr)] = r
+            groups.setdefault(r, []).append((dr, part))
+    return {"K": K, "owner": owner, "groups": groups}
 
 
 class MorphEngine:
-    """The operations the level pipeline needs, on a vm.Morph / vm.Pyramid of this rank's GPU."""
+    """The operations the wavefront needs, on a vm.Morph / vm.Pyramid of this rank's GPU."""
 
-    def __init__(self, morph, pyramid, device):
+    def __init__(self, morph, pyramid, device, params=None):
         self.m, self.p, self.device = morph, pyramid, device
         from . import _lib
         self._lib, self.L = _lib, _lib.load()
-        self.depths = [pyramid.info(l)["d"] for l in range(pyramid.num_levels)]
+        n = pyramid.num_levels
+        self.depths = [pyramid.info(l)["d"] for l in range(n)]
+        self.dims = {l: (pyramid.info(l)["w"], pyramid.info(l)["h"]) for l in range(n)}
+        prm = params if params is not None else morph.params
+        self.max_iters = level_max_iters(prm.max_iter, prm.max_iter_drop_factor, n)
 
-    def coarse_solve(self): self.m.cpu_optimize_level()
-    def upsample(self, l): self.m.upsample(l)
-    def initialize(self, l): self.m.initialize_level(l)
-    def optimize_chains(self, l, max_iter, chains): self.m.optimize_chains(l, max_iter, chains)
-    def upsample_frames(self, l, i): self.m.upsample_frames(l, i, 1)
-    def initialize_frames(self, l, i): self.m.initialize_frames(l, i, 1)
-    def init_temp(self, l, i, direction): self.m.initialize_temp(l, i, direction)
-    def optimize_frame(self, l, i, flag, max_iter): return self.m.optimize_frame(l, i, flag, max_iter)
+    def prepare(self):
+        """Everything above the wavefront, redundantly on every rank (deterministic => identical, no exchange): coarse solve,
+        the temporally subsampled levels, head level prolonged + initialised.  Returns the head level K."""
+        return self.m.wavefront_prepare()
+
+    def prep_frame(self, l, i, head, first, tdir):
+        if not head:
+            self.m.upsample_frames(l, i, 1)
+            self.m.initialize_frames(l, i, 1)
+        if not first:
+            self.m.initialize_temp(l, i, tdir)
+
+    def enqueue_jobs(self, jobs): self.m.enqueue_jobs(jobs)
+    def collect(self): self.m.collect()
 
     def _page(self, l):
         base, _ = self.p.dev_ptr(l, "v")
@@ -261,113 +259,82 @@ class MorphEngine:
             torch.cuda.current_stream().synchronize()
 
 
-def _swap_pages(eng, l, mine, theirs, peer):
-    """Send this rank's pages `mine` = (a, b) of level l to `peer` and receive the peer's pages `theirs`."""
-    ops, rt = [], None
-    if mine[1] > mine[0]:
-        ops.append(dist.P2POp(dist.isend, eng.get_pages(l, *mine), peer))
-    if theirs[1] > theirs[0]:
-        rt = eng.new_pages(l, theirs[1] - theirs[0])
-        ops.append(dist.P2POp(dist.irecv, rt, peer))
-    for w in (dist.batch_isend_irecv(ops) if ops else []):
-        w.wait()
-    if rt is not None:
-        eng.set_pages(l, theirs[0], rt)
-    eng.sync()
-
-
-_link_groups = {}
-
-
-def _links(plan, world):
-    """One 2-rank process group per hand-off link (downstream, upstream), created once per plan shape by ALL ranks in the
-    same order.  Separate groups keep a stage's receive from the level above and its send to the level below on
-    independent NCCL communicators / streams (P2P ops on one group are serialised in issue order)."""
-    key = (world, plan["nstages"])
-    if key not in _link_groups:
-        g = {}
-        for r in sorted(plan["ranks"]):
-            to = plan["ranks"][r]["send_to"]
-            if to is not None:
-                g[(to, r)] = dist.new_group([to, r])
-        _link_groups[key] = g
-    return _link_groups[key]
-
-
-def run_pipeline(eng, max_iter0, drop, rank, world):
-    """The level pipeline on one rank (see pipeline_plan).  `eng` is a MorphEngine (or, in the CPU tests, a stand-in with the
-    same methods).  Returns the plan; afterwards ranks 0 and 1 hold the complete level-1 field."""
+def run_wavefront(eng, rank, world):
+    """The direction x level wavefront on this rank (see wavefront_plan).  `eng` is a MorphEngine (or, in the CPU tests, a
+    stand-in with the same methods).  Chain (l, dr) works on position c (frame mid + c forward, mid - c backward) at tick
+    (K - l) + c: the frame of level l + 1 it prolongs and its chain neighbour were finished one tick earlier.  A backward
+    chain whose level's forward chain lives on another rank optimises the middle frame itself (position 0; deterministic
+    => the same bits), so the two directions never exchange anything.  Afterwards EVERY rank holds the whole level-1 field."""
     depths = eng.depths
-    n = len(depths)
-    plan = pipeline_plan(depths, world)
-    links = _links(plan, world) if plan["nstages"] > 1 else {}
-    me = plan["ranks"].get(rank)
-    if me is None:
-        return plan                                                      # this rank owns nothing
-    g_up = links.get((rank, me["recv_from"]))
-    g_down = links.get((me["send_to"], rank))
-    nst, dr = plan["nstages"], me["dir"]
-    partner = rank ^ 1 if world >= 2 else None
-    max_iter, mi = {}, np.float32(max_iter0)
-    for l in range(n - 2, 0, -1):                                        # morph.cu:163, float like the reference
-        max_iter[l] = float(mi)
-        mi = np.float32(mi / np.float32(drop))
+    plan = wavefront_plan(depths, eng.dims, eng.max_iters, world)
+    K, owner = plan["K"], plan["owner"]
+    assert world >= 2 and all(len({dr for dr, _ in g}) == 1 for g in plan["groups"].values())
+    assert eng.prepare() == K
+    d = depths[K]
+    mid = d // 2
+    npos = {0: d - mid, 1: mid + 1}                              # chain positions incl. the middle frame
+    mine = sorted([c for c, r in owner.items() if r == rank], key=lambda c: (-c[0], c[1]))
+
+    def active(l, dr, c):                                        # does chain (l, dr) run position c?  (every rank serves one direction,
+        return 0 <= c < npos[dr]                                 #  so a backward chain always optimises the middle frame itself)
+    frame = lambda dr, c: mid + c if dr == 0 else mid - c
     sends = []
-
-    def stream_level(l, recv_from, send_to, prepared):
-        """One chain of level l frame by frame; `prepared`: the whole level is already prolonged and initialised."""
-        tdir = -1 if dr == 0 else 1                                      # the neighbour the temporal term looks at
-        for i in chain_frames(depths[l], dr):
-            if recv_from is not None:
+    for T in range(K - 1 + max(npos.values())):
+        work = [(l, dr, T - (K - l)) for l, dr in mine if active(l, dr, T - (K - l))]
+        # ---- receive the frames of the next coarser level that another rank finished one tick ago
+        ops, incoming = [], []
+        for l, dr, c in work:
+            if l < K and owner[(l + 1, dr)] != rank:
                 t = eng.new_pages(l + 1)
-                dist.recv(t, recv_from, group=g_up)
-                eng.set_pages(l + 1, i, t)
-            if not prepared:
-                eng.upsample_frames(l, i)
-                eng.initialize_frames(l, i)
-            mid = i == depths[l] // 2
-            if not mid:
-                eng.init_temp(l, i, tdir)
-            eng.optimize_frame(l, i, not mid, max_iter[l])
-            if send_to is not None:
-                t = eng.get_pages(l, i, i + 1)
-                sends.append((t, dist.isend(t, send_to, group=g_down)))
-
-    if me["pair"] == nst - 1:                                            # coarse pair
-        eng.coarse_solve()
-        for l in me["levels"]:
-            eng.upsample(l)
-            eng.initialize(l)
-            d = depths[l]
-            mid = d // 2
-            if l == nst and nst > 1:
-                stream_level(l, None, me["send_to"], True)
-            else:
-                eng.optimize_chains(l, max_iter[l], 3 if partner is None else (1 << dr))
-                if partner is not None and d > 1:
-                    fwd, bwd = (mid + 1, d), (0, mid)
-                    _swap_pages(eng, l, fwd if dr == 0 else bwd, bwd if dr == 0 else fwd, partner)
-    else:
-        stream_level(me["levels"][0], me["recv_from"], me["send_to"], False)
-    for t, w in sends:
-        w.wait()
-    if me["pair"] == 0 and nst > 1 and partner is not None:              # both level-1 owners end with the whole field
-        d = depths[1]
-        mid = d // 2
-        fwd, bwd = (mid + 1, d), (0, mid)
-        _swap_pages(eng, 1, fwd if dr == 0 else bwd, bwd if dr == 0 else fwd, partner)
+                ops.append(dist.P2POp(dist.irecv, t, owner[(l + 1, dr)]))
+                incoming.append((l + 1, frame(dr, c), t))
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        for l1, f, t in incoming:
+            eng.set_pages(l1, f, t)
+        # ---- prolong / initialise / temporal reference, then ONE lock-step launch over this rank's chains
+        jobs = []
+        for l, dr, c in work:
+            first = c == 0
+            eng.prep_frame(l, frame(dr, c), l == K, first, -1 if dr == 0 else 1)
+            jobs.append((l, frame(dr, c), not first, eng.max_iters[l]))
+        if jobs:
+            eng.enqueue_jobs(jobs)
+        # ---- hand the finished frames to the owner of the next finer level of the same direction
+        ops = []
+        for l, dr, c in work:
+            if l > 1 and owner[(l - 1, dr)] != rank and active(l - 1, dr, c):
+                t = eng.get_pages(l, frame(dr, c), frame(dr, c) + 1)
+                ops.append(dist.P2POp(dist.isend, t, owner[(l - 1, dr)]))
+                sends.append(t)
+        sends += (dist.batch_isend_irecv(ops) if ops else [])
+    for w in sends:
+        if hasattr(w, "wait"):
+            w.wait()
+    eng.collect()
+    # ---- every rank gets the whole level-1 field: the two level-1 owners broadcast their halves
+    o0, o1 = owner[(1, 0)], owner[(1, 1)]
+    for src, a, b in ((o0, mid, d), (o1, 0, mid)):
+        if b <= a:
+            continue
+        if world > 1:
+            t = eng.get_pages(1, a, b) if rank == src else eng.new_pages(1, b - a)
+            dist.broadcast(t, src)
+            if rank != src:
+                eng.set_pages(1, a, t)
     eng.sync()
     return plan
 
 
 def optimize_video(morph, pyramid, params, device=0):
     """Morph::calculate_halfway_parametrization (morph.cu:150-168) for a video on 1 .. 8 GPUs, exact mode (the same
-    arithmetic as one GPU; ranks 0 and 1 end with the bit-identical level-1 field).  2-3 ranks: one frame chain per rank.
-    4+ ranks: direction x level pipeline (pipeline_plan).  Every rank holds the whole pyramid, built from the same frames."""
+    arithmetic as one GPU; every rank ends with the bit-identical level-1 field).  One rank: vm_morph_run (the wavefront
+    inside one GPU).  Several ranks: the same wavefront split by direction and level group (run_wavefront).  Every rank
+    holds the whole pyramid, built from the same frames."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
-    depths = [pyramid.info(l)["d"] for l in range(pyramid.num_levels)]
-    if pipeline_plan(depths, world)["nstages"] < 2:
-        return _optimize_video_two_chains(morph, pyramid, params, device)
-    run_pipeline(MorphEngine(morph, pyramid, device), float(params.max_iter), float(params.max_iter_drop_factor), rank, world)
+    if world == 1:
+        morph.run()
+        return morph
+    run_wavefront(MorphEngine(morph, pyramid, device, params), rank, world)
     return morph
