@@ -240,8 +240,8 @@ int vm_qpath_optimize_frames(int device, const float *vectors, float *qpaths, in
 int vm_selftest_exact_arith(int device, uint64_t n_div, uint64_t *mismatches3);
 
 /* Diagnostics of the multi-job sweep kernel (no reference counterpart): clock cycles one CTA spent per phase of the rounds
- * since the last reset -- out8 = compute, barrier after compute, schedule advance + commit gather, filter, barrier after
- * filter, then the number of rounds, queued pixels and accepted moves.  Feeds the phase tables under profiles/. */
+ * since the last reset -- out8 = compute phase of one job group, grid barrier, schedule advance of the other group, its commit
+ * gather + filter, (unused), then the number of compute phases, queued pixels and accepted moves.  Feeds profiles/. */
 int vm_debug_sweep_phases(int device, uint64_t *out8, int reset);
 
 /* device memory helpers for callers that keep inputs resident (bench, multi-frame render) */

@@ -1,4 +1,5 @@
-"""Phase table of the multi-job sweep kernel on the 720p video (frames configurable): cycles of CTA 0 per phase of a round.
+"""Phase table of the multi-job sweep kernel on the 720p video (frames configurable): cycles of CTA 0 per phase of a half-round
+(one job group computes while the other commits + filters; "rounds" counts compute phases).
     python tools/mj_phases.py [--frames 24] [--wavefront 1|0]"""
 import argparse, ctypes as C, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,7 +15,7 @@ def main():
     from videomorphing_b200 import synth
     L = vm._lib.load()
     v0, v1, flows, field = synth.video_pair(args.w, args.h, args.frames, 4001, 4002, 8.0)
-    cons = synth.video_tracks(args.w, args.h, args.frames, 4003, 4002, field, ntracks=4)
+    cons = synth.video_tracks(args.w, args.h, args.frames, 4003, 4002, field, ntracks=4, margin=min(96, args.h // 4))
     pyr = vm.Pyramid(0); pyr.build(v0, v1, flows, voxel_cap=1 << 62)
     m = vm.Morph(vm.Parameters(), pyr); m.set_constraints(*cons)
     m.run()
@@ -22,7 +23,7 @@ def main():
     L.vm_debug_sweep_phases(0, out, 1)
     t = time.perf_counter(); m.run(); dt = time.perf_counter() - t
     L.vm_debug_sweep_phases(0, out, 1)
-    names = ["compute", "barrier_after_compute", "advance_gather", "filter", "barrier_after_filter"]
+    names = ["compute_group_A", "grid_barrier", "advance_group_B", "gather_filter_group_B", "unused"]
     cyc = [int(out[k]) for k in range(5)]
     rounds, queued, accepted = int(out[5]), int(out[6]), int(out[7])
     tot = sum(cyc)

@@ -656,14 +656,14 @@ static int enqueue_jobs(vm_morph *m, const JobSpec *js, int n, cudaStream_t s) {
     if (seq0 + n >= (1 << 22)) { set_error("too many sweep launches in one call"); return VM_ERR_STATE; }
     int rc = grow_log(m, (size_t)seq0 + n); if (rc) return rc;
     const size_t gw = sweep_mj_gctrl_words(), jw = sweep_mj_job_ctrl_words();
-    size_t cand = 0;
+    size_t cand = 8192;                                   // entries per job group (even / odd jobs): its candidates + room for the first speculative read
     for (int k = 0; k < n; k++) cand += (size_t)sweep_num_tiles(p->lv[js[k].level].w, p->lv[js[k].level].h) * 256;
-    bool grow = m->mj_ctrl.bytes < 4 * (gw + MJ_MAX_JOBS * jw) || m->mj_jobs.bytes < sizeof(SweepJob) * MJ_MAX_JOBS || m->mj_queue.bytes < 4 * cand || m->mj_acc.bytes < 4 * cand;
+    bool grow = m->mj_ctrl.bytes < 4 * (gw + MJ_MAX_JOBS * jw) || m->mj_jobs.bytes < sizeof(SweepJob) * MJ_MAX_JOBS || m->mj_queue.bytes < 8 * cand || m->mj_acc.bytes < 8 * cand;
     for (int k = 0; k < n; k++) grow = grow || m->mj_scratch[k].bytes < 32 * (size_t)p->lv[js[k].level].ps;
     if (grow) {
         VM_CUDA(cudaDeviceSynchronize());
         VM_CUDA(m->mj_ctrl.ensure(4 * (gw + MJ_MAX_JOBS * jw))); VM_CUDA(m->mj_jobs.ensure(sizeof(SweepJob) * MJ_MAX_JOBS));
-        VM_CUDA(m->mj_queue.ensure(4 * cand + 4096)); VM_CUDA(m->mj_acc.ensure(4 * cand + 4096));
+        VM_CUDA(m->mj_queue.ensure(8 * cand)); VM_CUDA(m->mj_acc.ensure(8 * cand));
         for (int k = 0; k < n; k++) VM_CUDA(m->mj_scratch[k].ensure(32 * (size_t)p->lv[js[k].level].ps));
     }
     if (seq0 == 0) {                                      // time origin of this call's launch intervals
@@ -693,7 +693,7 @@ static int enqueue_jobs(vm_morph *m, const JobSpec *js, int n, cudaStream_t s) {
     while (m->ev.size() < 2 * (size_t)(seq0 + 1)) { cudaEvent_t e; VM_CUDA(cudaEventCreate(&e)); m->ev.push_back(e); }
     VM_CUDA(cudaEventRecord(m->ev[2 * seq0], s));
     VM_CUDA(launch_sweep_jobs(m->mj_jobs.as<SweepJob>(), host, n, kparams(m->prm), p->stencils.as<StencilTables>(), ctrl, m->mj_queue.as<unsigned>(),
-                              m->mj_acc.as<unsigned>(), m->run_flag_dev, m->progress_dev, p->sm_count, 0, s));
+                              m->mj_acc.as<unsigned>(), (unsigned)cand, m->run_flag_dev, m->progress_dev, p->sm_count, 0, s));
     VM_CUDA(cudaEventRecord(m->ev[2 * seq0 + 1], s));
     // per job: iterations -> log[2 seq], attempted updates -> log[2 seq + 1] (control words 0 and 2 of the job)
     for (int k = 0; k < n; k++) {

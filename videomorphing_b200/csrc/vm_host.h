@@ -165,8 +165,8 @@ void free_resample_cache(vm_pyramid *p);
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,
                          unsigned int *ctrl, volatile int *run_flag, volatile int *progress, int seq, int sm_count, int sm_budget, cudaStream_t stream);
 cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_host, int njobs, const KParams &P, const StencilTables *st,
-                              unsigned int *gctrl, unsigned int *queue, unsigned int *acclist, volatile int *run_flag, volatile int *progress,
-                              int sm_count, int sm_budget, cudaStream_t stream);
+                              unsigned int *gctrl, unsigned int *queue, unsigned int *acclist, unsigned int qcap /* entries per job group */,
+                              volatile int *run_flag, volatile int *progress, int sm_count, int sm_budget, cudaStream_t stream);
 size_t sweep_mj_gctrl_words();
 size_t sweep_mj_job_ctrl_words();
 void sweep_mj_reload_hooks();

@@ -123,6 +123,22 @@ struct PixelEval {
             out[k] = (w_ui * v_ui + w_ssim * term[k] + w_temp * v_temp * tmask * factor_d) * inv_wh + w_tps * v_tps;
         }
     }
+    // L1 prefetch of the texels a line search along `grad` over [0, c] can touch: lane l covers the sample at t = c l / 31
+    // (samples < 1/3 px apart) in image 0 (p - v - t grad) and image 1 (p + v + t grad), two texel rows each.
+    __device__ __forceinline__ void prefetch_segment(float2 grad, float c) const {
+        const float t = c * (float)lane * (1.0f / 31.0f);
+        const float dx = v.x + grad.x * t, dy = v.y + grad.y * t;
+#pragma unroll
+        for (int img = 0; img < 2; img++) {
+            const float x = (float)px + (img ? dx : -dx), y = (float)py + (img ? dy : -dy);
+            const int i0 = min(max((int)floorf(x), 0), W - 1), j0 = min(max((int)floorf(y), 0), H - 1), j1 = min(j0 + 1, H - 1), i1 = min(i0 + 1, W - 1);
+            const float *base = img ? I1 : I0;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(base + j0 * W + i0));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(base + j1 * W + i0));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(base + j0 * W + i1));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(base + j1 * W + i1));
+        }
+    }
     __device__ __forceinline__ float energy(float2 d) const {
         const float2 dd[1] = {d}; float o[1];
         energy_n<1>(dd, o);
@@ -179,7 +195,10 @@ __device__ __forceinline__ void fover_ring(int SIGN, int px, int py, const float
 #define TR_ARG
 #define TR_PASS
 #endif
-template <bool LAT>
+// PF (multi-job kernel: the pixels of a warp come from anywhere, nothing of the images is in L1): once the search direction
+// and the bracket [0, c] are known, the lanes prefetch the cache lines of both images along the search segment into L1, so
+// the ~15 dependent bilinear fetches of the line search hit L1 instead of paying an L2 round trip each.
+template <bool LAT, bool PF = false>
 __device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float eps, const float2 *nb, unsigned inb, bool spec, float2 &d_out TR_ARG) {
     float2 g;
     if (LAT) {
@@ -216,6 +235,7 @@ __device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float ep
         }
     }
     float c = maxf_std(t_min - eps, 0.0f);
+    if (PF) E.prefetch_segment(grad, c);
     TR(10);
     // golden_section_search, morph.cu:885-947
     const float R = 0.618033989f, C = 1.0f - R;

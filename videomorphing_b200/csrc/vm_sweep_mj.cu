@@ -33,7 +33,7 @@ constexpr int MJ_NW = 16;                        // warps per CTA (128 registers
 constexpr unsigned MJ_LOCKED = 1u << 26;         // queue entry: pixel has a mask index but is locked by the boundary condition
 constexpr unsigned MJ_PIX = (1u << 26) - 1u;     // queue entry: y * rowstride + x
 // global control words
-enum { GC_BAR = 0, GC_QN = 2, GC_PULL = 4, GC_ACC = 6, GC_WORDS = 16 };
+enum { GC_BAR = 0, GC_QN = 2, GC_PULL = 6, GC_ACC = 10, GC_WORDS = 16 };   // QN / PULL / ACC: [group * 2 + round parity]
 // per-job control words: iterations (out), cancelled (out), attempted updates (out), 4 iteration flag words (ring)
 enum { JC_ITERS = 0, JC_CANCELLED = 1, JC_UPDATES = 2, JC_FLAGS = 4, JC_WORDS = 8 };
 
@@ -49,7 +49,7 @@ struct MjShared {
     unsigned int iomask[25];
     unsigned int improv[25 * 9];
     unsigned int wmask[MJ_NW][MASK_W * MASK_H];  // per warp: improving-mask words around the tile being filtered
-    int any_live;
+    int glive[2];                                // group g (jobs with index % 2 == g) still has a live job
 };
 
 __device__ __forceinline__ bool step_empty(const LevelView &L, int step) {
@@ -62,7 +62,7 @@ __device__ __forceinline__ bool step_empty(const LevelView &L, int step) {
 // once into the warp's shared-memory scratch; a tile whose words are all clear has no candidate (most tiles of a fine
 // level after the first iterations) and costs one L2 round trip; otherwise the 256 pixels of the colour are tested from
 // shared memory and the hits are appended to the global queue with ONE atomic per tile, in slot order.
-__device__ __forceinline__ void mj_filter_tile(MjShared &S, int j, int t, const KParams &P, unsigned int *gctrl, unsigned int *queue, unsigned par,
+__device__ __forceinline__ void mj_filter_tile(MjShared &S, int j, int t, const KParams &P, unsigned int *qcount, unsigned int *queue,
                                                unsigned int *wm /* MASK_W * MASK_H words of this warp */, int lane) {
     const SweepJob &J = S.job[j];
     const LevelView &L = J.L;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void mj_filter_tile(MjShared &S, int j, int t, const 
     if (!total) return;
     unsigned base = 0;
     if (lane == 0) {
-        base = atomicAdd(&gctrl[GC_QN + par], (unsigned)total);
+        base = atomicAdd(qcount, (unsigned)total);
         if (nact) atomicAdd(&J.ctrl[JC_UPDATES], (unsigned)nact);         // attempted pixel updates (FP32-roofline unit)
     }
     base = __shfl_sync(0xffffffffu, base, 0);
@@ -128,19 +128,21 @@ __device__ __forceinline__ void mj_filter_tile(MjShared &S, int j, int t, const 
     }
 }
 
-__device__ __forceinline__ void mj_filter_all(MjShared &S, int njobs, const KParams &P, unsigned int *gctrl, unsigned int *queue, unsigned par,
+__device__ __forceinline__ void mj_filter_all(MjShared &S, int njobs, int g, const KParams &P, unsigned int *qcount, unsigned int *queue,
                                               unsigned gwarp, unsigned nwarps, int warp, int lane) {
     int total = 0;
-    for (int j = 0; j < njobs; j++) if (S.live[j]) total += S.job[j].gx * S.job[j].gy;
-    for (int wt = (int)gwarp; wt < total; wt += (int)nwarps) {
-        int j = 0, t = wt;
-        for (; j < njobs; j++) {
+    for (int j = g; j < njobs; j += 2) if (S.live[j]) total += S.job[j].gx * S.job[j].gy;
+    // (dealt from the last warp of the grid backwards: the commit gather of the previous round, dealt from the first warp
+    //  forwards, runs next to it on other warps)
+    for (int wt = (int)(nwarps - 1u - gwarp); wt < total; wt += (int)nwarps) {
+        int j = g, t = wt;
+        for (; j < njobs; j += 2) {
             if (!S.live[j]) continue;
             const int nt = S.job[j].gx * S.job[j].gy;
             if (t < nt) break;
             t -= nt;
         }
-        mj_filter_tile(S, j, t, P, gctrl, queue, par, S.wmask[warp], lane);
+        mj_filter_tile(S, j, t, P, qcount, queue, S.wmask[warp], lane);
     }
 }
 
@@ -213,14 +215,120 @@ __device__ __forceinline__ void mj_gather(const MjShared &S, const KParams &P, u
     if (ch_t) L.tps_b[c] = tb;
 }
 
+// One active pixel of the queue: the per-pixel step of morph.cu:1030-1083 by one warp, the commit of the pixel's own cells
+// and the deltas for the gather.
+__device__ __forceinline__ void mj_pixel(MjShared &S, const KParams &P, unsigned entry, unsigned rid, bool spec, unsigned int *acc_count,
+                                         unsigned int *acclist, int lane) {
+    const int j = (int)(entry >> 27);
+    const SweepJob &J = S.job[j];
+    const LevelView &L = J.L;
+    const int pix = (int)(entry & MJ_PIX);
+    const int py = pix / L.rs, px = pix - py * L.rs;
+    const int bcx = px / 5, bcy = py / 5;
+    unsigned int *mword = L.impmask + (bcy + 1) * L.irs + (bcx + 1);
+    const unsigned mbit = 1u << ((px - bcx * 5) + (py - bcy * 5) * 5);
+    bool ok = false;
+    if (!(entry & MJ_LOCKED)) {
+        PixelEval E;
+        E.I0 = L.img0; E.I1 = L.img1; E.W = L.w; E.H = L.h; E.px = px; E.py = py; E.lane = lane;
+        E.v = __ldcg(L.v + pix); E.old_luma = __ldcg(L.luma + pix);
+        E.tps_axy = __ldcg(L.tps_axy + pix); E.ui_axy = __ldcg(L.ui_axy + pix);
+        E.ui_b = __ldcg(L.ui_b + pix);
+        E.tps_b = __ldcg(L.tps_b + pix);
+        E.flag = J.flag != 0;
+        E.tref = make_float2(0.f, 0.f); E.tmask = 0.f;
+        if (E.flag) { E.tref = __ldcg(L.temp_ref + pix); E.tmask = __ldcg(L.temp_mask + pix); }
+        E.w_ui = P.w_ui; E.w_tps = P.w_tps; E.w_ssim = P.w_ssim; E.w_temp = P.w_temp; E.ssim_clamp = P.ssim_clamp;
+        E.inv_wh = L.inv_wh; E.factor_d = L.factor_d;
+        const int B = border_class(py, L.h) * 5 + border_class(px, L.w);
+        E.w_valid = false; E.w_mean = E.w_var = make_float2(0.f, 0.f); E.w_cross = E.w_value = 0.f; E.w_cnt = 0.f;
+        if (lane < 25) {
+            const int wi = lane / 5, wj = lane - wi * 5;
+            if ((S.iomask[B] >> lane) & 1u) {
+                const int c = (py + wi - 2) * L.rs + (px + wj - 2);
+                E.w_valid = true;
+                E.w_mean = __ldcg(L.mean + c); E.w_var = __ldcg(L.var + c); E.w_cross = __ldcg(L.cross + c);
+                E.w_value = __ldcg(L.value + c); E.w_cnt = __ldcg(L.counter + c);
+            }
+        }
+        // neighbour vectors for the fold-over test (morph.cu:788-789)
+        float2 nb[8]; unsigned inb = 0;
+        {
+            const int OX[8] = {-1, 0, 1, 1, 1, 0, -1, -1}, OY[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int nx = px + OX[k], ny = py + OY[k];
+                nb[k] = make_float2(0.f, 0.f);
+                if (nx >= 0 && nx < L.w && ny >= 0 && ny < L.h) { inb |= 1u << k; nb[k] = __ldcg(L.v + ny * L.rs + nx); }
+            }
+        }
+        float2 d;
+        ok = optimize_pixel_warp<true, true>(E, P.eps, nb, inb, spec, d);
+        if (ok) {
+            // commit of the pixel's own cells (morph.cu:951-971,1017-1025,1320-1327) + the deltas for the gather
+            const float2 newv = make_float2(E.v.x + d.x, E.v.y + d.y);
+            float2 luma;
+            luma.x = tex2d<true>(L.img0, L.w, L.h, (float)px - newv.x + 0.5f, (float)py - newv.y + 0.5f);
+            luma.y = tex2d<true>(L.img1, L.w, L.h, (float)px + newv.x + 0.5f, (float)py + newv.y + 0.5f);
+            if (lane == 0) {
+                J.sdm[pix] = make_float2(luma.x - E.old_luma.x, luma.y - E.old_luma.y);
+                J.sdv[pix] = make_float2(luma.x * luma.x - E.old_luma.x * E.old_luma.x, luma.y * luma.y - E.old_luma.y * E.old_luma.y);
+                J.sdc[pix] = luma.x * luma.y - E.old_luma.x * E.old_luma.y;
+                J.sd[pix] = d;
+                J.stamp[pix] = rid;
+                L.luma[pix] = luma;
+                float2 ub = E.ui_b;
+                ub.x += 2 * d.x * E.ui_axy; ub.y += 2 * d.y * E.ui_axy;
+                L.ui_b[pix] = ub;
+                L.v[pix] = newv;
+                acclist[atomicAdd(acc_count, 1u)] = entry;
+                atomicOr(mword, mbit);
+                if (!S.voted[j]) { S.voted[j] = 1; atomicOr(&J.ctrl[JC_FLAGS + (S.iter[j] & 3)], 1u); }
+            }
+        }
+    }
+    if (!ok && lane == 0) atomicAnd(mword, ~mbit);                       // had a mask index, did not move (morph.cu:1328-1332)
+}
+
+// End of a round of job j: next colour / offset step / iteration (morph.cu:1305-1309, 1382-1390); every CTA computes the same.
+__device__ __forceinline__ void mj_advance(MjShared &S, int j, volatile int *progress) {
+    int sp = S.sp[j] + 1, step = S.step[j], iter = S.iter[j];
+    if (sp == 4) {
+        sp = 0;
+        do { step++; } while (step < 4 && step_empty(S.job[j].L, step));
+        if (step >= 4) {                                                // end of an iteration (morph.cu:1386-1390)
+            const unsigned f = __ldcg(&S.job[j].ctrl[JC_FLAGS + (iter & 3)]);
+            iter++;
+            const bool go = ((float)iter < S.job[j].max_iter) && (f & 1u) && !(f & 2u);
+            if (blockIdx.x == 0) {
+                S.job[j].ctrl[JC_FLAGS + ((iter + 1) & 3)] = 0u;        // the flag word of the iteration after the next
+                if (!go) { S.job[j].ctrl[JC_ITERS] = (unsigned)iter; S.job[j].ctrl[JC_CANCELLED] = (f & 2u) ? 1u : 0u; }
+                if (progress && j == 0) { progress[1] = iter; progress[0] = S.job[j].seq; }
+            }
+            if (!go) S.live[j] = 0;
+            step = 0;
+            while (step < 4 && step_empty(S.job[j].L, step)) step++;
+            S.voted[j] = 0;
+        }
+    }
+    S.sp[j] = sp; S.step[j] = step; S.iter[j] = iter;
+}
+
+// The jobs form two groups (even / odd index) whose rounds are half a round apart: while group A computes round r, the
+// warps that have no pixel of A (most of them, in the sparse rounds that dominate) commit round r-1 of group B and filter
+// its round r.  Every job still sees queue -> barrier -> compute -> barrier -> gather + filter -> barrier ..., but each
+// grid barrier now ends a compute phase of one group AND a gather / filter phase of the other, and the latency chains
+// of the two kinds of phase (both a handful of dependent L2 round trips) overlap instead of adding up.
 __global__ void __launch_bounds__(MJ_NW * 32, 1)
 k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const StencilTables *__restrict__ st, unsigned int *gctrl,
-           unsigned int *queue, unsigned int *acclist, volatile int *run_flag, volatile int *progress) {
+           unsigned int *queue, unsigned int *acclist, unsigned int qcap, volatile int *run_flag, volatile int *progress) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MjShared &S = *reinterpret_cast<MjShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
-    const unsigned nwarps = gridDim.x * MJ_NW, gwarp = blockIdx.x * MJ_NW + warp;
+    const unsigned gtid = blockIdx.x * blockDim.x + tid;
+    // warp numbering across the grid is CTA-minor: work item k goes to warp k / #CTAs of CTA k % #CTAs, so a round with few
+    // active pixels spreads them over all SMs (one busy warp per SM runs at latency speed; sixteen on one SM share its issue slots)
+    const unsigned nwarps = gridDim.x * MJ_NW, gwarp = warp * gridDim.x + blockIdx.x;
     for (int k = tid; k < 625; k += MJ_NW * 32) S.tps[k] = (&st->tps[0][0])[k];
     if (tid < 25) S.iomask[tid] = st->iomask[tid];
     for (int k = tid; k < 225; k += MJ_NW * 32) S.improv[k] = (&st->improv[0][0])[k];
@@ -235,146 +343,73 @@ k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const Stenci
         while (s0 < 4 && step_empty(S.job[tid].L, s0)) s0++;            // step 0 (offset 0,0) is never empty
         S.iter[tid] = 0; S.step[tid] = s0; S.sp[tid] = 0; S.live[tid] = 1; S.voted[tid] = 0;
     }
+    if (tid == 0) { S.glive[0] = 1; S.glive[1] = njobs > 1 ? 1 : 0; }
     __syncthreads();
-    unsigned int epoch = 0, round = 0;
+    unsigned int epoch = 0, rnd[2] = {0u, 0u};
+    bool started1 = false;                                               // group 1 has had its first filter
     const bool tracer = gtid == 0;
     long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
 #define MJ_TR(k) do { if (tracer) { t1 = clock64(); tr[k] += t1 - t0; t0 = t1; } } while (0)
-    // ---- filter of round 0
-    mj_filter_all(S, njobs, P, gctrl, queue, 0u, gwarp, nwarps, warp, lane);
+    // ---- filter of round 0 of group 0
+    mj_filter_all(S, njobs, 0, P, &gctrl[GC_QN + 0], queue, gwarp, nwarps, warp, lane);
     grid_barrier(&gctrl[GC_BAR], epoch, gridDim.x);
-    while (true) {
-        const unsigned par = round & 1u, rid = round + 1u;
-        // =============== compute: the warps of the grid pull active pixels of all jobs from the queue ===============
-        const unsigned qn = __ldcg(&gctrl[GC_QN + par]);
-        if (gtid == 0) {
-            gctrl[GC_QN + (par ^ 1u)] = 0u; gctrl[GC_PULL + (par ^ 1u)] = 0u;                 // next round's queue
-            if (run_flag && *run_flag == 0)
-                for (int j = 0; j < njobs; j++) if (S.live[j]) atomicOr(&S.job[j].ctrl[JC_FLAGS + (S.iter[j] & 3)], 2u);   // morph.cu:1390 (m_cb)
-        }
-        // speculative line search only while most warps would otherwise idle (uniform over the grid; results do not depend on it)
-        const bool spec = qn * 16u <= 6u * nwarps;
-        if (tracer) { tr[5] += 1; tr[6] += qn; t0 = clock64(); }
-        unsigned e = gwarp;
-        while (e < qn) {
-            unsigned e_next = 0;                                          // requested now, needed when this pixel is done
-            if (lane == 0) e_next = nwarps + atomicAdd(&gctrl[GC_PULL + par], 1u);
-            const unsigned entry = __ldcg(queue + e);
-            const int j = (int)(entry >> 27);
-            const SweepJob &J = S.job[j];
-            const LevelView &L = J.L;
-            const int pix = (int)(entry & MJ_PIX);
-            const int py = pix / L.rs, px = pix - py * L.rs;
-            const int bcx = px / 5, bcy = py / 5;
-            unsigned int *mword = L.impmask + (bcy + 1) * L.irs + (bcx + 1);
-            const unsigned mbit = 1u << ((px - bcx * 5) + (py - bcy * 5) * 5);
-            bool ok = false;
-            if (!(entry & MJ_LOCKED)) {
-                PixelEval E;
-                E.I0 = L.img0; E.I1 = L.img1; E.W = L.w; E.H = L.h; E.px = px; E.py = py; E.lane = lane;
-                E.v = __ldcg(L.v + pix); E.old_luma = __ldcg(L.luma + pix);
-                E.tps_axy = __ldcg(L.tps_axy + pix); E.ui_axy = __ldcg(L.ui_axy + pix);
-                E.ui_b = __ldcg(L.ui_b + pix);
-                E.tps_b = __ldcg(L.tps_b + pix);
-                E.flag = J.flag != 0;
-                E.tref = make_float2(0.f, 0.f); E.tmask = 0.f;
-                if (E.flag) { E.tref = __ldcg(L.temp_ref + pix); E.tmask = __ldcg(L.temp_mask + pix); }
-                E.w_ui = P.w_ui; E.w_tps = P.w_tps; E.w_ssim = P.w_ssim; E.w_temp = P.w_temp; E.ssim_clamp = P.ssim_clamp;
-                E.inv_wh = L.inv_wh; E.factor_d = L.factor_d;
-                const int B = border_class(py, L.h) * 5 + border_class(px, L.w);
-                E.w_valid = false; E.w_mean = E.w_var = make_float2(0.f, 0.f); E.w_cross = E.w_value = 0.f; E.w_cnt = 0.f;
-                if (lane < 25) {
-                    const int wi = lane / 5, wj = lane - wi * 5;
-                    if ((S.iomask[B] >> lane) & 1u) {
-                        const int c = (py + wi - 2) * L.rs + (px + wj - 2);
-                        E.w_valid = true;
-                        E.w_mean = __ldcg(L.mean + c); E.w_var = __ldcg(L.var + c); E.w_cross = __ldcg(L.cross + c);
-                        E.w_value = __ldcg(L.value + c); E.w_cnt = __ldcg(L.counter + c);
-                    }
-                }
-                // neighbour vectors for the fold-over test (morph.cu:788-789)
-                float2 nb[8]; unsigned inb = 0;
-                {
-                    const int OX[8] = {-1, 0, 1, 1, 1, 0, -1, -1}, OY[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int nx = px + OX[k], ny = py + OY[k];
-                        nb[k] = make_float2(0.f, 0.f);
-                        if (nx >= 0 && nx < L.w && ny >= 0 && ny < L.h) { inb |= 1u << k; nb[k] = __ldcg(L.v + ny * L.rs + nx); }
-                    }
-                }
-                float2 d;
-                ok = optimize_pixel_warp<true>(E, P.eps, nb, inb, spec, d);
-                if (ok) {
-                    // commit of the pixel's own cells (morph.cu:951-971,1017-1025,1320-1327) + the deltas for the gather
-                    const float2 newv = make_float2(E.v.x + d.x, E.v.y + d.y);
-                    float2 luma;
-                    luma.x = tex2d<true>(L.img0, L.w, L.h, (float)px - newv.x + 0.5f, (float)py - newv.y + 0.5f);
-                    luma.y = tex2d<true>(L.img1, L.w, L.h, (float)px + newv.x + 0.5f, (float)py + newv.y + 0.5f);
-                    if (lane == 0) {
-                        J.sdm[pix] = make_float2(luma.x - E.old_luma.x, luma.y - E.old_luma.y);
-                        J.sdv[pix] = make_float2(luma.x * luma.x - E.old_luma.x * E.old_luma.x, luma.y * luma.y - E.old_luma.y * E.old_luma.y);
-                        J.sdc[pix] = luma.x * luma.y - E.old_luma.x * E.old_luma.y;
-                        J.sd[pix] = d;
-                        J.stamp[pix] = rid;
-                        L.luma[pix] = luma;
-                        float2 ub = E.ui_b;
-                        ub.x += 2 * d.x * E.ui_axy; ub.y += 2 * d.y * E.ui_axy;
-                        L.ui_b[pix] = ub;
-                        L.v[pix] = newv;
-                        acclist[atomicAdd(&gctrl[GC_ACC + par], 1u)] = entry;
-                        atomicOr(mword, mbit);
-                        if (!S.voted[j]) { S.voted[j] = 1; atomicOr(&J.ctrl[JC_FLAGS + (S.iter[j] & 3)], 1u); }
-                    }
-                }
-            }
-            if (!ok && lane == 0) atomicAnd(mword, ~mbit);               // had a mask index, did not move (morph.cu:1328-1332)
-            e = __shfl_sync(0xffffffffu, e_next, 0);
+    for (unsigned h = 0;; h++) {
+        const int A = (int)(h & 1u), B = A ^ 1;
+        const int liveA = S.glive[A], wasB = S.glive[B];
+        const bool gfB = wasB && (B == 0 || started1);                   // group B has a computed round to commit
+        // ---- schedule of group B moves on (needs the votes of its last compute phase, which ended at the previous barrier)
+        if (gfB && tid < njobs && (tid & 1) == B && S.live[tid]) mj_advance(S, tid, progress);
+        __syncthreads();
+        if (tid == 0) {
+            int l0 = 0, l1 = 0;
+            for (int j = 0; j < njobs; j++) if (S.live[j]) { if (j & 1) l1 = 1; else l0 = 1; }
+            S.glive[0] = l0; S.glive[1] = l1;
         }
         __syncthreads();
-        MJ_TR(0);
-        grid_barrier(&gctrl[GC_BAR], epoch, gridDim.x);
-        MJ_TR(1);
-        // =============== advance the jobs' schedules (every CTA computes the same), gather, filter of the next round ===============
-        if (tid < njobs && S.live[tid]) {
-            const int j = tid;
-            int sp = S.sp[j] + 1, step = S.step[j], iter = S.iter[j];
-            if (sp == 4) {
-                sp = 0;
-                do { step++; } while (step < 4 && step_empty(S.job[j].L, step));
-                if (step >= 4) {                                        // end of an iteration (morph.cu:1386-1390)
-                    const unsigned f = __ldcg(&S.job[j].ctrl[JC_FLAGS + (iter & 3)]);
-                    iter++;
-                    const bool go = ((float)iter < S.job[j].max_iter) && (f & 1u) && !(f & 2u);
-                    if (blockIdx.x == 0) {
-                        S.job[j].ctrl[JC_FLAGS + ((iter + 1) & 3)] = 0u;                // the flag word of the iteration after the next
-                        if (!go) { S.job[j].ctrl[JC_ITERS] = (unsigned)iter; S.job[j].ctrl[JC_CANCELLED] = (f & 2u) ? 1u : 0u; }
-                        if (progress && j == 0) { progress[1] = iter; progress[0] = S.job[j].seq; }
-                    }
-                    if (!go) S.live[j] = 0;
-                    step = 0;
-                    while (step < 4 && step_empty(S.job[j].L, step)) step++;
-                    S.voted[j] = 0;
-                }
-            }
-            S.sp[j] = sp; S.step[j] = step; S.iter[j] = iter;
-        }
-        if (tid == 0) S.any_live = 0;
-        __syncthreads();
-        if (tid < njobs && S.live[tid]) S.any_live = 1;
-        const unsigned nacc = __ldcg(&gctrl[GC_ACC + par]);
-        if (gtid == 0) gctrl[GC_ACC + (par ^ 1u)] = 0u;
-        for (unsigned a = gwarp; a < nacc; a += nwarps) mj_gather(S, P, __ldcg(acclist + a), rid, lane);
-        __syncthreads();
-        if (tracer) tr[7] += nacc;
         MJ_TR(2);
-        if (!S.any_live) break;
-        mj_filter_all(S, njobs, P, gctrl, queue, par ^ 1u, gwarp, nwarps, warp, lane);
-        round++;
+        // =============== group A: compute -- the warps of the grid pull its active pixels from the queue ===============
+        if (liveA) {
+            const unsigned par = rnd[A] & 1u, rid = rnd[A] + 1u;
+            const unsigned *qA = queue + (size_t)A * qcap;
+            unsigned e = gwarp;
+            unsigned entry = __ldcg(qA + e);                             // requested together with the count (unused if e >= qn)
+            const unsigned qn = __ldcg(&gctrl[GC_QN + A * 2 + par]);
+            if (gtid == 0) {
+                gctrl[GC_QN + A * 2 + (par ^ 1u)] = 0u; gctrl[GC_PULL + A * 2 + (par ^ 1u)] = 0u;   // next round's queue of the group
+                if (run_flag && *run_flag == 0)
+                    for (int j = A; j < njobs; j += 2) if (S.live[j]) atomicOr(&S.job[j].ctrl[JC_FLAGS + (S.iter[j] & 3)], 2u);   // morph.cu:1390 (m_cb)
+            }
+            // speculative line search only while most warps would otherwise idle (uniform over the grid; results do not depend on it)
+            const bool spec = qn * 16u <= 6u * nwarps;
+            if (tracer) { tr[5] += 1; tr[6] += qn; }
+            while (e < qn) {
+                unsigned e_next = 0;                                      // requested now, needed when this pixel is done
+                if (lane == 0) e_next = nwarps + atomicAdd(&gctrl[GC_PULL + A * 2 + par], 1u);
+                mj_pixel(S, P, entry, rid, spec, &gctrl[GC_ACC + A * 2 + par], acclist + (size_t)A * qcap, lane);
+                e = __shfl_sync(0xffffffffu, e_next, 0);
+                if (e < qn) entry = __ldcg(qA + e);
+            }
+            rnd[A]++;
+        }
+        MJ_TR(0);
+        // =============== group B: commit of its last round (gather) and filter of its next one ===============
+        if (gfB) {
+            const unsigned par = (rnd[B] - 1u) & 1u, rid = rnd[B];       // rnd[B] was incremented after its compute phase
+            const unsigned nacc = __ldcg(&gctrl[GC_ACC + B * 2 + par]);
+            if (gtid == 0) gctrl[GC_ACC + B * 2 + (par ^ 1u)] = 0u;
+            const unsigned *aB = acclist + (size_t)B * qcap;
+            for (unsigned a = gwarp; a < nacc; a += nwarps) mj_gather(S, P, __ldcg(aB + a), rid, lane);
+            if (tracer) tr[7] += nacc;
+            if (S.glive[B]) mj_filter_all(S, njobs, B, P, &gctrl[GC_QN + B * 2 + (par ^ 1u)], queue + (size_t)B * qcap, gwarp, nwarps, warp, lane);
+        } else if (B == 1 && !started1 && wasB) {
+            mj_filter_all(S, njobs, 1, P, &gctrl[GC_QN + 2 + 0], queue + (size_t)qcap, gwarp, nwarps, warp, lane);
+        }
+        if (B == 1) started1 = true;
         __syncthreads();
         MJ_TR(3);
+        if (!S.glive[0] && !S.glive[1]) break;
         grid_barrier(&gctrl[GC_BAR], epoch, gridDim.x);
-        MJ_TR(4);
+        MJ_TR(1);
     }
     if (tracer) for (int k = 0; k < 8; k++) atomicAdd(&g_mj_trace[k], (unsigned long long)tr[k]);
 }
@@ -401,7 +436,7 @@ size_t sweep_mj_gctrl_words() { return GC_WORDS; }
 size_t sweep_mj_job_ctrl_words() { return JC_WORDS; }
 
 cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_host, int njobs, const KParams &P, const StencilTables *st,
-                              unsigned int *gctrl, unsigned int *queue, unsigned int *acclist, volatile int *run_flag, volatile int *progress,
+                              unsigned int *gctrl, unsigned int *queue, unsigned int *acclist, unsigned int qcap, volatile int *run_flag, volatile int *progress,
                               int sm_count, int sm_budget, cudaStream_t stream) {
     if (njobs < 1 || njobs > MJ_MAX_JOBS) return cudaErrorInvalidValue;
     int device = 0;
@@ -430,7 +465,7 @@ cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_hos
     long long want = (cands + div - 1) / div;
     int grid = (int)(want < 4 ? 4 : want);
     if (grid > sm_budget * per_sm) grid = sm_budget * per_sm;
-    void *args[] = {(void *)&jobs_dev, (void *)&njobs, (void *)&P, (void *)&st, (void *)&gctrl, (void *)&queue, (void *)&acclist, (void *)&run_flag, (void *)&progress};
+    void *args[] = {(void *)&jobs_dev, (void *)&njobs, (void *)&P, (void *)&st, (void *)&gctrl, (void *)&queue, (void *)&acclist, (void *)&qcap, (void *)&run_flag, (void *)&progress};
     count_launch();
     return cudaLaunchCooperativeKernel((const void *)k_sweep_mj, dim3(grid), dim3(MJ_NW * 32), args, sizeof(MjShared), stream);
 }
