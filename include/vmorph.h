@@ -102,7 +102,11 @@ void vm_pyramid_destroy(vm_pyramid *p);
 /* pyramid.cu:219-236,463-477: level sizes only.  whd_out: 3 ints per level; returns #levels (<= max_levels)
  * or a negative status.  voxel_cap = 14000000 reproduces the reference (pyramid.cu:8). Pure host arithmetic. */
 int vm_level_schedule(int w, int h, int d, int start_res, int64_t voxel_cap, int max_levels, int32_t *whd_out, float *factor_d_out);
-/* Allocates all levels for w x h x d input (no image data yet). */
+/* Allocates all levels for w x h x d input (no image data yet).  A video whose full optimizer state would not fit (72 B per
+ * pixel and frame: 143 GB for 3840x2160 x 240) keeps, for the levels of its wavefront, a WINDOW of 4 state pages per level
+ * instead of one per frame (a frame chain only reads the previous frame's ssim.value); such a pyramid can only be run by
+ * vm_morph_run / the wavefront calls, and per-frame state (vm_level_get of the SSIM / TPS arrays, vm_level_energy) is
+ * not available afterwards -- the vector fields are.  VMORPH_ARENA_SLOTS=n (even, >= 2) forces a window, 0 forbids it. */
 int vm_pyramid_alloc(vm_pyramid *p, int w, int h, int d, int start_res, int64_t voxel_cap);
 /* Pyramid::build (Pyramid.h:28): video0/video1 = d frames of h*w*3 RGB8; f0,f1,b0,b1 = d frames of h*w float2
  * optical flow (may all be NULL when d == 1).  Builds every level's gray images and flows on the GPU. */
@@ -168,8 +172,9 @@ int vm_level_initialize_frames(vm_morph *m, int level, int frame0, int nframes, 
 /* The direction x level wavefront of a video, in pieces (vm_morph_run drives them on one GPU; videomorphing_b200/dist.py
  * drives the same schedule over several GPUs, one process each):
  *   vm_morph_wavefront_prepare  runs everything above the wavefront -- the coarse dense solve and the temporally
- *       subsampled levels, each whole (morph.cu:150-168 for those levels) -- then prolongs and initialises the head level
- *       K (the coarsest level whose finer levels all have its depth) and gives the levels 2 .. K their own state arenas.
+ *       subsampled levels, each whole (morph.cu:150-168 for those levels) -- then prolongs the head level K (the coarsest
+ *       level whose finer levels all have its depth) and gives the levels 2 .. K their own state arenas; the frames of the
+ *       levels K .. 1 are initialised one by one (vm_level_initialize_frames) when their chains reach them.
  *       Returns K (>= 1) or a negative status.  Asynchronous on `stream`.
  *   vm_level_enqueue_jobs       ONE persistent launch that optimises n <= 16 independent (level, frame) jobs in lock-step
  *       (the do / while of morph.cu:1377-1391 for each); the jobs' levels must be initialised (and, with flag = 1,

@@ -137,7 +137,7 @@ class _FakeEngine:
     def prep_frame(self, l, i, head, first, tdir):
         if not head:
             self._up(l, i)
-        assert i in self.ready[l]
+        assert i in self.ready[l]                        # (the real engine initialises the frame here, head level included)
         if not first:
             self._init_temp(l, i, tdir)
 

@@ -467,3 +467,25 @@ def test_both_sweep_kernels_and_the_wavefront_equal_the_oracle(vm, oracle_lib, s
     v_first = m.get_vectors()
     m.run()
     np.testing.assert_array_equal(m.get_vectors(), v_first)
+
+
+def test_window_of_state_pages_gives_the_same_vectors(vm, oracle_lib, monkeypatch):
+    """cfg5-style memory plan: the levels of the wavefront keep 4 state pages (2 per frame chain) instead of one per frame
+    (vm_pyramid_alloc, VMORPH_ARENA_SLOTS).  Same vectors and iteration log as the oracle; per-frame state is then not
+    addressable, the vector fields are."""
+    from videomorphing_b200 import synth
+    monkeypatch.setenv("VMORPH_ARENA_SLOTS", "4")
+    v0, v1, flows, _ = synth.video_pair(96, 64, 13, 41, 42, 3.0)
+    o = oracle_lib.Oracle(dict(max_iter=24, start_res=4))
+    n = o.build(v0, v1, flows=flows)
+    pyr = vm.Pyramid(0)
+    assert pyr.build(v0, v1, flows, start_res=4) == n
+    m = vm.Morph(vm.Parameters(max_iter=24, start_res=4), pyr)
+    o.run(); m.run()
+    np.testing.assert_array_equal(m.iters_log(), o.iters_log())
+    _assert_vec(m.get_vectors(), o.extract_vectors(), "windowed arenas")
+    np.testing.assert_array_equal(pyr.get(1, "v"), o.get(1, "v"))
+    with pytest.raises(vm._lib.VmError):
+        pyr.get(1, "mean")
+    m.run()                                                   # again on the same objects
+    _assert_vec(m.get_vectors(), o.extract_vectors(), "windowed arenas, second run")

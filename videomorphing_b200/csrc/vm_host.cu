@@ -129,9 +129,13 @@ LevelView make_view(vm_pyramid *p, int level) {
 // d = nframes, so the per-level kernels (grid z = page) work on a frame range unchanged.
 LevelView make_frames_view(vm_pyramid *p, int level, int frame0, int nframes) {
     LevelView V = make_view(p, level);
-    const size_t po = (size_t)frame0 * V.ps, io = (size_t)frame0 * V.ips, fo = (size_t)frame0 * V.w * V.h;
+    const Arena &A = arena_of(p, level);
+    const size_t vo = (size_t)frame0 * V.ps, fo = (size_t)frame0 * V.w * V.h;
+    const size_t page = (size_t)A.page_of(frame0, V.d);               // window mode: nframes == 1 (checked by the callers)
+    const size_t po = page * V.ps, io = page * V.ips;
     V.d = nframes;
-    V.v += po; V.mean += po; V.var += po; V.luma += po; V.tps_b += po; V.ui_b += po; V.temp_ref += po;
+    V.v += vo;
+    V.mean += po; V.var += po; V.luma += po; V.tps_b += po; V.ui_b += po; V.temp_ref += po;
     V.cross += po; V.value += po; V.counter += po; V.tps_axy += po; V.ui_axy += po; V.temp_mask += po;
     V.impmask += io;
     if (V.img0) V.img0 += fo;
@@ -229,6 +233,20 @@ int vm_pyramid_alloc(vm_pyramid *p, int w, int h, int d, int start_res, int64_t 
     p->lv.clear(); p->lv.resize(s.size());
     p->own.clear();
     p->w0 = w; p->h0 = h; p->d0 = d; p->shared.level = -1; p->a_start_res = start_res; p->a_cap = voxel_cap;
+    // head level of the video wavefront and the decision whether its levels keep every frame's optimizer state or a window
+    // (VMORPH_ARENA_SLOTS = n forces a window of n pages, 0 forces full arenas; default: window when the full state of the
+    // finest level would exceed 24 GB -- 4K x 240 needs 143 GB)
+    int K = 1;
+    while (K + 1 <= (int)s.size() - 2 && s[K].d == s[K + 1].d) K++;
+    if (2 * K > MJ_MAX_JOBS) K = MJ_MAX_JOBS / 2;
+    p->head_level = K;
+    {
+        const char *e = getenv("VMORPH_ARENA_SLOTS");
+        const size_t full1 = 72ull * ((size_t)((s[1].w + 31) / 32 * 32) * s[1].h) * s[1].d;
+        p->window_slots = e ? atoi(e) : ((d > 8 && full1 > (24ull << 30)) ? 4 : 0);
+        if (p->window_slots < 0 || p->window_slots == 1 || (p->window_slots & 1) || d <= 4) p->window_slots = 0;
+    }
+    p->shared.nslots = 0;
     size_t max_state = 0, max_ps = 0, max_imp = 0;
     for (size_t i = 0; i < s.size(); i++) {
         Level &L = p->lv[i];
@@ -245,9 +263,10 @@ int vm_pyramid_alloc(vm_pyramid *p, int w, int h, int d, int start_res, int64_t 
             size_t fs = (size_t)L.w * L.h * L.d;
             VM_CUDA(L.img0.ensure(sizeof(float) * fs)); VM_CUDA(L.img1.ensure(sizeof(float) * fs));
             if (d > 1) { VM_CUDA(L.f0.ensure(sizeof(float2) * fs)); VM_CUDA(L.f1.ensure(sizeof(float2) * fs)); VM_CUDA(L.b0.ensure(sizeof(float2) * fs)); VM_CUDA(L.b1.ensure(sizeof(float2) * fs)); }
-            max_state = std::max(max_state, (size_t)L.ps * L.d);
+            const size_t pages = (p->window_slots && (int)i <= K) ? (size_t)p->window_slots : (size_t)L.d;
+            max_state = std::max(max_state, (size_t)L.ps * pages);
             max_ps = std::max(max_ps, (size_t)L.ps);
-            max_imp = std::max(max_imp, (size_t)L.ips * L.d);
+            max_imp = std::max(max_imp, (size_t)L.ips * pages);
         }
     }
     VM_CUDA(p->shared.ensure(max_state, max_imp));
@@ -274,6 +293,7 @@ static int field_ptr(vm_pyramid *p, int level, int field, void **ptr, size_t *by
     bool state = field >= VM_FIELD_SSIM_MEAN && field <= VM_FIELD_IMPROVING_MASK;
     if (state && !(L.has_images)) { set_error("level %d has no optimizer state", level); return VM_ERR_STATE; }
     Arena &A = arena_of(p, level);      // (an arena that describes another level is still addressable with this level's strides)
+    if (state && A.nslots) { set_error("level %d keeps a window of %d state pages, not every frame", level, A.nslots); return VM_ERR_STATE; }
     switch (field) {
     case VM_FIELD_V: *ptr = L.v.p; *bytes = 8 * n; break;
     case VM_FIELD_SSIM_MEAN: *ptr = A.mean.p; *bytes = 8 * n; break;
@@ -464,6 +484,7 @@ int vm_level_initialize(vm_morph *m, int level, void *stream) {
     int rc = use_device(p->device); if (rc) return rc;
     Level &L = p->lv[level];
     if (!L.img0.p || !L.img1.p) { set_error("level %d has no images", level); return VM_ERR_STATE; }
+    if (arena_of(p, level).nslots) { set_error("level %d keeps a window of state pages: initialise it frame by frame", level); return VM_ERR_STATE; }
     size_t n = (size_t)L.ps * L.d;
     // morph.cu:280-314: (re)size + zero-fill of every per-level array (the arena is reused across levels)
     Arena &A = arena_of(p, level);
@@ -507,6 +528,7 @@ int vm_level_initialize_frames(vm_morph *m, int level, int frame0, int nframes, 
     Level &L = p->lv[level];
     if (!L.img0.p || !L.img1.p) { set_error("level %d has no images", level); return VM_ERR_STATE; }
     if (frame0 < 0 || nframes < 1 || frame0 + nframes > L.d) { set_error("bad frame range %d+%d", frame0, nframes); return VM_ERR_ARG; }
+    if (arena_of(p, level).nslots && nframes != 1) { set_error("level %d keeps a window of state pages: one frame per call", level); return VM_ERR_ARG; }
     int rc = use_device(p->device); if (rc) return rc;
     LevelView V = make_frames_view(p, level, frame0, nframes);
     size_t n = (size_t)L.ps * nframes;
@@ -535,7 +557,12 @@ static int init_temp_chain(vm_morph *m, int level, int frame, int dir, cudaStrea
     int rc = use_device(p->device); if (rc) return rc;
     DevBuf &acc = chain ? p->tmp_a2 : p->tmp_a;
     if (acc.bytes < sizeof(long long) * 3 * (size_t)L.ps) { VM_CUDA(cudaDeviceSynchronize()); VM_CUDA(acc.ensure(sizeof(long long) * 3 * (size_t)L.ps)); }
-    VM_CUDA(launch_initialize_temp(make_view(p, level), frame, dir, acc.as<long long>(), s));
+    const int n = frame + dir;                                        // the chain neighbour (upsample.cu:235-244)
+    const Arena &A = arena_of(p, level);
+    const size_t fs = (size_t)L.w * L.h;
+    const float2 *F0 = (dir < 0 ? L.f0 : L.b0).as<float2>() + (size_t)n * fs, *F1 = (dir < 0 ? L.f1 : L.b1).as<float2>() + (size_t)n * fs;
+    VM_CUDA(launch_initialize_temp(make_frames_view(p, level, frame, 1), L.v.as<float2>() + (size_t)n * L.ps,
+                                   A.value.as<float>() + (size_t)A.page_of(n, L.d) * L.ps, F0, F1, acc.as<long long>(), s));
     return VM_OK;
 }
 
@@ -727,14 +754,7 @@ static int enqueue_level_mj(vm_morph *m, int level, float max_iter, cudaStream_t
 // tick is ONE multi-job launch with up to 2 K jobs.  The coarser levels (temporally subsampled) run whole, one after the other.
 // Same arithmetic as the level-by-level order: bit-identical vectors, identical iteration counts.
 static int enqueue_level(vm_morph *m, int level, float max_iter, cudaStream_t s, int chains, bool allow_mj);
-static int wavefront_head(vm_morph *m) {
-    vm_pyramid *p = m->pyr;
-    const int n = (int)p->lv.size();
-    int K = 1;
-    while (K + 1 <= n - 2 && p->lv[K].d == p->lv[K + 1].d) K++;
-    if (2 * K > MJ_MAX_JOBS) K = MJ_MAX_JOBS / 2;                                                 // deeper pyramids: the coarsest equal-depth levels run whole
-    return K;
-}
+static int wavefront_head(vm_morph *m) { return m->pyr->head_level; }   // set by vm_pyramid_alloc
 // the levels in flight together own their arenas (level 1 keeps the shared one)
 static int wavefront_arenas(vm_morph *m, int K) {
     vm_pyramid *p = m->pyr;
@@ -744,7 +764,9 @@ static int wavefront_arenas(vm_morph *m, int K) {
         if (!p->own[l]) {
             VM_CUDA(cudaDeviceSynchronize());
             p->own[l].reset(new Arena());
-            VM_CUDA(p->own[l]->ensure((size_t)p->lv[l].ps * p->lv[l].d, (size_t)p->lv[l].ips * p->lv[l].d));
+            const size_t pages = p->window_slots ? (size_t)p->window_slots : (size_t)p->lv[l].d;
+            p->own[l]->nslots = p->window_slots;
+            VM_CUDA(p->own[l]->ensure((size_t)p->lv[l].ps * pages, (size_t)p->lv[l].ips * pages));
         }
     return VM_OK;
 }
@@ -753,6 +775,7 @@ static int wavefront_arenas(vm_morph *m, int K) {
 static int wavefront_coarse(vm_morph *m, int K, const std::vector<float> &mi, cudaStream_t s) {
     vm_pyramid *p = m->pyr;
     const int n = (int)p->lv.size();
+    p->shared.nslots = 0;                                              // the levels above the wavefront keep every frame
     int rc = vm_level_cpu_solve(m, s); if (rc) return rc;
     for (int l = n - 2; l > K; l--) {
         if (!keep_running(m)) { m->cancelled = true; return VM_OK; }
@@ -762,8 +785,11 @@ static int wavefront_coarse(vm_morph *m, int K, const std::vector<float> &mi, cu
         rc = enqueue_level(m, l, mi[l], s, 3, m->sweep_mode == 2); if (rc) return rc;
     }
     if (!keep_running(m)) { m->cancelled = true; return VM_OK; }
+    // the head level is prolonged whole (temporal in-fill needs its neighbours) and, like the levels below it, initialised
+    // frame by frame when its chains reach the frame; from here on the shared arena belongs to level 1
     rc = vm_level_upsample(m, K, s); if (rc) return rc;
-    return vm_level_initialize(m, K, s);
+    p->shared.nslots = p->window_slots;
+    return VM_OK;
 }
 
 static int run_wavefront(vm_morph *m, cudaStream_t s) {
@@ -776,6 +802,7 @@ static int run_wavefront(vm_morph *m, cudaStream_t s) {
     int rc = wavefront_arenas(m, K); if (rc) return rc;
     rc = wavefront_coarse(m, K, mi, s); if (rc) return rc;
     if (m->cancelled) return VM_OK;
+    if (K == 1) p->shared.level = -1;
     const int d = p->lv[K].d, mid = d / 2, nf = d - mid, nb = mid;
     const int nticks = K - 1 + std::max(nf, nb + 1);
     for (int T = 0; T < nticks; T++) {
@@ -787,10 +814,8 @@ static int run_wavefront(vm_morph *m, cudaStream_t s) {
                 const int c = T - st - dr;                       // the backward chain starts one tick after the middle frame
                 if (c < 0 || c >= (dr == 0 ? nf : nb)) continue;
                 const int i = dr == 0 ? mid + c : mid - 1 - c;
-                if (st > 0) {
-                    rc = vm_level_upsample_frames(m, l, i, 1, s); if (rc) return rc;
-                    rc = vm_level_initialize_frames(m, l, i, 1, s); if (rc) return rc;
-                }
+                if (st > 0) { rc = vm_level_upsample_frames(m, l, i, 1, s); if (rc) return rc; }
+                rc = vm_level_initialize_frames(m, l, i, 1, s); if (rc) return rc;
                 const bool first = dr == 0 && c == 0;            // the middle frame has no temporal term (morph.cu:1377-1391)
                 if (!first) { rc = init_temp_chain(m, l, i, dr == 0 ? -1 : 1, s, 0); if (rc) return rc; }
                 js[nj++] = {l, i, first ? 0 : 1, mi[l]};
@@ -954,6 +979,7 @@ int vm_morph_run(vm_morph *m, void *stream) {
     m->done_iter = 0;
     m->total_l = (int)p->lv.size() - 1;
     float max_iter = (float)m->prm.max_iter;
+    if (p->window_slots && !(use_mj(m) && p->d0 > 1 && !m->no_wavefront)) { set_error("this pyramid keeps a window of state pages: only the wavefront schedule can run it"); return VM_ERR_STATE; }
     if (use_mj(m) && p->d0 > 1 && !m->no_wavefront) {
         rc = run_wavefront(m, s); if (rc) return rc;
         return collect_log(m, from, s);
@@ -1019,6 +1045,7 @@ int vm_level_energy(vm_morph *m, int level, int frame, int flag, double *energy_
     vm_pyramid *p = m->pyr;
     if (level < 1 || level + 1 >= (int)p->lv.size() || arena_of(p, level).level != level) { set_error("level %d is not initialised", level); return VM_ERR_STATE; }
     if (frame < 0 || frame >= p->lv[level].d) { set_error("bad frame"); return VM_ERR_ARG; }
+    if (arena_of(p, level).nslots) { set_error("level %d keeps a window of state pages: no per-frame energy after the run", level); return VM_ERR_STATE; }
     int rc = use_device(p->device); if (rc) return rc;
     VM_CUDA(cudaDeviceSynchronize());
     DevBuf out; VM_CUDA(out.ensure(4 * sizeof(double)));

@@ -69,6 +69,15 @@ struct Conn { vm_conp l, r; };
 struct Arena {
     DevBuf mean, var, luma, tps_b, ui_b, temp_ref, cross, value, counter, tps_axy, ui_axy, temp_mask, impmask;
     int level = -1;                       // which level the arena currently describes
+    int nslots = 0;                       // 0: one page per frame of the level; else a WINDOW of pages (see page_of)
+    // Window mode (videos whose full state would not fit, e.g. 3840x2160 x 240: 143 GB at the finest level): a frame chain only
+    // ever touches the frame it optimises and the `ssim.value` of the frame before it (initialize_temp, upsample.cu:214-258),
+    // so each direction keeps nslots / 2 pages that the chain positions reuse round-robin.
+    int page_of(int frame, int depth) const {
+        if (!nslots) return frame;
+        const int W = nslots / 2, c = frame - depth / 2;
+        return c >= 0 ? c % W : W + ((-c - 1) % W);
+    }
     cudaError_t ensure(size_t px, size_t imp) {
         cudaError_t e;
         DevBuf *f2[] = {&mean, &var, &luma, &tps_b, &ui_b, &temp_ref}, *f1[] = {&cross, &value, &counter, &tps_axy, &ui_axy, &temp_mask};
@@ -106,6 +115,8 @@ struct vm_pyramid {
     vm::DevBuf tmp_a2;                    // splat accumulators of the second (backward) frame chain
     vm::HostStencils hst;
     int a_start_res = 0; int64_t a_cap = 0;   // arguments of the last vm_pyramid_alloc (identical re-allocations are no-ops)
+    int window_slots = 0;                 // > 0: the levels of the wavefront keep a window of this many state pages (Arena::nslots)
+    int head_level = 1;                   // head level K of the wavefront (coarsest level whose finer levels all have its depth)
     void *resample_cache = nullptr;       // vm::ResampleCache (vm_resample.cu): filter tables, prefilter factors, transient planes
 };
 
@@ -179,7 +190,9 @@ cudaError_t launch_initialize_level(const LevelView &L, const StencilTables *st,
 cudaError_t launch_ui_splat(const LevelView &L, const Conn *cons_dev, int ncons, int factor, int w0, int h0, int d0, cudaStream_t s, int z0 = 0);
 cudaError_t launch_upsample(const LevelView &dst, const float2 *src_v, int sw, int sh, int srs, int sps, int sd, int factor, cudaStream_t s);
 cudaError_t launch_temporal_infill(const LevelView &dst, long long *acc /*3*ps*/, float2 *vtmp /*ps*/, float *wtmp /*ps*/, cudaStream_t s);
-cudaError_t launch_initialize_temp(const LevelView &L, int frame, int dir, long long *acc /*3*ps*/, cudaStream_t s);
+// Lf: view of the frame being initialised (page 0); v_nb / value_nb: v and ssim.value pages of the chain neighbour; F0 / F1: its flows
+cudaError_t launch_initialize_temp(const LevelView &Lf, const float2 *v_nb, const float *value_nb, const float2 *F0, const float2 *F1,
+                                   long long *acc /*3*ps*/, cudaStream_t s);
 cudaError_t launch_coarse_solve(const LevelView &L, const KParams &P, const Conn *cons_dev, int ncons, int factor, int w0, int h0, int d0,
                                 float *Af, double *Ad, double *rhs, int *status, cudaStream_t s);
 cudaError_t launch_energy(const LevelView &L, const KParams &P, int frame, int flag, double *out4_dev, cudaStream_t s);

@@ -200,15 +200,13 @@ __global__ void k_temp_finish_init(LevelView L, int page, const long long *__res
     } else L.temp_mask[idx] = 0.0f;
 }
 
-cudaError_t launch_initialize_temp(const LevelView &L, int i, int dir, long long *acc, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(long long) * 3 * (size_t)L.ps, s);
+cudaError_t launch_initialize_temp(const LevelView &Lf, const float2 *v_nb, const float *value_nb, const float2 *F0, const float2 *F1,
+                                   long long *acc, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(long long) * 3 * (size_t)Lf.ps, s);
     if (e != cudaSuccess) return e;
-    int n = i + dir;
-    size_t fs = (size_t)L.w * L.h;
-    const float2 *F0 = (dir < 0 ? L.f0 : L.b0) + n * fs, *F1 = (dir < 0 ? L.f1 : L.b1) + n * fs;     // upsample.cu:235-244
-    dim3 b(32, 8), g = grid2(L.w, L.h, 32, 8);
-    k_temp_splat<<<g, b, 0, s>>>(L, L.v + (size_t)n * L.ps, L.value + (size_t)n * L.ps, F0, F1, (unsigned long long *)acc);
-    k_temp_finish_init<<<g, b, 0, s>>>(L, i, acc);
+    dim3 b(32, 8), g = grid2(Lf.w, Lf.h, 32, 8);
+    k_temp_splat<<<g, b, 0, s>>>(Lf, v_nb, value_nb, F0, F1, (unsigned long long *)acc);      // upsample.cu:235-245
+    k_temp_finish_init<<<g, b, 0, s>>>(Lf, 0, acc);
     count_launch(2);
     return cudaGetLastError();
 }

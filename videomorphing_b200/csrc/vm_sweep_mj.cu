@@ -128,16 +128,16 @@ __device__ __forceinline__ void mj_filter_tile(MjShared &S, int j, int t, const 
     }
 }
 
-__device__ __forceinline__ void mj_filter_all(MjShared &S, int njobs, int g, const KParams &P, unsigned int *qcount, unsigned int *queue,
+__device__ __forceinline__ void mj_filter_all(MjShared &S, int njobs, int g, int gmask, const KParams &P, unsigned int *qcount, unsigned int *queue,
                                               unsigned gwarp, unsigned nwarps, int warp, int lane) {
     int total = 0;
-    for (int j = g; j < njobs; j += 2) if (S.live[j]) total += S.job[j].gx * S.job[j].gy;
+    for (int j = 0; j < njobs; j++) if ((j & gmask) == g && S.live[j]) total += S.job[j].gx * S.job[j].gy;
     // (dealt from the last warp of the grid backwards: the commit gather of the previous round, dealt from the first warp
     //  forwards, runs next to it on other warps)
     for (int wt = (int)(nwarps - 1u - gwarp); wt < total; wt += (int)nwarps) {
-        int j = g, t = wt;
-        for (; j < njobs; j += 2) {
-            if (!S.live[j]) continue;
+        int j = 0, t = wt;
+        for (; j < njobs; j++) {
+            if ((j & gmask) != g || !S.live[j]) continue;
             const int nt = S.job[j].gx * S.job[j].gy;
             if (t < nt) break;
             t -= nt;
@@ -314,14 +314,15 @@ __device__ __forceinline__ void mj_advance(MjShared &S, int j, volatile int *pro
     S.sp[j] = sp; S.step[j] = step; S.iter[j] = iter;
 }
 
-// The jobs form two groups (even / odd index) whose rounds are half a round apart: while group A computes round r, the
-// warps that have no pixel of A (most of them, in the sparse rounds that dominate) commit round r-1 of group B and filter
-// its round r.  Every job still sees queue -> barrier -> compute -> barrier -> gather + filter -> barrier ..., but each
-// grid barrier now ends a compute phase of one group AND a gather / filter phase of the other, and the latency chains
-// of the two kinds of phase (both a handful of dependent L2 round trips) overlap instead of adding up.
+// The kernel alternates two kinds of phase, each ended by a grid barrier: COMPUTE (the warps pull the queued pixels) and
+// COMMIT (schedule advance, gather of the accepted moves, filter of the next round).  With ngroups == 2 (experiment hook
+// VMORPH_MJ_GROUPS=2) the jobs form two groups (even / odd index) half a round apart, so that one group's compute phase
+// shares its barrier with the other group's commit phase; measured on 720p x 120 this loses more packing in the dense
+// rounds (two half queues instead of one) than it hides latency in the sparse ones (3.41 s against 3.04 s), so the
+// default is one group: every phase below then serves all jobs.
 __global__ void __launch_bounds__(MJ_NW * 32, 1)
 k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const StencilTables *__restrict__ st, unsigned int *gctrl,
-           unsigned int *queue, unsigned int *acclist, unsigned int qcap, volatile int *run_flag, volatile int *progress) {
+           unsigned int *queue, unsigned int *acclist, unsigned int qcap, int ngroups, volatile int *run_flag, volatile int *progress) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MjShared &S = *reinterpret_cast<MjShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -343,7 +344,8 @@ k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const Stenci
         while (s0 < 4 && step_empty(S.job[tid].L, s0)) s0++;            // step 0 (offset 0,0) is never empty
         S.iter[tid] = 0; S.step[tid] = s0; S.sp[tid] = 0; S.live[tid] = 1; S.voted[tid] = 0;
     }
-    if (tid == 0) { S.glive[0] = 1; S.glive[1] = njobs > 1 ? 1 : 0; }
+    const int gmask = ngroups == 2 ? 1 : 0;                             // group of job j = j & gmask
+    if (tid == 0) { S.glive[0] = 1; S.glive[1] = (gmask && njobs > 1) ? 1 : 0; }
     __syncthreads();
     unsigned int epoch = 0, rnd[2] = {0u, 0u};
     bool started1 = false;                                               // group 1 has had its first filter
@@ -351,18 +353,18 @@ k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const Stenci
     long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = clock64(), t1;
 #define MJ_TR(k) do { if (tracer) { t1 = clock64(); tr[k] += t1 - t0; t0 = t1; } } while (0)
     // ---- filter of round 0 of group 0
-    mj_filter_all(S, njobs, 0, P, &gctrl[GC_QN + 0], queue, gwarp, nwarps, warp, lane);
+    mj_filter_all(S, njobs, 0, gmask, P, &gctrl[GC_QN + 0], queue, gwarp, nwarps, warp, lane);
     grid_barrier(&gctrl[GC_BAR], epoch, gridDim.x);
     for (unsigned h = 0;; h++) {
         const int A = (int)(h & 1u), B = A ^ 1;
         const int liveA = S.glive[A], wasB = S.glive[B];
         const bool gfB = wasB && (B == 0 || started1);                   // group B has a computed round to commit
         // ---- schedule of group B moves on (needs the votes of its last compute phase, which ended at the previous barrier)
-        if (gfB && tid < njobs && (tid & 1) == B && S.live[tid]) mj_advance(S, tid, progress);
+        if (gfB && tid < njobs && (tid & gmask) == B && S.live[tid]) mj_advance(S, tid, progress);
         __syncthreads();
         if (tid == 0) {
             int l0 = 0, l1 = 0;
-            for (int j = 0; j < njobs; j++) if (S.live[j]) { if (j & 1) l1 = 1; else l0 = 1; }
+            for (int j = 0; j < njobs; j++) if (S.live[j]) { if (j & gmask) l1 = 1; else l0 = 1; }
             S.glive[0] = l0; S.glive[1] = l1;
         }
         __syncthreads();
@@ -377,7 +379,7 @@ k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const Stenci
             if (gtid == 0) {
                 gctrl[GC_QN + A * 2 + (par ^ 1u)] = 0u; gctrl[GC_PULL + A * 2 + (par ^ 1u)] = 0u;   // next round's queue of the group
                 if (run_flag && *run_flag == 0)
-                    for (int j = A; j < njobs; j += 2) if (S.live[j]) atomicOr(&S.job[j].ctrl[JC_FLAGS + (S.iter[j] & 3)], 2u);   // morph.cu:1390 (m_cb)
+                    for (int j = 0; j < njobs; j++) if ((j & gmask) == A && S.live[j]) atomicOr(&S.job[j].ctrl[JC_FLAGS + (S.iter[j] & 3)], 2u);   // morph.cu:1390 (m_cb)
             }
             // speculative line search only while most warps would otherwise idle (uniform over the grid; results do not depend on it)
             const bool spec = qn * 16u <= 6u * nwarps;
@@ -400,9 +402,9 @@ k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const Stenci
             const unsigned *aB = acclist + (size_t)B * qcap;
             for (unsigned a = gwarp; a < nacc; a += nwarps) mj_gather(S, P, __ldcg(aB + a), rid, lane);
             if (tracer) tr[7] += nacc;
-            if (S.glive[B]) mj_filter_all(S, njobs, B, P, &gctrl[GC_QN + B * 2 + (par ^ 1u)], queue + (size_t)B * qcap, gwarp, nwarps, warp, lane);
+            if (S.glive[B]) mj_filter_all(S, njobs, B, gmask, P, &gctrl[GC_QN + B * 2 + (par ^ 1u)], queue + (size_t)B * qcap, gwarp, nwarps, warp, lane);
         } else if (B == 1 && !started1 && wasB) {
-            mj_filter_all(S, njobs, 1, P, &gctrl[GC_QN + 2 + 0], queue + (size_t)qcap, gwarp, nwarps, warp, lane);
+            mj_filter_all(S, njobs, 1, gmask, P, &gctrl[GC_QN + 2 + 0], queue + (size_t)qcap, gwarp, nwarps, warp, lane);
         }
         if (B == 1) started1 = true;
         __syncthreads();
@@ -419,11 +421,14 @@ struct MjCfg { bool init = false; int per_sm = 0; };
 static MjCfg g_mj_cfg[64];
 static std::mutex g_mj_mu;
 static int g_mj_div = 32;            // VMORPH_MJ_DIV: candidate pixels per CTA that decide the grid size of small launches
+static int g_mj_groups = 1;          // VMORPH_MJ_GROUPS: 2 = two job groups half a round apart (see k_sweep_mj)
 
 void sweep_mj_reload_hooks() {
     std::lock_guard<std::mutex> lock(g_mj_mu);
     const char *e = getenv("VMORPH_MJ_DIV");
     g_mj_div = (e && atoi(e) > 0) ? atoi(e) : 32;
+    e = getenv("VMORPH_MJ_GROUPS");
+    g_mj_groups = (e && atoi(e) == 2) ? 2 : 1;
 }
 
 cudaError_t sweep_mj_trace(unsigned long long *out8, int reset) {
@@ -443,7 +448,7 @@ cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_hos
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return e;
     if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
-    int per_sm, div;
+    int per_sm, div, ngroups;
     {
         std::lock_guard<std::mutex> lock(g_mj_mu);
         MjCfg &cfg = g_mj_cfg[device];
@@ -455,7 +460,7 @@ cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_hos
             if (cfg.per_sm < 1) return cudaErrorLaunchOutOfResources;
             cfg.init = true;
         }
-        per_sm = cfg.per_sm; div = g_mj_div;
+        per_sm = cfg.per_sm; div = g_mj_div; ngroups = g_mj_groups;
     }
     if (sm_budget <= 0 || sm_budget > sm_count) sm_budget = sm_count;
     // grid: enough warps for the candidate pixels of one round, at most the launch's share of the GPU (every CTA must be
@@ -465,7 +470,7 @@ cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_hos
     long long want = (cands + div - 1) / div;
     int grid = (int)(want < 4 ? 4 : want);
     if (grid > sm_budget * per_sm) grid = sm_budget * per_sm;
-    void *args[] = {(void *)&jobs_dev, (void *)&njobs, (void *)&P, (void *)&st, (void *)&gctrl, (void *)&queue, (void *)&acclist, (void *)&qcap, (void *)&run_flag, (void *)&progress};
+    void *args[] = {(void *)&jobs_dev, (void *)&njobs, (void *)&P, (void *)&st, (void *)&gctrl, (void *)&queue, (void *)&acclist, (void *)&qcap, (void *)&ngroups, (void *)&run_flag, (void *)&progress};
     count_launch();
     return cudaLaunchCooperativeKernel((const void *)k_sweep_mj, dim3(grid), dim3(MJ_NW * 32), args, sizeof(MjShared), stream);
 }

@@ -204,13 +204,13 @@ class MorphEngine:
 
     def prepare(self):
         """Everything above the wavefront, redundantly on every rank (deterministic => identical, no exchange): coarse solve,
-        the temporally subsampled levels, head level prolonged + initialised.  Returns the head level K."""
+        the temporally subsampled levels, head level prolonged.  Returns the head level K."""
         return self.m.wavefront_prepare()
 
     def prep_frame(self, l, i, head, first, tdir):
-        if not head:
+        if not head:                                  # the head level was prolonged whole by prepare() (temporal in-fill)
             self.m.upsample_frames(l, i, 1)
-            self.m.initialize_frames(l, i, 1)
+        self.m.initialize_frames(l, i, 1)
         if not first:
             self.m.initialize_temp(l, i, tdir)
 
