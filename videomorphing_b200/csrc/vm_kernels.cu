@@ -82,37 +82,45 @@ cudaError_t launch_initialize_level(const LevelView &L, const StencilTables *st,
 // UI splat (morph.cu:345-388): the reference copies v to the host and loops there.  One thread per frame walks the
 // connection list in order (same accumulation order), directly on the device arrays.
 // (z0: frame number of the view's first page, for views that cover a frame range of the level)
+// One warp per frame: the lanes scan the connection list for the frame's entries 32 at a time, lane 0 applies the matches
+// in list order (the accumulation order of the reference's loop).
 __global__ void k_ui_splat(LevelView L, const Conn *__restrict__ cons, int ncons, int factor, int w0, int h0, int d0, int z0) {
-    int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = blockIdx.x, lane = threadIdx.x;
     if (z >= L.d) return;
-    int conz = min((z0 + z) * factor, d0 - 1);
-    for (int k = 0; k < ncons; k++) {
-        vm_conp l = cons[k].l, r = cons[k].r;
-        if (conz != l.z) continue;                                  // left point's frame only (morph.cu:359)
-        float x0 = (float)((l.x + 0.5) / w0 * L.w - 0.5f);
-        float y0 = (float)((l.y + 0.5) / h0 * L.h - 0.5f);
-        float x1 = (float)((r.x + 0.5) / w0 * L.w - 0.5f);
-        float y1 = (float)((r.y + 0.5) / h0 * L.h - 0.5f);
-        float weight = minf_std(l.weight, r.weight);
-        float con_x = (x0 + x1) / 2.0f, con_y = (y0 + y1) / 2.0f;
-        float vx = (x1 - x0) / 2.0f, vy = (y1 - y0) / 2.0f;
-        for (int y = (int)floorf(con_y); y <= (int)ceilf(con_y); y++)
-            for (int x = (int)floorf(con_x); x <= (int)ceilf(con_x); x++)
-                if (x >= 0 && x < L.w && y >= 0 && y < L.h) {
-                    size_t idx = (size_t)y * L.rs + x + (size_t)z * L.ps;
-                    float bw = (1 - fabsf((float)y - con_y)) * (1 - fabsf((float)x - con_x)) * weight;
-                    L.ui_axy[idx] += bw;
-                    float kk = 2 * bw;
-                    float2 v = L.v[idx], b = L.ui_b[idx];
-                    b.x += kk * (v.x - vx); b.y += kk * (v.y - vy);
-                    L.ui_b[idx] = b;
-                }
+    const int conz = min((z0 + z) * factor, d0 - 1);
+    for (int base = 0; base < ncons; base += 32) {
+        const int kq = base + lane;
+        unsigned bal = __ballot_sync(0xffffffffu, kq < ncons && cons[kq].l.z == conz);   // left point's frame only (morph.cu:359)
+        if (lane != 0) continue;
+        while (bal) {
+            const int k = base + __ffs(bal) - 1;
+            bal &= bal - 1;
+            vm_conp l = cons[k].l, r = cons[k].r;
+            float x0 = (float)((l.x + 0.5) / w0 * L.w - 0.5f);
+            float y0 = (float)((l.y + 0.5) / h0 * L.h - 0.5f);
+            float x1 = (float)((r.x + 0.5) / w0 * L.w - 0.5f);
+            float y1 = (float)((r.y + 0.5) / h0 * L.h - 0.5f);
+            float weight = minf_std(l.weight, r.weight);
+            float con_x = (x0 + x1) / 2.0f, con_y = (y0 + y1) / 2.0f;
+            float vx = (x1 - x0) / 2.0f, vy = (y1 - y0) / 2.0f;
+            for (int y = (int)floorf(con_y); y <= (int)ceilf(con_y); y++)
+                for (int x = (int)floorf(con_x); x <= (int)ceilf(con_x); x++)
+                    if (x >= 0 && x < L.w && y >= 0 && y < L.h) {
+                        size_t idx = (size_t)y * L.rs + x + (size_t)z * L.ps;
+                        float bw = (1 - fabsf((float)y - con_y)) * (1 - fabsf((float)x - con_x)) * weight;
+                        L.ui_axy[idx] += bw;
+                        float kk = 2 * bw;
+                        float2 v = L.v[idx], b = L.ui_b[idx];
+                        b.x += kk * (v.x - vx); b.y += kk * (v.y - vy);
+                        L.ui_b[idx] = b;
+                    }
+        }
     }
 }
 
 cudaError_t launch_ui_splat(const LevelView &L, const Conn *cons_dev, int ncons, int factor, int w0, int h0, int d0, cudaStream_t s, int z0) {
     if (ncons <= 0) return cudaSuccess;
-    k_ui_splat<<<(L.d + 63) / 64, 64, 0, s>>>(L, cons_dev, ncons, factor, w0, h0, d0, z0);
+    k_ui_splat<<<L.d, 32, 0, s>>>(L, cons_dev, ncons, factor, w0, h0, d0, z0);
     count_launch();
     return cudaGetLastError();
 }

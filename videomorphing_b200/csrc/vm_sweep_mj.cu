@@ -322,7 +322,7 @@ __device__ __forceinline__ void mj_advance(MjShared &S, int j, volatile int *pro
 // default is one group: every phase below then serves all jobs.
 __global__ void __launch_bounds__(MJ_NW * 32, 1)
 k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const StencilTables *__restrict__ st, unsigned int *gctrl,
-           unsigned int *queue, unsigned int *acclist, unsigned int qcap, int ngroups, volatile int *run_flag, volatile int *progress) {
+           unsigned int *queue, unsigned int *acclist, unsigned int qcap, int ngroups, unsigned int spec16, volatile int *run_flag, volatile int *progress) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MjShared &S = *reinterpret_cast<MjShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -382,7 +382,7 @@ k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const Stenci
                     for (int j = 0; j < njobs; j++) if ((j & gmask) == A && S.live[j]) atomicOr(&S.job[j].ctrl[JC_FLAGS + (S.iter[j] & 3)], 2u);   // morph.cu:1390 (m_cb)
             }
             // speculative line search only while most warps would otherwise idle (uniform over the grid; results do not depend on it)
-            const bool spec = qn * 16u <= 6u * nwarps;
+            const bool spec = qn * 16u <= spec16 * nwarps;
             if (tracer) { tr[5] += 1; tr[6] += qn; }
             while (e < qn) {
                 unsigned e_next = 0;                                      // requested now, needed when this pixel is done
@@ -422,6 +422,7 @@ static MjCfg g_mj_cfg[64];
 static std::mutex g_mj_mu;
 static int g_mj_div = 32;            // VMORPH_MJ_DIV: candidate pixels per CTA that decide the grid size of small launches
 static int g_mj_groups = 1;          // VMORPH_MJ_GROUPS: 2 = two job groups half a round apart (see k_sweep_mj)
+static int g_mj_spec = 6;            // VMORPH_MJ_SPEC: speculative line search while queued pixels <= this / 16 of the grid's warps
 
 void sweep_mj_reload_hooks() {
     std::lock_guard<std::mutex> lock(g_mj_mu);
@@ -429,6 +430,8 @@ void sweep_mj_reload_hooks() {
     g_mj_div = (e && atoi(e) > 0) ? atoi(e) : 32;
     e = getenv("VMORPH_MJ_GROUPS");
     g_mj_groups = (e && atoi(e) == 2) ? 2 : 1;
+    e = getenv("VMORPH_MJ_SPEC");
+    g_mj_spec = (e && atoi(e) >= 0) ? atoi(e) : 6;
 }
 
 cudaError_t sweep_mj_trace(unsigned long long *out8, int reset) {
@@ -448,7 +451,7 @@ cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_hos
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return e;
     if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
-    int per_sm, div, ngroups;
+    int per_sm, div, ngroups; unsigned spec16;
     {
         std::lock_guard<std::mutex> lock(g_mj_mu);
         MjCfg &cfg = g_mj_cfg[device];
@@ -460,7 +463,7 @@ cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_hos
             if (cfg.per_sm < 1) return cudaErrorLaunchOutOfResources;
             cfg.init = true;
         }
-        per_sm = cfg.per_sm; div = g_mj_div; ngroups = g_mj_groups;
+        per_sm = cfg.per_sm; div = g_mj_div; ngroups = g_mj_groups; spec16 = (unsigned)g_mj_spec;
     }
     if (sm_budget <= 0 || sm_budget > sm_count) sm_budget = sm_count;
     // grid: enough warps for the candidate pixels of one round, at most the launch's share of the GPU (every CTA must be
@@ -470,7 +473,7 @@ cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_hos
     long long want = (cands + div - 1) / div;
     int grid = (int)(want < 4 ? 4 : want);
     if (grid > sm_budget * per_sm) grid = sm_budget * per_sm;
-    void *args[] = {(void *)&jobs_dev, (void *)&njobs, (void *)&P, (void *)&st, (void *)&gctrl, (void *)&queue, (void *)&acclist, (void *)&qcap, (void *)&ngroups, (void *)&run_flag, (void *)&progress};
+    void *args[] = {(void *)&jobs_dev, (void *)&njobs, (void *)&P, (void *)&st, (void *)&gctrl, (void *)&queue, (void *)&acclist, (void *)&qcap, (void *)&ngroups, (void *)&spec16, (void *)&run_flag, (void *)&progress};
     count_launch();
     return cudaLaunchCooperativeKernel((const void *)k_sweep_mj, dim3(grid), dim3(MJ_NW * 32), args, sizeof(MjShared), stream);
 }
