@@ -278,7 +278,7 @@ def roofline_objects(px, upd, sweep_ms, sweep_n, busy_ms, dev_ms, clocks, worklo
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get(workload)
-    roof = {"bound": "hbm", "kernel": "k_sweep (optimizer sweep, one persistent launch per level x frame)",
+    roof = {"bound": "hbm", "kernel": "optimizer sweep: k_sweep_mj (videos: one persistent multi-job launch per wavefront tick) / k_sweep (image pairs: one per level)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": a_bytes, "avg_launch_ms": a_ms,
             "launches_timed": int(sweep_n),
@@ -440,15 +440,15 @@ def run_ours_video(args):
     sw1, nl1 = m.sweep_time_ms()
     sweep_ms, sweep_n = sw1 - sw0, nl1 - nl0
     upd, busy_ms = m.attempted_updates - upd0, m.sweep_busy_ms - busy0
-    # per level (this rank's launches of the timed steps): frames, iterations, sweep ms, attempted updates, and the average
-    # number of active pixels per executed colour round and tile -- where the time goes and how sparse the rounds are
+    # per level (this rank's jobs of the timed steps): frames, iterations, attempted updates and updates per pixel-iteration
+    # (a pixel is visited 2.83 times per iteration on average: 2.83 would mean every visit is an active pixel)
     per_level = {}
-    ms_l, up_l = m.ms_log()[nlog0:], m.updates_log()[nlog0:]
-    for (lvl, frm, it), ms, u in zip(log, ms_l, up_l):
-        a = per_level.setdefault(int(lvl), [0, 0, 0.0, 0.0])
-        a[0] += 1; a[1] += int(it); a[2] += float(ms); a[3] += float(u)
-    per_level = {str(k): {"launches": v[0], "iterations": v[1], "sweep_ms": round(v[2], 1), "attempted_updates": v[3],
-                          "updates_per_pixel_iter": v[3] / max(1.0, dims[k][0] * dims[k][1] * v[1])} for k, v in sorted(per_level.items())}
+    up_l = m.updates_log()[nlog0:]
+    for (lvl, frm, it), u in zip(log, up_l):
+        a = per_level.setdefault(int(lvl), [0, 0, 0.0])
+        a[0] += 1; a[1] += int(it); a[2] += float(u)
+    per_level = {str(k): {"frames": v[0], "iterations": v[1], "attempted_updates": v[2],
+                          "updates_per_pixel_iter": v[2] / max(1.0, dims[k][0] * dims[k][1] * v[1])} for k, v in sorted(per_level.items())}
     # the result every later stage uses: level-1 field checksum (must equal the one-GPU run's, printed in config)
     vec_pin = torch.empty((d, h, w, 2), dtype=torch.float32).pin_memory()
     checksum = None
@@ -555,6 +555,10 @@ def run_ours_video(args):
             out["qpath"] = qpath
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline_video(args, V, vm, local)
+        if world == 1 and args.cfg5_frames > 0:
+            del m, pyr, flush
+            torch.cuda.empty_cache()
+            out["cfg5_probe"] = cfg5_probe(vm, local, args.cfg5_frames)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -580,6 +584,45 @@ def cpu_baseline_video(args, V, vm, device):
             "sample": f"the middle {S['d']} frames of the video run as a {S['d']}-frame video (every level, full iteration budget); pyramid build not timed",
             "parity_max_dv_px": float(np.abs(vg - vo).max()), "parity_iteration_logs_equal": same_log,
             "parity_note": "GPU path (Pyramid::build on the GPU + optimiser) vs the oracle on the same sample, level-0 vectors"}
+
+
+def cfg5_probe(vm, device, frames):
+    """BASELINE.json configs[4] (3840x2160 x 240) does not fit the bench's time budget; this probe runs the same shape with
+    `frames` frames in the memory plan the full video needs -- a WINDOW of 4 optimizer-state pages per level instead of one
+    per frame -- and states the bytes of the full 240-frame run."""
+    import torch
+    from videomorphing_b200 import synth
+    w, h = 3840, 2160
+    v0, v1, flows, _ = synth.video_pair_shift(w, h, frames, 5001, 5002, 16.0)
+    free0, total = torch.cuda.mem_get_info(device)
+    old = os.environ.get("VMORPH_ARENA_SLOTS")
+    os.environ["VMORPH_ARENA_SLOTS"] = "4"
+    try:
+        pyr = vm.Pyramid(device)
+        t0 = time.perf_counter(); n = pyr.build(v0, v1, flows, voxel_cap=1 << 62); tb = time.perf_counter() - t0
+        m = vm.Morph(vm.Parameters(), pyr)
+        m.run()                                                        # warm-up (allocates the window arenas)
+        px0 = m.executed_pixel_iters
+        t0 = time.perf_counter(); m.run(); torch.cuda.synchronize(); tr = time.perf_counter() - t0
+        px = m.executed_pixel_iters - px0
+        free1, _ = torch.cuda.mem_get_info(device)
+        vec = m.get_vectors()
+        levels = [[pyr.info(l)["w"], pyr.info(l)["h"], pyr.info(l)["d"]] for l in range(1, n)]
+        m.close(); pyr.close()
+    finally:
+        if old is None:
+            os.environ.pop("VMORPH_ARENA_SLOTS", None)
+        else:
+            os.environ["VMORPH_ARENA_SLOTS"] = old
+    px1 = ((w + 31) // 32 * 32) * h
+    gb = lambda x: round(x / 2 ** 30, 1)
+    full = {"frames": 240, "gray_images_GiB": gb(2 * 4 * px1 * 240 * 4 / 3), "flows_GiB": gb(4 * 8 * px1 * 240 * 4 / 3), "v_GiB": gb(8 * px1 * 240 * 4 / 3),
+            "state_every_frame_GiB": gb(72 * px1 * 240 * 4 / 3), "state_window_of_4_pages_GiB": gb(72 * px1 * 4 * 4 / 3),
+            "note": "all levels (x 4/3); with the window the 240-frame video needs ~127 GiB of images, flows and v + 3 GiB of state on a 180 GB B200"}
+    return {"workload": f"3840x2160 video pair x {frames} frames (integer-shift synthetic video), voxel cap lifted, state window of 4 pages per level",
+            "levels": levels, "build_s": tb, "optimize_s": tr, "mpixel_iters_per_s": px / tr / 1e6, "pixel_iters": px,
+            "device_GiB_used_by_the_probe": gb(free0 - free1), "result_checksum_sum_abs_v": float(np.abs(vec).sum(dtype=np.float64)),
+            "memory_plan_240_frames": full}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm: image pairs
@@ -711,6 +754,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="video workloads: cap on the timed end-to-end steps (0 = as many as --steps)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="video workloads: frames of the CPU sample (default 4 for cpu_baseline; by time budget for --impl reference)")
     ap.add_argument("--cpu-seconds", type=float, default=25.0, help="image-pair workloads: bound of the cpu_baseline sample")
+    ap.add_argument("--cfg5-frames", type=int, default=16, help="video workloads, one GPU: frames of the 3840x2160 probe reported as cfg5_probe (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     args = ap.parse_args()

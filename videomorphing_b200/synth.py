@@ -154,6 +154,26 @@ def video_pair(w, h, d, seed_img, seed_warp, amp, vel=1.5, wobble=1.0):
     return v0, v1, (f, f.copy(), b, b.copy()), field[64:64 + h, 64:64 + w]
 
 
+def video_pair_shift(w, h, d, seed_img, seed_warp, amp, vel=2):
+    """A cheap large video pair (cfg5 probes): frame t = the base image shifted by vel * (t - d // 2) WHOLE pixels in x (plain
+    slicing, no interpolation), video 1 = the same motion of the warped base; flows are the exact constant shift (zero
+    for the last / first frame like UI/MdiEditor.cpp:1637-1641,1668-1672)."""
+    pad = vel * (d // 2 + 1)
+    base0 = _noise_image(w + 2 * pad, h, seed_img)
+    field = smooth_warp(w + 2 * pad, h, seed_warp, amp)
+    base1 = warp_image(base0, field)
+    to8 = lambda a: np.clip(np.rint(a), 0, 255).astype(np.uint8)
+    b0, b1 = to8(base0), to8(base1)
+    v0 = np.empty((d, h, w, 3), np.uint8); v1 = np.empty((d, h, w, 3), np.uint8)
+    for t in range(d):
+        o = pad - vel * (t - d // 2)                     # content moves by +vel px per frame
+        v0[t] = b0[:, o:o + w]; v1[t] = b1[:, o:o + w]
+    f = np.zeros((d, h, w, 2), np.float32); b = np.zeros((d, h, w, 2), np.float32)
+    f[:-1, ..., 0] = vel
+    b[1:, ..., 0] = -vel
+    return v0, v1, (f, f, b, b), field[:, pad:pad + w]
+
+
 CONFIGS = {
     # name: (w, h, d, seed_img, seed_warp, amp)
     "cfg1": (256, 256, 1, 1001, 1002, 6.0),
