@@ -618,7 +618,7 @@ def cfg5_probe(vm, device, frames):
     gb = lambda x: round(x / 2 ** 30, 1)
     full = {"frames": 240, "gray_images_GiB": gb(2 * 4 * px1 * 240 * 4 / 3), "flows_GiB": gb(4 * 8 * px1 * 240 * 4 / 3), "v_GiB": gb(8 * px1 * 240 * 4 / 3),
             "state_every_frame_GiB": gb(72 * px1 * 240 * 4 / 3), "state_window_of_4_pages_GiB": gb(72 * px1 * 4 * 4 / 3),
-            "note": "all levels (x 4/3); with the window the 240-frame video needs ~127 GiB of images, flows and v + 3 GiB of state on a 180 GB B200"}
+            "note": "all levels (x 4/3); with the window the 240-frame video needs ~119 GiB of images, flows and v + 3 GiB of state on a 180 GB B200"}
     return {"workload": f"3840x2160 video pair x {frames} frames (integer-shift synthetic video), voxel cap lifted, state window of 4 pages per level",
             "levels": levels, "build_s": tb, "optimize_s": tr, "mpixel_iters_per_s": px / tr / 1e6, "pixel_iters": px,
             "device_GiB_used_by_the_probe": gb(free0 - free1), "result_checksum_sum_abs_v": float(np.abs(vec).sum(dtype=np.float64)),
