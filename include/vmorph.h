@@ -95,6 +95,11 @@ typedef struct vm_tracks {
 } vm_tracks;
 int vm_params_parse_xml(const char *path, vm_params *out, vm_tracks *tracks_out);
 void vm_tracks_free(vm_tracks *t);
+/* MdiEditor::WriteXmlFile (UI/MdiEditor.cpp:751-1040), the settings.xml part: stage (MdiEditor's thread_flag), weights, the
+ * point tracks and connections in the reference's token format (every track / group closed by an all -1 tuple, num = key
+ * points of both images), boundary lock, debug parameters; numbers formatted like QString::sprintf("%d" / "%f").
+ * tracks may be NULL (no points).  The frame export (PNG / avconv) next to it is video I/O and not part of this path. */
+int vm_params_write_xml(const char *path, const vm_params *prm, const vm_tracks *tracks, int stage);
 
 /* ---- Pyramid (Pyramid.h:14-49; Pyramid::build pyramid.cu:166-485) ---- */
 int vm_pyramid_create(int device, vm_pyramid **out);

@@ -68,3 +68,36 @@ def test_errors(tmp_path):
     p.write_text("<notaproject/>")
     with pytest.raises(vm._lib.VmError):
         api.parse_config_xml(str(p))
+
+
+def test_writer_produces_the_reference_format_and_round_trips(tmp_path):
+    """vm_params_write_xml = the settings.xml part of MdiEditor::WriteXmlFile (UI/MdiEditor.cpp:751-1040): the attribute values
+    are the token strings the reference's sprintf calls produce (checked against the helper above, which follows them), num
+    counts the key points of both images, and reader(writer(x)) == x."""
+    lp = [[(10, 20, 0, 1, 1.0), (11, 21, 1, 0, 0.5)], [(40, 50, 0, 1, 0.25)]]
+    rp = [[(12, 22, 0, 1, 1.0), (13, 23, 1, 0, 0.75)], [(44, 55, 0, 1, 1.0)]]
+    cnt = [[(0, 0, 0, 0), (0, 1, 0, 1)], [(1, 0, 1, 0)]]
+    prm = vm.Parameters(w_ssim=100.0, w_tps=0.05, w_ui=100000.0, w_temp=10.0, ssim_clamp=0.0, max_iter=800, max_iter_drop_factor=2.0, eps=0.01,
+                        start_res=8, bcond=vm.BCOND_BORDER)
+    prm.lp, prm.rp, prm.cnt = lp, rp, cnt
+    out = tmp_path / "written.xml"
+    api.write_config_xml(str(out), prm, stage=3)
+    text = out.read_text()
+    want = open(_write(tmp_path, lp, rp, cnt)).read()
+    import re
+    attrs = lambda s: dict(re.findall(r'(\w+)="([^"]*)"', s))
+    a, b = attrs(text), attrs(want)
+    assert a.pop("num") == "4" and b.pop("num") == "4"               # key points (p.w == 1) of image1 + image2
+    assert a == b                                                     # every attribute value, token for token
+    assert text.startswith("<?xml version='1.0'?>\n<project>\n    <stage stage=\"3\"/>")
+    back = api.parse_config_xml(str(out))
+    assert back.lp == lp and back.rp == rp and back.cnt == cnt
+    for k in ("w_ssim", "w_tps", "w_ui", "w_temp", "ssim_clamp", "max_iter", "max_iter_drop_factor", "eps", "start_res", "bcond"):
+        assert getattr(back, k) == pytest.approx(getattr(prm, k)), k
+    # no points at all, corner lock
+    q = vm.Parameters(bcond=vm.BCOND_CORNER)
+    api.write_config_xml(str(tmp_path / "empty.xml"), q, stage=5)
+    r = api.parse_config_xml(str(tmp_path / "empty.xml"))
+    assert r.lp == [] and r.rp == [] and r.cnt == [] and r.bcond == vm.BCOND_CORNER and r.max_iter == q.max_iter
+    with pytest.raises(vm._lib.VmError):
+        api.write_config_xml(str(tmp_path / "no_such_dir" / "x.xml"), q)

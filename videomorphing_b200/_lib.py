@@ -37,7 +37,7 @@ class VmTracks(C.Structure):
 
 # every symbol include/vmorph.h declares (tests/test_cabi.py checks the list against the header)
 EXPORTS = [
-    "vm_last_error", "vm_device_count", "vm_version", "vm_params_default", "vm_params_parse_xml", "vm_tracks_free",
+    "vm_last_error", "vm_device_count", "vm_version", "vm_params_default", "vm_params_parse_xml", "vm_params_write_xml", "vm_tracks_free",
     "vm_pyramid_create", "vm_pyramid_destroy", "vm_level_schedule", "vm_pyramid_alloc", "vm_pyramid_build",
     "vm_pyramid_num_levels", "vm_pyramid_level_info", "vm_level_get", "vm_level_set", "vm_morph_create", "vm_morph_destroy",
     "vm_morph_set_tracks", "vm_morph_set_constraints", "vm_morph_run", "vm_morph_progress", "vm_morph_executed_pixel_iters",
@@ -65,6 +65,7 @@ def load():
     L.vm_kernel_launch_count.restype = C.c_uint64
     L.vm_params_default.argtypes = [C.POINTER(VmParams)]
     L.vm_params_parse_xml.argtypes = [C.c_char_p, C.POINTER(VmParams), C.POINTER(VmTracks)]
+    L.vm_params_write_xml.argtypes = [C.c_char_p, C.POINTER(VmParams), C.POINTER(VmTracks), i32]
     L.vm_tracks_free.argtypes = [C.POINTER(VmTracks)]
     L.vm_pyramid_create.argtypes = [i32, C.POINTER(vp)]
     L.vm_pyramid_destroy.argtypes = [vp]

@@ -85,7 +85,9 @@ class Pyramid:
         return check(self.L.vm_pyramid_alloc(self.h, w, h, d, start_res, voxel_cap))
 
     def build(self, video0, video1, flows=None, start_res=8, voxel_cap=REFERENCE_VOXEL_CAP, stream=None):
-        """Pyramid::build (Pyramid.h:28): video0/1 (d,h,w,3) uint8 RGB; flows = (f0,f1,b0,b1) each (d,h,w,2) float32."""
+        """Pyramid::build (Pyramid.h:28): video0/1 (d,h,w,3) uint8 frames byte for byte as the reference's cv::Mat holds them
+        (channel 0 = blue: the luma weights .299/.587/.114 go to channels 0/1/2 like image::load + store_gray, pyramid.cu:267-280;
+        swap channels 0 and 2 of true RGB data); flows = (f0,f1,b0,b1) each (d,h,w,2) float32."""
         v0 = np.ascontiguousarray(video0, np.uint8)
         v1 = np.ascontiguousarray(video1, np.uint8)
         d, h, w, _ = v0.shape
@@ -372,6 +374,31 @@ def parse_config_xml(path):
     finally:
         L.vm_tracks_free(C.byref(tr))
     return prm
+
+
+def write_config_xml(path, prm, stage=3):
+    """MdiEditor::WriteXmlFile (UI/MdiEditor.cpp:751-1040), the settings.xml part, for a Parameters with lp / rp / cnt in the
+    layout parse_config_xml returns."""
+    from ._lib import VmConnect, VmTracks
+    tr = VmTracks()
+    def flat(tracks):
+        lens = (C.c_int32 * max(1, len(tracks)))(*[len(t) for t in tracks])
+        pts = [p for t in tracks for p in t]
+        arr = (VmConp * max(1, len(pts)))()
+        for k, p in enumerate(pts):
+            arr[k] = VmConp(int(p[0]), int(p[1]), int(p[2]), int(p[3]), float(p[4]))
+        return lens, arr
+    ll, la = flat(prm.lp)
+    rl, ra = flat(prm.rp)
+    gl = (C.c_int32 * max(1, len(prm.cnt)))(*[len(g) for g in prm.cnt])
+    cs = [c for g in prm.cnt for c in g]
+    ca = (VmConnect * max(1, len(cs)))()
+    for k, c in enumerate(cs):
+        ca[k] = VmConnect(int(c[0]), int(c[1]), int(c[2]), int(c[3]))
+    tr.n_left, tr.n_right, tr.n_groups = len(prm.lp), len(prm.rp), len(prm.cnt)
+    tr.left_len, tr.right_len, tr.group_len = ll, rl, gl
+    tr.left, tr.right, tr.connects = la, ra, ca
+    check(_lib.load().vm_params_write_xml(str(path).encode(), C.byref(prm._p), C.byref(tr), int(stage)))
 
 
 def quadratic_path_frames(vectors, max_iter=10000, tol=1e-12, device=0, stream=None):

@@ -359,10 +359,14 @@ int vm_morph_create(const vm_params *prm, vm_pyramid *pyr, volatile int *run_fla
         m->no_wavefront = wv && atoi(wv) == 0;
     }
     if (run_flag) {
-        if (cudaHostRegister((void *)run_flag, sizeof(int), cudaHostRegisterMapped) == cudaSuccess) {
+        // the sweep kernels poll the caller's flag through mapped host memory once per iteration (m_cb, morph.cu:1390); a
+        // flag that cannot be mapped would silently turn cancellation off, so that is an error
+        cudaError_t er = cudaHostRegister((void *)run_flag, sizeof(int), cudaHostRegisterMapped);
+        if (er == cudaSuccess) {
             m->run_flag_registered = true;
-            if (cudaHostGetDevicePointer((void **)&m->run_flag_dev, (void *)run_flag, 0) != cudaSuccess) m->run_flag_dev = nullptr;
-        } else cudaGetLastError();
+            er = cudaHostGetDevicePointer((void **)&m->run_flag_dev, (void *)run_flag, 0);
+        }
+        if (er != cudaSuccess) { cudaGetLastError(); if (m->run_flag_registered) cudaHostUnregister((void *)run_flag); delete m; return cuda_fail(er, "mapping run_flag for the device"); }
     }
     cudaError_t e = cudaHostAlloc((void **)&m->progress_host, 64, cudaHostAllocMapped);
     if (e == cudaSuccess) { m->progress_host[0] = 0; m->progress_host[1] = 0; e = cudaHostGetDevicePointer((void **)&m->progress_dev, m->progress_host, 0); }
@@ -671,6 +675,7 @@ static int collect_log(vm_morph *m, size_t /*from*/, cudaStream_t s) {
     if (hi >= lo) m->sweep_busy_ms += hi - lo;
     m->seqs.clear();
     if (m->progress_host) { m->progress_host[0] = 0; m->progress_host[1] = 0; }
+    if (!keep_running(m)) m->cancelled = true;            // the launches that were already enqueued stopped after one iteration each
     return VM_OK;
 }
 

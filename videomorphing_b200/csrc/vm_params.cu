@@ -1,4 +1,4 @@
-// vm_params.cu -- project settings reader (host code only).
+// vm_params.cu -- project settings reader and writer (host code only).
 //
 // parse_config_xml(Parameters&, const std::string&) (Algorithm/param_io.h:8) is stale GPUMorph code in the reference
 // (SURVEY R2); the live reader is MdiEditor::ReadXmlFile (UI/MdiEditor.cpp:566-749) for the schema written by
@@ -182,6 +182,63 @@ void vm_tracks_free(vm_tracks *t) {
     if (!t) return;
     free(t->left_len); free(t->right_len); free(t->group_len); free(t->left); free(t->right); free(t->connects);
     memset(t, 0, sizeof(*t));
+}
+
+
+// MdiEditor::WriteXmlFile (UI/MdiEditor.cpp:751-1040), the XML part: <stage>, <videos> (the four attribute values the
+// reference always writes; exporting the frames as PNGs / mp4s through avconv is video I/O and out of scope), <parameters>
+// with <weight>, <points> (image1 / image2 / connection / num), <boundary>, <debug>.  Numbers are formatted like
+// QString::sprintf("%d" / "%f"); every track / connection group is closed by an all -1 tuple; num counts the key points
+// (p.w == 1) of both images (MdiEditor.cpp:922,949,978).  QDomDocument::save(out, 4): four spaces per nesting level.
+int vm_params_write_xml(const char *path, const vm_params *prm, const vm_tracks *tr, int stage) {
+    if (!path || !prm) { set_error("vm_params_write_xml: null argument"); return VM_ERR_ARG; }
+    std::string img[2], con;
+    int counter = 0;
+    char num[64];
+    auto app = [&](std::string &dst, const char *fmt, double v, bool is_int) {
+        if (is_int) snprintf(num, sizeof(num), fmt, (int)v); else snprintf(num, sizeof(num), fmt, v);
+        dst += num;
+    };
+    if (tr) {
+        for (int side = 0; side < 2; side++) {
+            const int n = side ? tr->n_right : tr->n_left;
+            const int32_t *len = side ? tr->right_len : tr->left_len;
+            const vm_conp *pts = side ? tr->right : tr->left;
+            size_t o = 0;
+            for (int i = 0; i < n; i++) {
+                for (int j = 0; j < len[i]; j++, o++) {
+                    app(img[side], "%d ", pts[o].x, true); app(img[side], "%d ", pts[o].y, true); app(img[side], "%d ", pts[o].z, true);
+                    app(img[side], "%d ", pts[o].w, true); app(img[side], "%f ", pts[o].weight, false);
+                    if (pts[o].w == 1) counter++;
+                }
+                for (int k = 0; k < 4; k++) app(img[side], "%d ", -1, true);
+                app(img[side], "%f ", -1.0, false);
+            }
+        }
+        size_t o = 0;
+        for (int i = 0; i < tr->n_groups; i++) {
+            for (int j = 0; j < tr->group_len[i]; j++, o++) {
+                app(con, "%d ", tr->connects[o].li_track, true); app(con, "%d ", tr->connects[o].li_idx, true);
+                app(con, "%d ", tr->connects[o].ri_track, true); app(con, "%d ", tr->connects[o].ri_idx, true);
+            }
+            for (int k = 0; k < 4; k++) app(con, "%d ", -1, true);
+        }
+    }
+    FILE *f = fopen(path, "wb");
+    if (!f) { set_error("vm_params_write_xml: cannot open %s for writing", path); return VM_ERR_PARSE; }
+    fprintf(f, "<?xml version='1.0'?>\n<project>\n");
+    fprintf(f, "    <stage stage=\"%d\"/>\n", stage);
+    fprintf(f, "    <videos video1=\"\\video1.mp4\" video2=\"\\video2.mp4\" resample1=\"\\resample1.mp4\" resample2=\"\\resample2.mp4\"/>\n");
+    fprintf(f, "    <parameters>\n");
+    fprintf(f, "        <weight ssim=\"%f\" tps=\"%f\" ui=\"%f\" temp=\"%f\" ssimclamp=\"%f\"/>\n", prm->w_ssim, prm->w_tps, prm->w_ui, prm->w_temp, prm->ssim_clamp);
+    fprintf(f, "        <points image1=\"%s\" image2=\"%s\" connection=\"%s\" num=\"%d\"/>\n", img[0].c_str(), img[1].c_str(), con.c_str(), counter);
+    fprintf(f, "        <boundary lock=\"%d\"/>\n", prm->bcond == VM_BCOND_CORNER ? 1 : (prm->bcond == VM_BCOND_BORDER ? 2 : 0));
+    fprintf(f, "        <debug iternum=\"%d\" dropfactor=\"%f\" eps=\"%f\" startres=\"%d\"/>\n", prm->max_iter, prm->max_iter_drop_factor, prm->eps, prm->start_res);
+    fprintf(f, "    </parameters>\n</project>\n");
+    bool ok = ferror(f) == 0;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { set_error("vm_params_write_xml: write to %s failed", path); return VM_ERR_PARSE; }
+    return VM_OK;
 }
 
 }  // extern "C"

@@ -169,7 +169,7 @@ def wavefront_plan(depths, dims, max_iters, world):
             nonlocal best
             if left == 1:
                 cand = acc + [levels[start:]]
-                cost = max(_group_cost(c, dims, max_iters) for c in cand)
+                cost = sorted((_group_cost(c, dims, max_iters) for c in cand), reverse=True)   # most expensive group first, then the next ...
                 if best is None or cost < best[0]:
                     best = (cost, cand)
                 return
