@@ -428,14 +428,15 @@ def test_qpath_resident_and_streaming_kernels_agree(vm, oracle_lib, w, h, max_it
     np.testing.assert_array_equal(q_auto, qo)
 
 
-@pytest.mark.parametrize("sweep,wavefront", [("tile", "1"), ("mj", "1"), ("mj", "0")])
-def test_both_sweep_kernels_and_the_wavefront_equal_the_oracle(vm, oracle_lib, sweep, wavefront, monkeypatch):
+@pytest.mark.parametrize("sweep,wavefront,memo", [("tile", "1", "0"), ("mj", "1", "0"), ("mj", "0", "0"), ("mj", "1", "1")])
+def test_both_sweep_kernels_and_the_wavefront_equal_the_oracle(vm, oracle_lib, sweep, wavefront, memo, monkeypatch):
     """VMORPH_SWEEP=tile: one tile per CTA cluster, state replicated in shared memory (vm_sweep.cu); =mj: several frames in
     lock-step, state in L2, one global pixel queue (vm_sweep_mj.cu); VMORPH_WAVEFRONT=0: a video level by level instead of
     the direction x level wavefront.  Every combination gives the oracle's bits and the reference-ordered iteration log."""
     from videomorphing_b200 import synth
     monkeypatch.setenv("VMORPH_SWEEP", sweep)
     monkeypatch.setenv("VMORPH_WAVEFRONT", wavefront)
+    monkeypatch.setenv("VMORPH_MJ_MEMO", memo)                # 1: evaluations whose inputs provably did not change are skipped (exact)
     # image pair: UI constraints, locked border (BCOND_BORDER), several tiles, a partial tile row
     rgb0, rgb1, field = synth.image_pair(150, 70, 250, 270, 3.0)
     cons = synth.point_pairs(6, 150, 70, 7, field, margin=6)

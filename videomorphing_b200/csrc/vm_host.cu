@@ -691,12 +691,13 @@ static int enqueue_jobs(vm_morph *m, const JobSpec *js, int n, cudaStream_t s) {
     size_t cand = 8192;                                   // entries per job group (even / odd jobs): its candidates + room for the first speculative read
     for (int k = 0; k < n; k++) cand += (size_t)sweep_num_tiles(p->lv[js[k].level].w, p->lv[js[k].level].h) * 256;
     bool grow = m->mj_ctrl.bytes < 4 * (gw + MJ_MAX_JOBS * jw) || m->mj_jobs.bytes < sizeof(SweepJob) * MJ_MAX_JOBS || m->mj_queue.bytes < 8 * cand || m->mj_acc.bytes < 8 * cand;
-    for (int k = 0; k < n; k++) grow = grow || m->mj_scratch[k].bytes < 32 * (size_t)p->lv[js[k].level].ps;
+    auto scratch_bytes = [&](const Level &L) { return 36 * (size_t)L.ps + 4 * (size_t)((L.w + 7) / 8) * ((L.h + 7) / 8) + 64; };
+    for (int k = 0; k < n; k++) grow = grow || m->mj_scratch[k].bytes < scratch_bytes(p->lv[js[k].level]);
     if (grow) {
         VM_CUDA(cudaDeviceSynchronize());
         VM_CUDA(m->mj_ctrl.ensure(4 * (gw + MJ_MAX_JOBS * jw))); VM_CUDA(m->mj_jobs.ensure(sizeof(SweepJob) * MJ_MAX_JOBS));
         VM_CUDA(m->mj_queue.ensure(8 * cand)); VM_CUDA(m->mj_acc.ensure(8 * cand));
-        for (int k = 0; k < n; k++) VM_CUDA(m->mj_scratch[k].ensure(32 * (size_t)p->lv[js[k].level].ps));
+        for (int k = 0; k < n; k++) VM_CUDA(m->mj_scratch[k].ensure(scratch_bytes(p->lv[js[k].level])));
     }
     if (seq0 == 0) {                                      // time origin of this call's launch intervals
         if (!m->ev_base) VM_CUDA(cudaEventCreate(&m->ev_base));
@@ -716,9 +717,12 @@ static int enqueue_jobs(vm_morph *m, const JobSpec *js, int n, cudaStream_t s) {
         J.ctrl = ctrl + gw + (size_t)k * jw;
         unsigned char *sc = m->mj_scratch[k].as<unsigned char>();
         const size_t ps = (size_t)L.ps;
-        J.stamp = reinterpret_cast<unsigned *>(sc); J.sd = reinterpret_cast<float2 *>(sc + 4 * ps); J.sdm = reinterpret_cast<float2 *>(sc + 12 * ps);
-        J.sdv = reinterpret_cast<float2 *>(sc + 20 * ps); J.sdc = reinterpret_cast<float *>(sc + 28 * ps);
-        VM_CUDA(cudaMemsetAsync(J.stamp, 0, 4 * ps, s));
+        J.stamp = reinterpret_cast<unsigned *>(sc); J.evalr = reinterpret_cast<unsigned *>(sc + 4 * ps); J.bstamp = reinterpret_cast<unsigned *>(sc + 8 * ps);
+        J.bw = (L.w + 7) / 8; J.pad2 = 0;
+        const size_t nb = 4 * (size_t)J.bw * ((L.h + 7) / 8), off = (8 * ps + nb + 63) / 64 * 64;
+        J.sd = reinterpret_cast<float2 *>(sc + off); J.sdm = reinterpret_cast<float2 *>(sc + off + 8 * ps);
+        J.sdv = reinterpret_cast<float2 *>(sc + off + 16 * ps); J.sdc = reinterpret_cast<float *>(sc + off + 24 * ps);
+        VM_CUDA(cudaMemsetAsync(J.stamp, 0, 8 * ps + nb, s));                     // stamps, evaluation rounds, block stamps
         m->seqs.push_back({js[k].level, js[k].frame, (double)L.w * L.h, js[k].max_iter, k == 0 ? seq0 : -1});
     }
     VM_CUDA(cudaMemcpyAsync(m->mj_jobs.p, host, sizeof(SweepJob) * n, cudaMemcpyHostToDevice, s));

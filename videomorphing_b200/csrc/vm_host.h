@@ -97,6 +97,9 @@ struct SweepJob {
     int seq, pad;
     unsigned int *ctrl;                   // per-job control words
     unsigned int *stamp;                  // per pixel: round in which the pixel last moved
+    unsigned int *evalr;                  // per pixel: round of its last evaluation that ended without a move (0: none yet)
+    unsigned int *bstamp;                 // per 8x8 block of pixels: last round in which a pixel of the block moved
+    int bw, pad2;                         // blocks per row
     float2 *sd, *sdm, *sdv;               // per pixel: accepted step and SSIM-sum deltas of that round
     float *sdc;
 };

@@ -217,7 +217,7 @@ __device__ __forceinline__ void mj_gather(const MjShared &S, const KParams &P, u
 
 // One active pixel of the queue: the per-pixel step of morph.cu:1030-1083 by one warp, the commit of the pixel's own cells
 // and the deltas for the gather.
-__device__ __forceinline__ void mj_pixel(MjShared &S, const KParams &P, unsigned entry, unsigned rid, bool spec, unsigned int *acc_count,
+__device__ __forceinline__ void mj_pixel(MjShared &S, const KParams &P, unsigned entry, unsigned rid, bool spec, bool memo, unsigned int *acc_count,
                                          unsigned int *acclist, int lane) {
     const int j = (int)(entry >> 27);
     const SweepJob &J = S.job[j];
@@ -228,7 +228,26 @@ __device__ __forceinline__ void mj_pixel(MjShared &S, const KParams &P, unsigned
     unsigned int *mword = L.impmask + (bcy + 1) * L.irs + (bcx + 1);
     const unsigned mbit = 1u << ((px - bcx * 5) + (py - bcy * 5) * 5);
     bool ok = false;
-    if (!(entry & MJ_LOCKED)) {
+    // Memoisation (exact): the outcome of optimize_pixel is a deterministic function of v / luma / ui.b / tps.b of the pixel,
+    // v of its 8 neighbours and the SSIM sums of its 25 windows -- all of which only change when a pixel within 4 px
+    // (Chebyshev) moves.  If the pixel's last evaluation ended without a move and no pixel of the 8x8 blocks that cover its
+    // 9x9 surroundings has moved since (block stamps are conservative), the evaluation would repeat that result: no
+    // move, own improving-mask bit cleared.  The reference re-evaluates such pixels for as long as a neighbour's mask bit
+    // stays set (on the fine levels > 99 % of the queued pixels end without a move).  Measured: only ~13 % of the fine-level
+    // evaluations are repeats of this kind -- the mask already retires a pixel after one evaluation without a move nearby.
+    bool known_still = false;
+    if (!(entry & MJ_LOCKED) && memo) {
+        const unsigned ev = __ldcg(J.evalr + pix);
+        if (ev) {
+            const int bx0 = max(px - 4, 0) >> 3, bx1 = min(px + 4, L.w - 1) >> 3, by0 = max(py - 4, 0) >> 3, by1 = min(py + 4, L.h - 1) >> 3;
+            unsigned last = __ldcg(J.bstamp + by0 * J.bw + bx0);
+            last = max(last, __ldcg(J.bstamp + by0 * J.bw + bx1));
+            last = max(last, __ldcg(J.bstamp + by1 * J.bw + bx0));
+            last = max(last, __ldcg(J.bstamp + by1 * J.bw + bx1));
+            known_still = last < ev;
+        }
+    }
+    if (!(entry & MJ_LOCKED) && !known_still) {
         PixelEval E;
         E.I0 = L.img0; E.I1 = L.img1; E.W = L.w; E.H = L.h; E.px = px; E.py = py; E.lane = lane;
         E.v = __ldcg(L.v + pix); E.old_luma = __ldcg(L.luma + pix);
@@ -282,12 +301,16 @@ __device__ __forceinline__ void mj_pixel(MjShared &S, const KParams &P, unsigned
                 L.ui_b[pix] = ub;
                 L.v[pix] = newv;
                 acclist[atomicAdd(acc_count, 1u)] = entry;
+                atomicMax(J.bstamp + (py >> 3) * J.bw + (px >> 3), rid);
                 atomicOr(mword, mbit);
                 if (!S.voted[j]) { S.voted[j] = 1; atomicOr(&J.ctrl[JC_FLAGS + (S.iter[j] & 3)], 1u); }
             }
         }
     }
-    if (!ok && lane == 0) atomicAnd(mword, ~mbit);                       // had a mask index, did not move (morph.cu:1328-1332)
+    if (!ok && lane == 0) {
+        atomicAnd(mword, ~mbit);                                         // had a mask index, did not move (morph.cu:1328-1332)
+        if (!(entry & MJ_LOCKED) && !known_still) J.evalr[pix] = rid;    // evaluated in this round, no move
+    }
 }
 
 // End of a round of job j: next colour / offset step / iteration (morph.cu:1305-1309, 1382-1390); every CTA computes the same.
@@ -322,7 +345,7 @@ __device__ __forceinline__ void mj_advance(MjShared &S, int j, volatile int *pro
 // default is one group: every phase below then serves all jobs.
 __global__ void __launch_bounds__(MJ_NW * 32, 1)
 k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const StencilTables *__restrict__ st, unsigned int *gctrl,
-           unsigned int *queue, unsigned int *acclist, unsigned int qcap, int ngroups, unsigned int spec16, volatile int *run_flag, volatile int *progress) {
+           unsigned int *queue, unsigned int *acclist, unsigned int qcap, int ngroups, unsigned int spec16, int memo_on, volatile int *run_flag, volatile int *progress) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MjShared &S = *reinterpret_cast<MjShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -345,6 +368,7 @@ k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const Stenci
         S.iter[tid] = 0; S.step[tid] = s0; S.sp[tid] = 0; S.live[tid] = 1; S.voted[tid] = 0;
     }
     const int gmask = ngroups == 2 ? 1 : 0;                             // group of job j = j & gmask
+    const bool memo = memo_on != 0;
     if (tid == 0) { S.glive[0] = 1; S.glive[1] = (gmask && njobs > 1) ? 1 : 0; }
     __syncthreads();
     unsigned int epoch = 0, rnd[2] = {0u, 0u};
@@ -387,7 +411,7 @@ k_sweep_mj(const SweepJob *__restrict__ jobs, int njobs, KParams P, const Stenci
             while (e < qn) {
                 unsigned e_next = 0;                                      // requested now, needed when this pixel is done
                 if (lane == 0) e_next = nwarps + atomicAdd(&gctrl[GC_PULL + A * 2 + par], 1u);
-                mj_pixel(S, P, entry, rid, spec, &gctrl[GC_ACC + A * 2 + par], acclist + (size_t)A * qcap, lane);
+                mj_pixel(S, P, entry, rid, spec, memo, &gctrl[GC_ACC + A * 2 + par], acclist + (size_t)A * qcap, lane);
                 e = __shfl_sync(0xffffffffu, e_next, 0);
                 if (e < qn) entry = __ldcg(qA + e);
             }
@@ -422,6 +446,8 @@ static MjCfg g_mj_cfg[64];
 static std::mutex g_mj_mu;
 static int g_mj_div = 32;            // VMORPH_MJ_DIV: candidate pixels per CTA that decide the grid size of small launches
 static int g_mj_groups = 1;          // VMORPH_MJ_GROUPS: 2 = two job groups half a round apart (see k_sweep_mj)
+static int g_mj_memo = 0;            // VMORPH_MJ_MEMO=1: skip evaluations whose inputs provably did not change (exact; see mj_pixel).  Off by default:
+                                     // measured 2.96 -> 2.90 s on one GPU but +3 % per round on the latency-bound levels (profiles/r2_wavefront.md)
 static int g_mj_spec = 6;            // VMORPH_MJ_SPEC: speculative line search while queued pixels <= this / 16 of the grid's warps
 
 void sweep_mj_reload_hooks() {
@@ -430,6 +456,8 @@ void sweep_mj_reload_hooks() {
     g_mj_div = (e && atoi(e) > 0) ? atoi(e) : 32;
     e = getenv("VMORPH_MJ_GROUPS");
     g_mj_groups = (e && atoi(e) == 2) ? 2 : 1;
+    e = getenv("VMORPH_MJ_MEMO");
+    g_mj_memo = (e && atoi(e) == 1) ? 1 : 0;
     e = getenv("VMORPH_MJ_SPEC");
     g_mj_spec = (e && atoi(e) >= 0) ? atoi(e) : 6;
 }
@@ -451,7 +479,7 @@ cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_hos
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return e;
     if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
-    int per_sm, div, ngroups; unsigned spec16;
+    int per_sm, div, ngroups, memo_on; unsigned spec16;
     {
         std::lock_guard<std::mutex> lock(g_mj_mu);
         MjCfg &cfg = g_mj_cfg[device];
@@ -463,7 +491,7 @@ cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_hos
             if (cfg.per_sm < 1) return cudaErrorLaunchOutOfResources;
             cfg.init = true;
         }
-        per_sm = cfg.per_sm; div = g_mj_div; ngroups = g_mj_groups; spec16 = (unsigned)g_mj_spec;
+        per_sm = cfg.per_sm; div = g_mj_div; ngroups = g_mj_groups; spec16 = (unsigned)g_mj_spec; memo_on = g_mj_memo;
     }
     if (sm_budget <= 0 || sm_budget > sm_count) sm_budget = sm_count;
     // grid: enough warps for the candidate pixels of one round, at most the launch's share of the GPU (every CTA must be
@@ -473,7 +501,7 @@ cudaError_t launch_sweep_jobs(const SweepJob *jobs_dev, const SweepJob *jobs_hos
     long long want = (cands + div - 1) / div;
     int grid = (int)(want < 4 ? 4 : want);
     if (grid > sm_budget * per_sm) grid = sm_budget * per_sm;
-    void *args[] = {(void *)&jobs_dev, (void *)&njobs, (void *)&P, (void *)&st, (void *)&gctrl, (void *)&queue, (void *)&acclist, (void *)&qcap, (void *)&ngroups, (void *)&spec16, (void *)&run_flag, (void *)&progress};
+    void *args[] = {(void *)&jobs_dev, (void *)&njobs, (void *)&P, (void *)&st, (void *)&gctrl, (void *)&queue, (void *)&acclist, (void *)&qcap, (void *)&ngroups, (void *)&spec16, (void *)&memo_on, (void *)&run_flag, (void *)&progress};
     count_launch();
     return cudaLaunchCooperativeKernel((const void *)k_sweep_mj, dim3(grid), dim3(MJ_NW * 32), args, sizeof(MjShared), stream);
 }
