@@ -369,7 +369,11 @@ def run_ours_video(args):
     prm = vm.Parameters()
 
     def build():
-        _lib.check(L.vm_pyramid_build(pyr.h, vp(p_v0), vp(p_v1), vp(p_f), vp(p_f), vp(p_b), vp(p_b), w, h, d, 8, V["cap"], sh))
+        if world == 1:
+            _lib.check(L.vm_pyramid_build(pyr.h, vp(p_v0), vp(p_v1), vp(p_f), vp(p_f), vp(p_b), vp(p_b), w, h, d, 8, V["cap"], sh))
+        else:       # each rank uploads and resamples its frame block from the pinned buffers, NCCL all-gather of the blocks
+            vd.build_pyramid(pyr, p_v0.numpy(), p_v1.numpy(), (p_f.numpy(), p_f.numpy(), p_b.numpy(), p_b.numpy()), voxel_cap=V["cap"],
+                             device=local, stream=sh)
     build()
     m = vm.Morph(prm, pyr)
     m.set_constraints(*V["cons"])
@@ -496,7 +500,7 @@ def run_ours_video(args):
         e2e_step()
     _barrier(torch, dist, world)
     e2e_s = time.perf_counter() - t0
-    h2d = int(p_v0.numel() + p_v1.numel() + 2 * 4 * (p_f.numel() + p_b.numel()) + (p_e0.numel() + p_e1.numel() if nb else 0))
+    h2d = int((p_v0.numel() + p_v1.numel() + 2 * 4 * (p_f.numel() + p_b.numel())) * (nb / d if world > 1 else 1.0) + (p_e0.numel() + p_e1.numel() if nb else 0))
     d2h = int((vec_pin.numel() * 4 if rank == 0 else 0) + (out_pin.numel() if nb else 0))
 
     # ---------------- secondary figures (rank 0, local synchronisation only): render fps, QuadraticPath
@@ -542,7 +546,7 @@ def run_ours_video(args):
                        "frames_per_s_optimize_plus_render": d * e2e_steps / e2e_max,
                        "ms_build_optimize_extract_render_rank0": [1e3 * v / e2e_steps for v in e2e_parts],
                        "path": "vm_pyramid_build(host, pinned) -> optimise -> vm_morph_get_vectors(host) -> vm_morph_render_frames(host ext frames -> host RGB8), "
-                               "render sharded by frame over the ranks; wall clock"},
+                               "Pyramid::build and render sharded by frame over the ranks (build: frame blocks + NCCL all-gather); wall clock"},
                "gpu_launches": int(launches_all),
                "clocks": clocks,
                "roofline": roof, "roofline_fp32": roof32,

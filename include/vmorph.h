@@ -60,7 +60,8 @@ enum {
     VM_FIELD_SSIM_VALUE = 5, VM_FIELD_SSIM_COUNTER = 6, VM_FIELD_TPS_AXY = 7, VM_FIELD_TPS_B = 8, VM_FIELD_UI_AXY = 9,
     VM_FIELD_UI_B = 10, VM_FIELD_TEMP_REF = 11, VM_FIELD_TEMP_MASK = 12, VM_FIELD_IMPROVING_MASK = 13,
     VM_FIELD_IMG0 = 14, VM_FIELD_IMG1 = 15, VM_FIELD_F0 = 16, VM_FIELD_F1 = 17, VM_FIELD_B0 = 18, VM_FIELD_B1 = 19,
-    VM_FIELD_COUNT = 20
+    VM_FIELD_KEEP0 = 20, VM_FIELD_KEEP1 = 21,   /* linear-light planes (d,3,h,w) of the last level vm_pyramid_build_frames built */
+    VM_FIELD_COUNT = 22
 };
 
 /* Pyramid.h:60-66 + pyramid.cu:531-543 */
@@ -117,6 +118,16 @@ int vm_pyramid_alloc(vm_pyramid *p, int w, int h, int d, int start_res, int64_t 
  * optical flow (may all be NULL when d == 1).  Builds every level's gray images and flows on the GPU. */
 int vm_pyramid_build(vm_pyramid *p, const uint8_t *video0, const uint8_t *video1, const float *f0, const float *f1,
                      const float *b0, const float *b1, int w, int h, int d, int start_res, int64_t voxel_cap, void *stream);
+/* Frame-sharded Pyramid::build (pyramid.cu:267-403 are per-frame for the levels that keep every frame, the
+ * temporal halving of pyramid.cu:406-459 reads the neighbouring frames): vm_pyramid_build_frames allocates like
+ * vm_pyramid_build and builds frames [frame0, frame0 + nframes) of levels 1 .. K (K = return value, the levels with all d
+ * frames); the caller fills the other frames of those levels' VM_FIELD_IMG0 .. VM_FIELD_B1 and of level K's
+ * VM_FIELD_KEEP0 / VM_FIELD_KEEP1 (vm_level_dev_ptr; frames are contiguous, bytes / d apart) with what the other GPUs built,
+ * then vm_pyramid_build_finish builds the temporally halved levels.  vm_pyramid_build = build_frames(0, d) + finish. */
+int vm_pyramid_build_frames(vm_pyramid *p, const uint8_t *video0, const uint8_t *video1, const float *f0, const float *f1,
+                            const float *b0, const float *b1, int w, int h, int d, int start_res, int64_t voxel_cap,
+                            int frame0, int nframes, void *stream);
+int vm_pyramid_build_finish(vm_pyramid *p, void *stream);
 int vm_pyramid_num_levels(const vm_pyramid *p);
 int vm_pyramid_level_info(const vm_pyramid *p, int level, vm_level_info *out);
 /* Raw access to a level array (all frames).  Layout: images/flows tight (d,h,w[,2]); state (d,h,rowstride[,2]);

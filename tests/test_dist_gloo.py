@@ -236,3 +236,53 @@ def test_wavefront_hand_offs_on_gloo(world, depths):
     assert np.isfinite(want).all()
     for rank, K, v1, launches in res:
         np.testing.assert_array_equal(v1, want)
+
+
+class _FakeArrays:
+    """Stand-in for dist.LevelArrays: byte arrays in host memory; a rank starts with its own frame block only."""
+
+    def __init__(self, sizes, d, blocks, rank):
+        import torch
+        self.want = {k: (torch.arange(n, dtype=torch.int64) * (7 + k[0]) % 251).to(torch.uint8) for k, n in sizes.items()}
+        self.data = {}
+        a, b = blocks[rank]
+        for k, n in sizes.items():
+            per = n // d
+            t = torch.full((n,), 255, dtype=torch.uint8)                 # frames this rank did not build: garbage
+            t[a * per: b * per] = self.want[k][a * per: b * per]
+            self.data[k] = t
+
+    def nbytes(self, l, name): return self.data[(l, name)].numel()
+    def read(self, l, name, off, t): t.copy_(self.data[(l, name)][off: off + t.numel()])
+    def write(self, l, name, off, t): self.data[(l, name)][off: off + t.numel()] = t
+
+
+def _exchange_worker(rank, world, port, d, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from videomorphing_b200 import dist as vd
+    vd.init(backend="gloo")
+    blocks = vd.frame_blocks(d, world)
+    sizes = {(1, "img0"): d * 40, (1, "f0"): d * 80, (2, "img0"): d * 12, (2, "keep0"): d * 36}
+    arr = _FakeArrays(sizes, d, blocks, rank)
+    vd.exchange_frames(arr, list(sizes), d, blocks, rank, "cpu")
+    ok = all(bool((arr.data[k] == arr.want[k]).all()) for k in sizes)
+    dist.barrier()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,d", [(2, 8), (3, 7), (4, 9)])
+def test_frame_sharded_build_exchange_on_gloo(world, d):
+    """dist.exchange_frames (the all-gather of dist.build_pyramid): equal and ragged frame blocks, every rank ends with every frame."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, d, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res) and len(res) == world

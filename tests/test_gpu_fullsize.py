@@ -211,6 +211,15 @@ def test_four_gpu_level_pipeline_is_bit_identical_to_one_gpu(vm):
     assert allr == one                                     # together the four ranks ran every (level, frame) of the one-GPU log
 
 
+def _pyramid_digest(pyr):
+    import hashlib
+    out = {}
+    for l in range(1, pyr.num_levels - 1):
+        for nm in ("img0", "img1", "f0", "f1", "b0", "b1"):
+            out[(l, nm)] = hashlib.sha1(pyr.get(l, nm).tobytes()).hexdigest()
+    return out
+
+
 def _one_gpu_pipeline_worker(rank, port, q, world):
     """Rank of the exact multi-GPU schedule with EVERY rank on cuda:0 (gloo carries the hand-offs through pinned host
     memory): the real kernels and the real run_pipeline / chain-split code on a one-GPU lease."""
@@ -224,12 +233,13 @@ def _one_gpu_pipeline_worker(rank, port, q, world):
     vd.init("gloo")
     v0, v1, flows, _ = synth.video_pair(96, 64, 9, 41, 42, 3.0)
     prm = vm.Parameters(max_iter=24, start_res=4)
-    pyr = vm.Pyramid(0); pyr.build(v0, v1, flows, start_res=4)
+    pyr = vm.Pyramid(0); vd.build_pyramid(pyr, v0, v1, flows, start_res=4, device=0)      # each rank builds its frame block
+    digest = _pyramid_digest(pyr)
     m = vm.Morph(prm, pyr)
     vd.optimize_video(m, pyr, prm, device=0)
     vec = m.get_vectors()                                  # every rank ends with the whole level-1 field
     dist.barrier()
-    q.put((rank, vec, m.iters_log().copy()))
+    q.put((rank, vec, m.iters_log().copy(), digest))
     dist.destroy_process_group()
 
 
@@ -248,7 +258,7 @@ def test_exact_multi_rank_schedules_on_one_gpu_are_bit_identical(vm, world):
     procs = [ctx.Process(target=_one_gpu_pipeline_worker, args=(r, port, q, world)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict((r, (v, it)) for r, v, it in (q.get(timeout=600) for _ in range(world)))
+    res = dict((r, (v, it, dg)) for r, v, it, dg in (q.get(timeout=600) for _ in range(world)))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -258,9 +268,11 @@ def test_exact_multi_rank_schedules_on_one_gpu_are_bit_identical(vm, world):
     if world == 8:                                         # 4 equal-depth levels: each of the 8 ranks owns one (level, direction) chain
         eng = vd.MorphEngine(vm.Morph(prm, pyr), pyr, 0, prm)
         assert sorted(vd.wavefront_plan(eng.depths, eng.dims, eng.max_iters, world)["groups"]) == list(range(8))
+    digest = _pyramid_digest(pyr)
     m = vm.Morph(prm, pyr); m.run()
     ref = m.get_vectors()
     for r in range(world):
+        assert res[r][2] == digest                         # dist.build_pyramid (frame blocks + exchange) == Pyramid::build on one GPU
         np.testing.assert_array_equal(res[r][0], ref)      # every rank ends with the whole field
     one = {(int(l), int(f)): int(i) for l, f, i in m.iters_log()}
     allr = {}

@@ -14,7 +14,7 @@ BCOND_NONE, BCOND_CORNER, BCOND_BORDER = 0, 1, 2          # parameters.h:9-14
 REFERENCE_VOXEL_CAP = 14000000                               # Max_stage2, pyramid.cu:8
 
 FIELDS = dict(v=0, mean=1, var=2, luma=3, cross=4, value=5, counter=6, tps_axy=7, tps_b=8, ui_axy=9, ui_b=10,
-              temp_ref=11, temp_mask=12, impmask=13, img0=14, img1=15, f0=16, f1=17, b0=18, b1=19)
+              temp_ref=11, temp_mask=12, impmask=13, img0=14, img1=15, f0=16, f1=17, b0=18, b1=19, keep0=20, keep1=21)
 _F2 = {"v", "mean", "var", "luma", "tps_b", "ui_b", "temp_ref", "f0", "f1", "b0", "b1"}
 _TIGHT = {"img0", "img1", "f0", "f1", "b0", "b1"}
 
@@ -94,6 +94,19 @@ class Pyramid:
         fl = [None] * 4 if flows is None else [np.ascontiguousarray(f, np.float32) for f in flows]
         return check(self.L.vm_pyramid_build(self.h, _vp(v0), _vp(v1), _vp(fl[0]), _vp(fl[1]), _vp(fl[2]), _vp(fl[3]),
                                              w, h, d, start_res, voxel_cap, stream))
+
+    def build_frames(self, video0, video1, flows, frame0, nframes, start_res=8, voxel_cap=REFERENCE_VOXEL_CAP, stream=None):
+        """The frames [frame0, frame0 + nframes) of the levels that keep every frame (returns their number K: levels 1..K); the
+        other frames come from the other GPUs (dist.build_pyramid), then build_finish() adds the temporally halved levels."""
+        v0 = np.ascontiguousarray(video0, np.uint8)
+        v1 = np.ascontiguousarray(video1, np.uint8)
+        d, h, w, _ = v0.shape
+        fl = [None] * 4 if flows is None else [np.ascontiguousarray(f, np.float32) for f in flows]
+        return check(self.L.vm_pyramid_build_frames(self.h, _vp(v0), _vp(v1), _vp(fl[0]), _vp(fl[1]), _vp(fl[2]), _vp(fl[3]),
+                                                    w, h, d, start_res, voxel_cap, frame0, nframes, stream))
+
+    def build_finish(self, stream=None):
+        return check(self.L.vm_pyramid_build_finish(self.h, stream))
 
     @property
     def num_levels(self):

@@ -290,6 +290,12 @@ static int field_ptr(vm_pyramid *p, int level, int field, void **ptr, size_t *by
     if (!p || level < 0 || level >= (int)p->lv.size()) { set_error("bad level %d", level); return VM_ERR_ARG; }
     Level &L = p->lv[level];
     size_t n = (size_t)L.ps * L.d, fs = (size_t)L.w * L.h * L.d;
+    if (field == VM_FIELD_KEEP0 || field == VM_FIELD_KEEP1) {       // linear-light planes of the level built last (multi-GPU build)
+        int kl = 0;
+        int rc = keep_planes(p, field - VM_FIELD_KEEP0, &kl, ptr, bytes); if (rc) return rc;
+        if (kl != level) { set_error("the retained planes belong to level %d, not %d", kl, level); return VM_ERR_STATE; }
+        return VM_OK;
+    }
     bool state = field >= VM_FIELD_SSIM_MEAN && field <= VM_FIELD_IMPROVING_MASK;
     if (state && !(L.has_images)) { set_error("level %d has no optimizer state", level); return VM_ERR_STATE; }
     Arena &A = arena_of(p, level);      // (an arena that describes another level is still addressable with this level's strides)

@@ -174,6 +174,7 @@ Arena &arena_of(vm_pyramid *p, int level);
 LevelView make_view(vm_pyramid *p, int level);
 LevelView make_frames_view(vm_pyramid *p, int level, int frame0, int nframes);   // pages [frame0, frame0+nframes) as a level of depth nframes
 void free_resample_cache(vm_pyramid *p);
+int keep_planes(vm_pyramid *p, int video, int *level, void **ptr, size_t *bytes);
 
 // kernels (launchers) -- vm_kernels.cu / vm_sweep.cu / vm_render.cu / vm_resample.cu
 cudaError_t launch_sweep(const LevelView &L, const KParams &P, const StencilTables *st, int page, int flag, float max_iter,

@@ -108,6 +108,7 @@ struct ResampleCache {
     std::map<int, TridiagDev> tri;
     // transient planes of a build, kept between builds of the same shape (no cudaMalloc / cudaFree per call)
     DevBuf keep[2], keep_next[2], pa, pb, stage, tmpf;
+    int keep_level = 0;                  // level whose linear-light planes keep[] holds
 };
 
 static cudaError_t upload(DevBuf &b, const void *src, size_t bytes) {
@@ -514,102 +515,165 @@ void free_resample_cache(vm_pyramid *p) {
     p->resample_cache = nullptr;
 }
 
+// number of leading levels (el = 0 ..) that keep every input frame: their frames are built independently of each other
+// (pyramid.cu:267-326, 334-403 with factor_t == 1), so a multi-GPU build shards them by frame
+static int frame_parallel_levels(const vm_pyramid *p) {
+    const int maxl = (int)p->lv.size() - 1;
+    int n = 0;
+    for (int el = 0; el < maxl; el++) {
+        if (el >= maxl - 1 && el > 0) break;                                  // coarsest level: no images / flows (pyramid.cu:329)
+        if (el > 0 && p->lv[el + 1].factor_t > 1) break;
+        n++;
+    }
+    return n;
+}
+
+// One level of Pyramid::build (pyramid.cu:267-326 first level, 334-459 others) for the frames [fr0, fr0 + nfr) of a level
+// that keeps every frame, or (whole) for every frame of a temporally halved level, which reads all frames of the previous one.
+static int build_level(vm_pyramid *p, Resampler &R, int el, const uint8_t *const vids[2], const float *const fin[4], bool have_flow,
+                       int fr0, int nfr, bool whole) {
+    cudaStream_t s = R.s;
+    ResampleCache &C = *R.cache;
+    DevBuf *keep = C.keep, *keep_next = C.keep_next, &pa = C.pa, &pb = C.pb, &stage = C.stage, &tmpf = C.tmpf;
+    const int w0 = p->w0, h0 = p->h0, d0 = p->d0;
+    const size_t fs0 = (size_t)w0 * h0;
+    const int prev_w = p->lv[el].w, prev_h = p->lv[el].h, prev_d = p->lv[el].d;
+    Level &L = p->lv[el + 1];
+    const int w = L.w, h = L.h, d = L.d, factor_t = L.factor_t;
+    const size_t fs = (size_t)w * h, pfs = (size_t)prev_w * prev_h;
+    const float ratiox = (float)w / (float)prev_w, ratioy = (float)h / (float)prev_h;
+    const int do_ratio = (ratiox < 1 || ratioy < 1) ? 1 : 0;
+    DevBuf *fl_dst[4] = {&L.f0, &L.f1, &L.b0, &L.b1};
+    const size_t big = (size_t)std::max(w, prev_w) * std::max(h, prev_h);
+    // frames per batch: bound the transient planes to ~2 GiB
+    auto batch_for = [&](size_t px_per_frame, int nc) { size_t per = px_per_frame * nc * 4 * 3; size_t b = ((size_t)2 << 30) / (per ? per : 1); return (int)std::max<size_t>(1, std::min<size_t>(b, 4096)); };
+    const int i_lo = whole ? 0 : fr0, i_hi = whole ? d : fr0 + nfr;           // frames of this level to build
+    // ---- images (pyramid.cu:267-280 first level, 334-365 others); the linear-light planes [d][3][h][w] are retained for the next level
+    for (int vi = 0; vi < 2; vi++) {
+        float *gray = (vi ? L.img1 : L.img0).as<float>();
+        VM_CUDA(keep_next[vi].ensure(sizeof(float) * 3 * fs * d));
+        int B = batch_for(big, 3);
+        VM_CUDA(pa.ensure(sizeof(float) * 3 * big * std::min(B, i_hi - i_lo))); VM_CUDA(pb.ensure(sizeof(float) * 3 * big * std::min(B, i_hi - i_lo)));
+        for (int t0 = i_lo; t0 < i_hi; t0 += B) {
+            int nf = std::min(B, i_hi - t0);
+            if (el == 0) {
+                VM_CUDA(stage.ensure(pfs * 3 * nf));
+                VM_CUDA(cudaMemcpyAsync(stage.p, vids[vi] + (size_t)t0 * fs0 * 3, pfs * 3 * nf, cudaMemcpyHostToDevice, s));
+                k_load_rgb<<<dim3((unsigned)((pfs + 255) / 256), nf), 256, 0, s>>>(stage.as<uint8_t>(), pa.as<float>(), pfs, nf);
+                count_launch();
+            } else {
+                for (int t = 0; t < nf; t++) {                        // source frame min(t*factor_t, prev_d-1) (pyramid.cu:355)
+                    int src = std::min((t0 + t) * factor_t, prev_d - 1);
+                    VM_CUDA(cudaMemcpyAsync(pa.as<float>() + (size_t)t * 3 * pfs, keep[vi].as<float>() + (size_t)src * 3 * pfs,
+                                            sizeof(float) * 3 * pfs, cudaMemcpyDeviceToDevice, s));
+                }
+            }
+            float *dst = keep_next[vi].as<float>() + (size_t)t0 * 3 * fs;
+            R.scale(pa.as<float>(), pb.as<float>(), dst, nf * 3, prev_h, prev_w, h, w);
+            if (R.err != cudaSuccess) return cuda_fail(R.err, "resample tables");
+            k_store_gray<<<dim3((unsigned)((fs + 255) / 256), nf), 256, 0, s>>>(dst, gray + (size_t)t0 * fs, fs);
+            count_launch();
+        }
+    }
+    // ---- flows (pyramid.cu:283-326 first level, 367-459 others)
+    if (have_flow && d0 > 1) {
+        const int s_lo = whole ? 0 : fr0, s_hi = whole ? ((el == 0) ? d : prev_d) : fr0 + nfr;   // every frame of the previous level is rescaled (pyramid.cu:369)
+        for (int k = 0; k < 4; k++) {
+            float2 *T = fl_dst[k]->as<float2>();
+            if (el > 0 && factor_t > 1) { VM_CUDA(tmpf.ensure(sizeof(float2) * fs * (s_hi - s_lo))); T = tmpf.as<float2>(); }
+            const float2 *prev_fl = (el == 0) ? nullptr : (k == 0 ? p->lv[el].f0 : k == 1 ? p->lv[el].f1 : k == 2 ? p->lv[el].b0 : p->lv[el].b1).as<float2>();
+            int B = batch_for(big, 2);
+            VM_CUDA(pa.ensure(sizeof(float) * 3 * big * std::min(B, s_hi - s_lo))); VM_CUDA(pb.ensure(sizeof(float) * 3 * big * std::min(B, s_hi - s_lo)));
+            DevBuf &res = stage;                                      // result planes of the batch
+            for (int t0 = s_lo; t0 < s_hi; t0 += B) {
+                int nf = std::min(B, s_hi - t0);
+                VM_CUDA(res.ensure(std::max(sizeof(float) * 2 * fs * nf, sizeof(float2) * pfs * nf)));
+                const float2 *src_dev;
+                if (el == 0) {
+                    VM_CUDA(cudaMemcpyAsync(res.p, fin[k] + (size_t)t0 * fs0 * 2, sizeof(float2) * pfs * nf, cudaMemcpyHostToDevice, s));
+                    src_dev = res.as<float2>();
+                } else src_dev = prev_fl + (size_t)t0 * pfs;
+                k_load_flow<<<dim3((unsigned)((pfs + 255) / 256), nf), 256, 0, s>>>(src_dev, pa.as<float>(), pfs);
+                count_launch();
+                R.scale(pa.as<float>(), pb.as<float>(), res.as<float>(), nf * 2, prev_h, prev_w, h, w);
+                if (R.err != cudaSuccess) return cuda_fail(R.err, "resample tables");
+                k_store_flow<<<dim3((unsigned)((fs + 255) / 256), nf), 256, 0, s>>>(res.as<float>(), T + (size_t)t0 * fs, fs, ratiox, ratioy, do_ratio);
+                count_launch();
+            }
+            if (el > 0 && factor_t > 1) {
+                k_compose_flow<<<dim3((w + 31) / 32, (h + 7) / 8, d), dim3(32, 8), 0, s>>>(T, fl_dst[k]->as<float2>(), w, h, prev_d, factor_t, k < 2 ? 1 : -1);
+                count_launch();
+            }
+        }
+        L.flows_valid = true;
+    }
+    std::swap(keep[0], keep_next[0]); std::swap(keep[1], keep_next[1]);
+    C.keep_level = el + 1;
+    VM_CUDA(cudaGetLastError());
+    return VM_OK;
+}
+
+// linear-light planes [d][3][h][w] of video vi at the level built last (the input of the next coarser level)
+int keep_planes(vm_pyramid *p, int vi, int *level, void **ptr, size_t *bytes) {
+    ResampleCache *C = static_cast<ResampleCache *>(p->resample_cache);
+    if (!C || C->keep_level < 1 || !C->keep[vi].p) { set_error("no retained planes: call vm_pyramid_build_frames first"); return VM_ERR_STATE; }
+    const Level &L = p->lv[C->keep_level];
+    *level = C->keep_level; *ptr = C->keep[vi].p; *bytes = sizeof(float) * 3 * (size_t)L.w * L.h * L.d;
+    return VM_OK;
+}
+
 }  // namespace vm
 
 using namespace vm;
 
-extern "C" int vm_pyramid_build(vm_pyramid *p, const uint8_t *video0, const uint8_t *video1, const float *f0, const float *f1,
-                                const float *b0, const float *b1, int w0, int h0, int d0, int start_res, int64_t voxel_cap, void *stream) {
+extern "C" {
+
+// Pyramid::build for the frames [frame0, frame0 + nframes) of the levels that keep every frame (levels 1 .. the returned
+// value); the other frames of those levels are filled in by the caller (another GPU's build of the same video, exchanged
+// through vm_level_dev_ptr), then vm_pyramid_build_finish builds the temporally halved levels from them.
+int vm_pyramid_build_frames(vm_pyramid *p, const uint8_t *video0, const uint8_t *video1, const float *f0, const float *f1,
+                            const float *b0, const float *b1, int w0, int h0, int d0, int start_res, int64_t voxel_cap,
+                            int frame0, int nframes, void *stream) {
     if (!p || !video0 || !video1) { set_error("vm_pyramid_build: null argument"); return VM_ERR_ARG; }
+    if (frame0 < 0 || nframes < 0 || frame0 + nframes > d0) { set_error("vm_pyramid_build_frames: frames [%d, %d) outside the %d-frame video", frame0, frame0 + nframes, d0); return VM_ERR_ARG; }
     int nl = vm_pyramid_alloc(p, w0, h0, d0, start_res, voxel_cap);
     if (nl < 0) return nl;
-    cudaStream_t s = (cudaStream_t)stream;
     const bool have_flow = f0 && f1 && b0 && b1;
     if (d0 > 1 && !have_flow) { set_error("vm_pyramid_build: a video (d = %d) needs the four optical-flow fields", d0); return VM_ERR_ARG; }
-    Resampler R{p, cache_of(p), s};
-    const int maxl = nl - 1;
-    const size_t fs0 = (size_t)w0 * h0;
-    // frames per batch: bound the transient planes to ~2 GiB
-    auto batch_for = [&](size_t px_per_frame, int nc) { size_t per = px_per_frame * nc * 4 * 3; size_t b = ((size_t)2 << 30) / (per ? per : 1); return (int)std::max<size_t>(1, std::min<size_t>(b, 4096)); };
-
-    // retained linear-light planes of the previous level, per video: [d][3][h][w]
-    ResampleCache &C = *R.cache;
-    DevBuf *keep = C.keep, *keep_next = C.keep_next, &pa = C.pa, &pb = C.pb, &stage = C.stage, &tmpf = C.tmpf;
+    Resampler R{p, cache_of(p), (cudaStream_t)stream};
+    R.cache->keep_level = 0;
     const uint8_t *vids[2] = {video0, video1};
     const float *fin[4] = {f0, f1, b0, b1};
-    int prev_w = w0, prev_h = h0, prev_d = d0;
-    for (int el = 0; el < maxl; el++) {
-        Level &L = p->lv[el + 1];
-        const int w = L.w, h = L.h, d = L.d, factor_t = L.factor_t;
-        const size_t fs = (size_t)w * h, pfs = (size_t)prev_w * prev_h;
-        const float ratiox = (float)w / (float)prev_w, ratioy = (float)h / (float)prev_h;
-        const int do_ratio = (ratiox < 1 || ratioy < 1) ? 1 : 0;
-        DevBuf *fl_dst[4] = {&L.f0, &L.f1, &L.b0, &L.b1};
-        if (el >= maxl - 1 && el > 0) break;                              // coarsest level: no images / flows (pyramid.cu:329)
-        const size_t big = (size_t)std::max(w, prev_w) * std::max(h, prev_h);
-        // ---- images (pyramid.cu:267-280 first level, 334-365 others)
-        for (int vi = 0; vi < 2; vi++) {
-            float *gray = (vi ? L.img1 : L.img0).as<float>();
-            VM_CUDA(keep_next[vi].ensure(sizeof(float) * 3 * fs * d));
-            int B = batch_for(big, 3);
-            VM_CUDA(pa.ensure(sizeof(float) * 3 * big * std::min(B, d))); VM_CUDA(pb.ensure(sizeof(float) * 3 * big * std::min(B, d)));
-            for (int t0 = 0; t0 < d; t0 += B) {
-                int nf = std::min(B, d - t0);
-                if (el == 0) {
-                    VM_CUDA(stage.ensure(pfs * 3 * nf));
-                    VM_CUDA(cudaMemcpyAsync(stage.p, vids[vi] + (size_t)t0 * fs0 * 3, pfs * 3 * nf, cudaMemcpyHostToDevice, s));
-                    k_load_rgb<<<dim3((unsigned)((pfs + 255) / 256), nf), 256, 0, s>>>(stage.as<uint8_t>(), pa.as<float>(), pfs, nf);
-                    count_launch();
-                } else {
-                    for (int t = 0; t < nf; t++) {                        // source frame min(t*factor_t, prev_d-1) (pyramid.cu:355)
-                        int src = std::min((t0 + t) * factor_t, prev_d - 1);
-                        VM_CUDA(cudaMemcpyAsync(pa.as<float>() + (size_t)t * 3 * pfs, keep[vi].as<float>() + (size_t)src * 3 * pfs,
-                                                sizeof(float) * 3 * pfs, cudaMemcpyDeviceToDevice, s));
-                    }
-                }
-                float *dst = keep_next[vi].as<float>() + (size_t)t0 * 3 * fs;
-                R.scale(pa.as<float>(), pb.as<float>(), dst, nf * 3, prev_h, prev_w, h, w);
-                if (R.err != cudaSuccess) return cuda_fail(R.err, "resample tables");
-                k_store_gray<<<dim3((unsigned)((fs + 255) / 256), nf), 256, 0, s>>>(dst, gray + (size_t)t0 * fs, fs);
-                count_launch();
-            }
-        }
-        // ---- flows (pyramid.cu:283-326 first level, 367-459 others)
-        if (have_flow && d0 > 1) {
-            for (int k = 0; k < 4; k++) {
-                const int nsrc = (el == 0) ? d : prev_d;                  // every frame of the previous level is rescaled (pyramid.cu:369)
-                float2 *T = fl_dst[k]->as<float2>();
-                if (el > 0 && factor_t > 1) { VM_CUDA(tmpf.ensure(sizeof(float2) * fs * nsrc)); T = tmpf.as<float2>(); }
-                const float2 *prev_fl = (el == 0) ? nullptr : (k == 0 ? p->lv[el].f0 : k == 1 ? p->lv[el].f1 : k == 2 ? p->lv[el].b0 : p->lv[el].b1).as<float2>();
-                int B = batch_for(big, 2);
-                VM_CUDA(pa.ensure(sizeof(float) * 3 * big * std::min(B, nsrc))); VM_CUDA(pb.ensure(sizeof(float) * 3 * big * std::min(B, nsrc)));
-                DevBuf &res = stage;                                      // result planes of the batch
-                for (int t0 = 0; t0 < nsrc; t0 += B) {
-                    int nf = std::min(B, nsrc - t0);
-                    VM_CUDA(res.ensure(std::max(sizeof(float) * 2 * fs * nf, sizeof(float2) * pfs * nf)));
-                    const float2 *src_dev;
-                    if (el == 0) {
-                        VM_CUDA(cudaMemcpyAsync(res.p, fin[k] + (size_t)t0 * fs0 * 2, sizeof(float2) * pfs * nf, cudaMemcpyHostToDevice, s));
-                        src_dev = res.as<float2>();
-                    } else src_dev = prev_fl + (size_t)t0 * pfs;
-                    k_load_flow<<<dim3((unsigned)((pfs + 255) / 256), nf), 256, 0, s>>>(src_dev, pa.as<float>(), pfs);
-                    count_launch();
-                    R.scale(pa.as<float>(), pb.as<float>(), res.as<float>(), nf * 2, prev_h, prev_w, h, w);
-                    if (R.err != cudaSuccess) return cuda_fail(R.err, "resample tables");
-                    k_store_flow<<<dim3((unsigned)((fs + 255) / 256), nf), 256, 0, s>>>(res.as<float>(), T + (size_t)t0 * fs, fs, ratiox, ratioy, do_ratio);
-                    count_launch();
-                }
-                if (el > 0 && factor_t > 1) {
-                    k_compose_flow<<<dim3((w + 31) / 32, (h + 7) / 8, d), dim3(32, 8), 0, s>>>(T, fl_dst[k]->as<float2>(), w, h, prev_d, factor_t, k < 2 ? 1 : -1);
-                    count_launch();
-                }
-            }
-            L.flows_valid = true;
-        }
-        std::swap(keep[0], keep_next[0]); std::swap(keep[1], keep_next[1]);
-        prev_w = w; prev_h = h; prev_d = d;
-        VM_CUDA(cudaGetLastError());
+    const int nfull = frame_parallel_levels(p);
+    for (int el = 0; el < nfull; el++) {
+        int rc = build_level(p, R, el, vids, fin, have_flow, frame0, nframes, false);
+        if (rc != VM_OK) return rc;
     }
-    VM_CUDA(cudaStreamSynchronize(s));
-    return nl;
+    return nfull;
 }
+
+int vm_pyramid_build_finish(vm_pyramid *p, void *stream) {
+    if (!p || p->lv.empty() || !p->resample_cache) { set_error("vm_pyramid_build_finish: call vm_pyramid_build_frames first"); return VM_ERR_STATE; }
+    Resampler R{p, cache_of(p), (cudaStream_t)stream};
+    const int nfull = frame_parallel_levels(p), maxl = (int)p->lv.size() - 1;
+    if (R.cache->keep_level != nfull) { set_error("vm_pyramid_build_finish: levels 1..%d are not built (last built level %d)", nfull, R.cache->keep_level); return VM_ERR_STATE; }
+    const uint8_t *vids[2] = {nullptr, nullptr};
+    const float *fin[4] = {nullptr, nullptr, nullptr, nullptr};
+    const bool have_flow = p->lv[1].flows_valid;
+    for (int el = nfull; el < maxl; el++) {
+        if (el >= maxl - 1 && el > 0) break;                                  // coarsest level: no images / flows (pyramid.cu:329)
+        int rc = build_level(p, R, el, vids, fin, have_flow, 0, 0, true);
+        if (rc != VM_OK) return rc;
+    }
+    VM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return (int)p->lv.size();
+}
+
+int vm_pyramid_build(vm_pyramid *p, const uint8_t *video0, const uint8_t *video1, const float *f0, const float *f1,
+                     const float *b0, const float *b1, int w0, int h0, int d0, int start_res, int64_t voxel_cap, void *stream) {
+    int rc = vm_pyramid_build_frames(p, video0, video1, f0, f1, b0, b1, w0, h0, d0, start_res, voxel_cap, 0, d0, stream);
+    if (rc < 0) return rc;
+    return vm_pyramid_build_finish(p, stream);
+}
+
+}  // extern "C"

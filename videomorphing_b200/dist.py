@@ -123,6 +123,83 @@ def quadratic_path_sharded(vectors, max_iter=10000, tol=1e-12, device=0, gather=
     return gather_frames(q, d), gather_frames(np.asarray(it, np.int32), d)
 
 
+# ------------------------------------------------------------------------------------------ Pyramid::build, sharded by frame
+class LevelArrays:
+    """Byte ranges of a vm.Pyramid's device arrays, for the exchange of build_pyramid (the CPU tests use a stand-in)."""
+
+    def __init__(self, pyramid, device):
+        self.p, self.device = pyramid, device
+        from . import _lib
+        self._lib, self.L = _lib, _lib.load()
+
+    def nbytes(self, l, name):
+        return self.p.dev_ptr(l, name)[1]
+
+    def read(self, l, name, off, t):                 # device array [off, off + len(t)) -> t (on this GPU, or pinned host memory)
+        base = self.p.dev_ptr(l, name)[0]
+        f = self.L.vm_dev_copy if t.is_cuda else self.L.vm_dev_download
+        self._lib.check(f(self.device, t.data_ptr(), base + off, t.numel(), None))
+        if not t.is_cuda:
+            self._lib.check(self.L.vm_stream_sync(self.device, None))
+
+    def write(self, l, name, off, t):
+        base = self.p.dev_ptr(l, name)[0]
+        f = self.L.vm_dev_copy if t.is_cuda else self.L.vm_dev_upload
+        self._lib.check(f(self.device, base + off, t.data_ptr(), t.numel(), None))
+        if not t.is_cuda:
+            self._lib.check(self.L.vm_stream_sync(self.device, None))
+
+
+def exchange_frames(arrays, items, d, blocks, rank, staging):
+    """Every array in `items` [(level, name), ...] holds d contiguous frames of which this rank built blocks[rank]; afterwards
+    every rank holds all of them.  NCCL: one in-place all-gather per array over NVLink (equal blocks) or one broadcast per
+    block; gloo (CPU tests, several ranks on one GPU): broadcasts of host staging buffers."""
+    world = len(blocks)
+    a, b = blocks[rank]
+    equal = len({e - s for s, e in blocks}) == 1
+    for l, name in items:
+        n = arrays.nbytes(l, name)
+        per = n // d
+        t = torch.empty(n, dtype=torch.uint8, device=staging, pin_memory=(staging == "cpu" and torch.cuda.is_available()))
+        if b > a:
+            arrays.read(l, name, a * per, t[a * per: b * per])
+        if equal and t.is_cuda:
+            dist.all_gather_into_tensor(t, t[a * per: b * per])
+        else:
+            for r, (s, e) in enumerate(blocks):
+                if e > s:
+                    dist.broadcast(t[s * per: e * per], r)
+        if a > 0:
+            arrays.write(l, name, 0, t[: a * per])
+        if b < d:
+            arrays.write(l, name, b * per, t[b * per:])
+
+
+def build_pyramid(pyramid, video0, video1, flows=None, start_res=8, voxel_cap=None, device=0, stream=None):
+    """Pyramid::build (pyramid.cu:166-485) on all ranks' GPUs: the levels that keep every frame are per-frame work
+    (pyramid.cu:267-403), so each rank uploads and resamples its contiguous frame block only, the blocks are all-gathered
+    (gray images, the four flow fields, and the linear-light planes of the last such level), and the temporally halved
+    levels (pyramid.cu:406-459: frame t composes the flows of frames 2t and 2t +- 1) are then built by every rank from
+    the complete level below -- they are tiny.  Every rank ends with the pyramid a one-GPU build gives, bit for bit."""
+    from . import api
+    cap = api.REFERENCE_VOXEL_CAP if voxel_cap is None else voxel_cap
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    d = video0.shape[0]
+    if world == 1 or d < world:
+        return pyramid.build(video0, video1, flows, start_res=start_res, voxel_cap=cap, stream=stream)
+    rank = dist.get_rank()
+    blocks = frame_blocks(d, world)
+    a, b = blocks[rank]
+    K = pyramid.build_frames(video0, video1, flows, a, b - a, start_res=start_res, voxel_cap=cap, stream=stream)
+    names = ["img0", "img1"] + (["f0", "f1", "b0", "b1"] if flows is not None else [])
+    items = [(l, nm) for l in range(1, K + 1) for nm in names] + [(K, "keep0"), (K, "keep1")]
+    staging = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
+    arrays = LevelArrays(pyramid, device)
+    arrays._lib.check(arrays.L.vm_stream_sync(device, stream))       # the exchange runs on the default stream
+    exchange_frames(arrays, items, d, blocks, rank, staging)
+    return pyramid.build_finish(stream=stream)
+
+
 # ------------------------------------------------------------------------------------------ optimizer, exact mode
 def wavefront_head(depths):
     """Head level K of the wavefront: the coarsest level whose finer levels all have its depth (no temporal in-fill between
@@ -330,7 +407,7 @@ def optimize_video(morph, pyramid, params, device=0):
     """Morph::calculate_halfway_parametrization (morph.cu:150-168) for a video on 1 .. 8 GPUs, exact mode (the same
     arithmetic as one GPU; every rank ends with the bit-identical level-1 field).  One rank: vm_morph_run (the wavefront
     inside one GPU).  Several ranks: the same wavefront split by direction and level group (run_wavefront).  Every rank
-    holds the whole pyramid, built from the same frames."""
+    holds the whole pyramid (build_pyramid: built by frame block, all-gathered)."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:
