@@ -421,204 +421,6 @@ __global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res(float *X0, float *X
     if (blockIdx.x == 0 && tid == 0) { iters_out[0] = kk[0]; iters_out[1] = kk[1]; }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Resident variant 2 (default): the two Poisson systems of a frame are INDEPENDENT solves, so they need not share their
-// barriers.  Threads 0..511 of a CTA run system 0, threads 512..1023 run system 1 (each thread owns the lanes ht and
-// ht + 512 of its system: the same pixels, the same fixed dot order), each half with its own named CTA barrier and its own
-// grid-barrier counter; system 1 starts half an iteration late, so that one system's serial stretch (group tree, grid
-// barrier, tree over the 128 group sums: ~40 % of an iteration) is filled by the other system's stencil / update passes
-// instead of idling the SM.  Arithmetic, dot order and iteration counts are those of k_qpath_cg_res / k_qpath_cg / the oracle.
-constexpr int QP_HALF = QP_THREADS / 2;
-struct QpRes2Smem {
-    float p[2][QP_MAXK][QP_THREADS];
-    float r[2][QP_MAXK][QP_THREADS];
-    float x[2][QP_MAXK][QP_THREADS];
-    double red[2][QP_HALF];
-    double tot[2];
-    int act[2];
-};
-__device__ __forceinline__ void qp_half_sync(int half) {
-    if (half) asm volatile("bar.sync 2, 512;" ::: "memory");
-    else asm volatile("bar.sync 1, 512;" ::: "memory");
-}
-// grid barrier of one system's halves (128 arrivals per epoch step)
-__device__ __forceinline__ void qp_half_grid_barrier(int half, int ht, unsigned int *counter, unsigned int &epoch) {
-    qp_half_sync(half);
-    epoch += QP_BLOCKS;
-    if (ht == 0) grid_arrive_and_wait(counter, epoch);
-    qp_half_sync(half);
-}
-// D6 dot of one system: v = this thread's two lane sums added (the stride-512 level of the 1024-lane tree); warp 0 of the
-// half folds the strides 256 .. 32 (warp w with w + 8, 4, 2, 1) out of shared memory and 16 .. 1 by shuffle, publishes the
-// group sum, crosses the grid barrier and sums the 128 group sums (stride 64 .. 1); the result is rounded to f32.
-__device__ __forceinline__ float qp_half_dot(double v, QpRes2Smem &S, int half, int ht, double *part, unsigned int *counter, unsigned int &epoch) {
-    S.red[half][ht] = v;
-    qp_half_sync(half);
-    epoch += QP_BLOCKS;
-    if (ht < 32) {
-        double a[8];
-#pragma unroll
-        for (int m = 0; m < 8; m++) a[m] = S.red[half][32 * m + ht] + S.red[half][32 * (m + 8) + ht];
-#pragma unroll
-        for (int m = 0; m < 4; m++) a[m] += a[m + 4];
-        a[0] += a[2]; a[1] += a[3];
-        a[0] += a[1];
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) a[0] += __shfl_down_sync(0xffffffffu, a[0], off);
-        if (ht == 0) {
-            __stcg(part + blockIdx.x, a[0]);
-            grid_arrive_and_wait(counter, epoch);
-        }
-        __syncwarp();
-        double a0 = __ldcg(part + ht), a1 = __ldcg(part + ht + 32), a2 = __ldcg(part + ht + 64), a3 = __ldcg(part + ht + 96);
-        a0 += a2; a1 += a3;                      // stride 64
-        a0 += a1;                                // stride 32
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) a0 += __shfl_down_sync(0xffffffffu, a0, off);
-        if (ht == 0) S.tot[half] = a0;
-    }
-    qp_half_sync(half);
-    return (float)S.tot[half];
-}
-
-__global__ void __launch_bounds__(QP_THREADS) k_qpath_cg_res2(float *X0, float *X1, float *R0, float *R1, float *P0, float *P1,
-                                                              int cols, int rows, int max_iter, float tol, double *part, unsigned int *bar, int *iters_out) {
-    extern __shared__ __align__(16) unsigned char qp_smem_raw[];
-    QpRes2Smem &S = *reinterpret_cast<QpRes2Smem *>(qp_smem_raw);
-    const int N = cols * rows;
-    const int half = threadIdx.x >> 9, ht = threadIdx.x & (QP_HALF - 1);      // half = system
-    const int K = (N + QP_LANES - 1) / QP_LANES;                               // <= QP_MAXK (checked by the launcher)
-    float *X = half ? X1 : X0, *R = half ? R1 : R0, *P = half ? P1 : P0;
-    double *part_po = part + (half * 2 + 0) * QP_BLOCKS, *part_rr = part + (half * 2 + 1) * QP_BLOCKS;
-    unsigned int *counter = bar + 32 * half;                                   // one 128-byte line per system
-    float (*Sp)[QP_THREADS] = S.p[half], (*Sr)[QP_THREADS] = S.r[half], (*Sx)[QP_THREADS] = S.x[half];
-    const int laneA = ht, laneB = ht + QP_HALF;
-    const int baseA = blockIdx.x * QP_THREADS + laneA, baseB = baseA + QP_HALF;
-    // per pixel: which of the four neighbours exist (bits 4k .. 4k+3 = up, left, right, down), one word per lane
-    unsigned nbm[2] = {0, 0};
-#pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int k = 0; k < QP_MAXK; k++) {
-            int i = (j ? baseB : baseA) + k * QP_LANES;
-            if (k < K && i < N) {
-                int y = i / cols, x = i - y * cols;
-                nbm[j] |= ((y - 1 >= 0 ? 1u : 0u) | (x - 1 >= 0 ? 2u : 0u) | (x + 1 < cols ? 4u : 0u) | (y + 1 < rows ? 8u : 0u)) << (4 * k);
-            }
-        }
-    float om[2][QP_MAXK];
-    unsigned int epoch = 0;
-    float r1, r0 = 0.f;
-    {   // r = B (written by k_qpath_rhs), x = 0, p = 0; r1 = r.r
-        double acc[2] = {0, 0};
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int k = 0; k < QP_MAXK; k++) {
-                const int lane = j ? laneB : laneA, i = (j ? baseB : baseA) + k * QP_LANES;
-                float v = 0.f;
-                if (k < K && i < N) { v = R[i]; acc[j] += (double)v * (double)v; }
-                Sr[k][lane] = v; Sp[k][lane] = 0.f; Sx[k][lane] = 0.f; om[j][k] = 0.f;
-            }
-        r1 = qp_half_dot(acc[0] + acc[1], S, half, ht, part_rr, counter, epoch);
-    }
-    int kk = 0;
-    bool active = r1 > tol * tol && kk <= max_iter;
-    // stagger: system 1 starts when system 0 has applied its first operator (3 epochs of system 0's counter: the initial dot,
-    // the publication of p, the p.Ap dot) -- unless system 0 has nothing to do
-    if (ht == 0) S.act[half] = active ? 1 : 0;
-    __syncthreads();
-    if (half == 1 && active && S.act[0]) {                                             // uniform over the half
-        if (ht == 0) {
-            unsigned int v;
-            do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < 3u * QP_BLOCKS);
-        }
-        qp_half_sync(half);
-    }
-    while (active) {
-        // ---- phase A, pass 1: own p_new = r (+ beta p_old) into shared memory and into the global array the neighbour rows' owners read
-        kk++;
-        const bool first = (kk == 1);
-        const float beta = first ? 0.0f : r1 / r0;
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int k = 0; k < QP_MAXK; k++) {
-                const int lane = j ? laneB : laneA, i = (j ? baseB : baseA) + k * QP_LANES;
-                if (k < K && i < N) {
-                    float rv = Sr[k][lane];
-                    float pc = rv;
-                    if (!first) { float t = beta * Sp[k][lane]; pc = 1.0f * rv + t; }
-                    Sp[k][lane] = pc;
-                    P[i] = pc;
-                }
-            }
-        qp_half_grid_barrier(half, ht, counter, epoch);
-        // ---- phase A, pass 2: om = A p_new (QuadraticPath.cpp:170-202), partial p_new.om; rows above / below first (all loads in flight)
-        float pu[2][QP_MAXK], pd[2][QP_MAXK];
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int k = 0; k < QP_MAXK; k++) {
-                const int i = (j ? baseB : baseA) + k * QP_LANES;
-                const unsigned nb = nbm[j] >> (4 * k);
-                pu[j][k] = pd[j][k] = 0.f;
-                if (nb & 1u) pu[j][k] = __ldcg(P + i - cols);
-                if (nb & 8u) pd[j][k] = __ldcg(P + i + cols);
-            }
-        double accA[2] = {0, 0};
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int k = 0; k < QP_MAXK; k++) {
-                const int lane = j ? laneB : laneA, i = (j ? baseB : baseA) + k * QP_LANES;
-                if (k < K && i < N) {
-                    const unsigned nb = nbm[j] >> (4 * k);
-                    float pc = Sp[k][lane];
-                    float diag = 0, sum = 0;
-                    if (nb & 1u) { diag += 1.0f; sum += -1.0f * pu[j][k]; }
-                    if (nb & 2u) { diag += 1.0f; sum += -1.0f * (lane > 0 ? Sp[k][lane - 1] : __ldcg(P + i - 1)); }
-                    float right = 0, down = 0;
-                    if (nb & 4u) { diag += 1.0f; right = -1.0f * (lane < QP_THREADS - 1 ? Sp[k][lane + 1] : __ldcg(P + i + 1)); }
-                    if (nb & 8u) { diag += 1.0f; down = -1.0f * pd[j][k]; }
-                    if (diag != 0) sum += diag * pc;
-                    if (nb & 4u) sum += right;
-                    if (nb & 8u) sum += down;
-                    om[j][k] = sum;
-                    accA[j] += (double)pc * (double)sum;
-                }
-            }
-        const float dt = qp_half_dot(accA[0] + accA[1], S, half, ht, part_po, counter, epoch);
-        // ---- phase B: alpha = r1 / (p.om); x += alpha p; r -= alpha om; partial r.r
-        const float alpha = r1 / dt, nalpha = -alpha;
-        double accB[2] = {0, 0};
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int k = 0; k < QP_MAXK; k++) {
-                const int lane = j ? laneB : laneA, i = (j ? baseB : baseA) + k * QP_LANES;
-                if (k < K && i < N) {
-                    float pv = Sp[k][lane];
-                    Sx[k][lane] = alpha * pv + Sx[k][lane];
-                    float rv = nalpha * om[j][k] + Sr[k][lane];
-                    Sr[k][lane] = rv;
-                    accB[j] += (double)rv * (double)rv;
-                }
-            }
-        const float nr = qp_half_dot(accB[0] + accB[1], S, half, ht, part_rr, counter, epoch);
-        r0 = r1; r1 = nr;
-        active = r1 > tol * tol && kk <= max_iter;
-    }
-#pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int k = 0; k < QP_MAXK; k++) {
-            const int lane = j ? laneB : laneA, i = (j ? baseB : baseA) + k * QP_LANES;
-            if (k < K && i < N) X[i] = Sx[k][lane];
-        }
-    if (blockIdx.x == 0 && ht == 0) iters_out[half] = kk;
-}
-
 // interleave the two solutions into the float2 result (QuadraticPath.cpp:208-211)
 __global__ void k_qpath_pack(const float *__restrict__ X, const float *__restrict__ Y, float2 *__restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -649,18 +451,7 @@ cudaError_t launch_qpath(const float2 *vec, float2 *out, int cols, int rows, int
     // frames whose unknowns fit QP_MAXK steps of the lane grid keep r / p on chip (VMORPH_QPATH=global forces the streaming kernel: test hook)
     const char *eq = getenv("VMORPH_QPATH");
     const bool resident = N <= (size_t)QP_MAXK * QP_LANES && !(eq && !strcmp(eq, "global"));
-    const bool lockstep = eq && !strcmp(eq, "res1");                                   // the round-1 resident kernel (both systems share the barriers)
-    if (resident && !lockstep) {
-        static std::atomic<bool> attr_set2[64];
-        int dev = 0; cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || !attr_set2[dev].load(std::memory_order_acquire)) {
-            e = cudaFuncSetAttribute(k_qpath_cg_res2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QpRes2Smem));
-            if (e != cudaSuccess) return e;
-            if (dev >= 0 && dev < 64) attr_set2[dev].store(true, std::memory_order_release);
-        }
-        void *args[] = {&X0, &X1, &R0, &R1, &P00, &P10, &cols, &rows, &max_iter, &tol, &part, &bar, &iters_dev};
-        e = cudaLaunchCooperativeKernel((const void *)k_qpath_cg_res2, dim3(QP_BLOCKS), dim3(QP_THREADS), args, sizeof(QpRes2Smem), s);
-    } else if (resident) {
+    if (resident) {
         // per device: the attribute belongs to the current device's context
         static std::atomic<bool> attr_set[64];
         int dev = 0; cudaGetDevice(&dev);
