@@ -352,6 +352,7 @@ def run_ours_video(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not precede the JSON line on stdout
     vd.init("nccl", device_id=local)                      # one process per GPU; no-op for a single rank
     import videomorphing_b200 as vm
     from videomorphing_b200 import _lib, synth

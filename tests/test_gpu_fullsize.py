@@ -88,10 +88,15 @@ def _two_gpu_worker(rank, port, q, world=2):
     vd.init("nccl", device_id=rank)
     v0, v1, flows, _ = synth.video_pair(96, 64, 9, 41, 42, 3.0)
     prm = vm.Parameters(max_iter=24, start_res=4)
-    pyr = vm.Pyramid(rank); pyr.build(v0, v1, flows, start_res=4)
+    pyr = vm.Pyramid(rank); vd.build_pyramid(pyr, v0, v1, flows, start_res=4, device=rank)   # ragged frame blocks: one broadcast per block
     m = vm.Morph(prm, pyr)
     vd.optimize_video(m, pyr, prm, device=rank)
     vec = m.get_vectors()                                  # every rank ends with the whole level-1 field
+    # equal frame blocks (8 frames): the in-place NCCL all-gather of dist.build_pyramid == Pyramid::build on this GPU
+    fl8 = tuple(f[:8] for f in flows)
+    pa = vm.Pyramid(rank); vd.build_pyramid(pa, v0[:8], v1[:8], fl8, start_res=4, device=rank)
+    pb = vm.Pyramid(rank); pb.build(v0[:8], v1[:8], fl8, start_res=4)
+    assert _pyramid_digest(pa) == _pyramid_digest(pb)
     dist.barrier()
     q.put((rank, vec, m.iters_log().copy()))
     dist.destroy_process_group()

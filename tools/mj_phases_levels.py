@@ -9,6 +9,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=24)
     ap.add_argument("--w", type=int, default=1280); ap.add_argument("--h", type=int, default=720)
+    ap.add_argument("--chains", type=int, default=3, help="3: both frame chains (two jobs per launch); 1: the forward chain only (one job per launch: what a rank of the 8-GPU plan runs)")
     args = ap.parse_args()
     os.environ["VMORPH_SWEEP"] = "mj"
     import videomorphing_b200 as vm
@@ -26,7 +27,7 @@ def main():
         for l in range(n - 2, 0, -1):
             m.upsample(l); m.initialize_level(l)
             L.vm_debug_sweep_phases(0, out, 1)
-            t = time.perf_counter(); m.optimize_level(l, float(mi)); dt = time.perf_counter() - t
+            t = time.perf_counter(); m.optimize_chains(l, float(mi), args.chains); dt = time.perf_counter() - t
             L.vm_debug_sweep_phases(0, out, 1)
             if rep == 1:
                 i = pyr.info(l); r = max(1, int(out[5]))
