@@ -344,6 +344,23 @@ def render_bench(vm, L, device, sh, stream, sync, nframes=60):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm: the video (headline)
+def _init_nccl(vd, torch, dist, local, world):
+    """One process per GPU; no-op for a single rank.  NCCL prints its version banner on stdout when the communicator comes up:
+    stdout is pointed at stderr for that moment, so that the JSON line is the only thing rank 0 prints there."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        vd.init("nccl", device_id=local)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def run_ours_video(args):
     import torch
     import torch.distributed as dist
@@ -352,8 +369,7 @@ def run_ours_video(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not precede the JSON line on stdout
-    vd.init("nccl", device_id=local)                      # one process per GPU; no-op for a single rank
+    _init_nccl(vd, torch, dist, local, world)
     import videomorphing_b200 as vm
     from videomorphing_b200 import _lib, synth
     L = _lib.load()
@@ -639,7 +655,7 @@ def run_ours_pair(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    vd.init("nccl", device_id=local)
+    _init_nccl(vd, torch, dist, local, world)
     import videomorphing_b200 as vm
     from videomorphing_b200 import _lib
     L = _lib.load()
