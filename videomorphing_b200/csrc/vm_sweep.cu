@@ -214,20 +214,12 @@ __device__ void tile_step(SweepSmem &S, const LevelView &L, const KParams &P, co
                         E.w_mean = S.mean[c]; E.w_var = S.var[c]; E.w_cross = S.cross[c]; E.w_value = S.value[c]; E.w_cnt = S.cnt[c];
                     }
                 }
-                // neighbour vectors for the fold-over test (morph.cu:788-789)
-                float2 nb[8]; unsigned inb = 0;
-                {
-                    const int OX[8] = {-1, 0, 1, 1, 1, 0, -1, -1}, OY[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        int nx = px + OX[k], ny = py + OY[k];
-                        nb[k] = make_float2(0.f, 0.f);
-                        if (nx >= 0 && nx < L.w && ny >= 0 && ny < L.h) { inb |= 1u << k; nb[k] = __ldcg(L.v + (size_t)ny * L.rs + nx + poff); }
-                    }
-                }
+                // neighbour vectors for the fold-over test (morph.cu:788-789), one per lane
+                float2 nbl; unsigned inb;
+                fover_neighbours(L.v + poff, L.rs, L.w, L.h, px, py, lane, nbl, inb);
                 float2 d;
                 TR(8);
-                bool ok = optimize_pixel_warp<LAT>(E, P.eps, nb, inb, spec, d TR_PASS);
+                bool ok = optimize_pixel_warp<LAT>(E, P.eps, nbl, inb, spec, d TR_PASS);
                 if (ok) {
                     // commit of the pixel's own cells (morph.cu:951-971,1017-1025,1320-1327)
                     float2 newv = make_float2(E.v.x + d.x, E.v.y + d.y);

@@ -146,7 +146,7 @@ struct PixelEval {
     }
 };
 
-// morph.cu:794-831, split in two: the geometry of one ring segment (branch-free, all 16 segments overlap) ...
+// morph.cu:794-831, split in two: the geometry of one ring segment (branch-free) ...
 struct Isec { float ud, d, td; };
 __device__ __forceinline__ Isec fover_isec(float2 c, float2 grad, float2 e0, float2 e1) {
     float2 de = make_float2(e1.x - e0.x, e1.y - e0.y), dce = make_float2(c.x - e0.x, c.y - e0.y);
@@ -159,26 +159,43 @@ __device__ __forceinline__ Isec fover_isec(float2 c, float2 grad, float2 e0, flo
     r.td *= (float)(-sign * 2 + 1);
     return r;
 }
-// ... and the sequential minimum update (the division only runs when a fold-over constraint really binds)
-__device__ __forceinline__ void fover_update(const Isec &s, float &t_min) {
-    if (s.ud >= 0 && s.ud <= s.d)
-        if (s.td >= 0 && s.td < t_min * s.d) t_min = s.td / s.d;
+// ring offsets (-1,-1),(0,-1),(1,-1),(1,0),(1,1),(0,1),(-1,1),(-1,0) of neighbour k, packed two bits (value + 1) per entry
+__device__ __forceinline__ int fover_ox(int k) { return (int)((0x6A4u >> (2 * k)) & 3u) - 1; }
+__device__ __forceinline__ int fover_oy(int k) { return (int)((0x6A40u >> (2 * k)) & 3u) - 1; }
+// Neighbour vectors for the fold-over test (morph.cu:788-789), one per lane: lane l gets v of neighbour l & 7 (zero outside
+// the image), inb bit k = neighbour k inside.  `v` points at the frame's page.
+__device__ __forceinline__ void fover_neighbours(const float2 *v, int rs, int w, int h, int px, int py, int lane, float2 &nbl, unsigned &inb) {
+    const int k = lane & 7, nx = px + fover_ox(k), ny = py + fover_oy(k);
+    const bool in = nx >= 0 && nx < w && ny >= 0 && ny < h;
+    nbl = make_float2(0.f, 0.f);
+    if (in) nbl = __ldcg(v + (size_t)ny * rs + nx);
+    inb = __ballot_sync(0xffffffffu, in) & 0xffu;
 }
-
-// morph.cu:782-792 + 833-870.  nb[8] = v of the 8 neighbours in the order (-1,-1),(0,-1),(1,-1),(1,0),(1,1),(0,1),(-1,1),(-1,0),
-// inb bit k = neighbour k inside the image.  Quirk kept: vertex position is p-off with the vector of p+off.
-__device__ __forceinline__ void fover_ring(int SIGN, int px, int py, const float2 *nb, unsigned inb, float2 v, float2 grad, Isec (&out)[8]) {
-    const int OX[8] = {-1, 0, 1, 1, 1, 0, -1, -1}, OY[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
-    float2 c = make_float2((float)px + v.x, (float)py + v.y);
-    float2 e[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        float2 vv = v;
-        if ((inb >> k) & 1) vv = make_float2((float)SIGN * nb[k].x, (float)SIGN * nb[k].y);
-        e[k] = make_float2(vv.x + (float)(px - OX[k]), vv.y + (float)(py - OY[k]));
+// prevent_foldover (morph.cu:782-792, 833-883): the 16 segment tests (ring of SIGN = -1 with -v / -grad, then SIGN = +1) are the
+// same arithmetic on different data, so lane l < 16 computes segment l & 7 of ring l >> 3 instead of every lane computing all
+// sixteen; the sequential minimum update (the division only runs when a constraint really binds) then walks the lanes whose
+// ray test passed in the reference's order.  Quirk kept: vertex position is p - off with the vector of p + off.
+__device__ __forceinline__ float fover_tmin_warp(int px, int py, float2 nbl, unsigned inb, float2 v, float2 grad, int lane) {
+    const int k = lane & 7, k1 = (k + 1) & 7;
+    const float sg = (lane & 8) ? 1.0f : -1.0f;
+    const float2 n1 = make_float2(__shfl_sync(0xffffffffu, nbl.x, k1), __shfl_sync(0xffffffffu, nbl.y, k1));
+    const float2 vs = make_float2(sg * v.x, sg * v.y), gs = make_float2(sg * grad.x, sg * grad.y);
+    const float2 c = make_float2((float)px + vs.x, (float)py + vs.y);
+    float2 v0 = vs, v1 = vs;
+    if ((inb >> k) & 1u) v0 = make_float2(sg * nbl.x, sg * nbl.y);
+    if ((inb >> k1) & 1u) v1 = make_float2(sg * n1.x, sg * n1.y);
+    const float2 e0 = make_float2(v0.x + (float)(px - fover_ox(k)), v0.y + (float)(py - fover_oy(k)));
+    const float2 e1 = make_float2(v1.x + (float)(px - fover_ox(k1)), v1.y + (float)(py - fover_oy(k1)));
+    const Isec s = fover_isec(c, gs, e0, e1);
+    unsigned hit = __ballot_sync(0xffffffffu, lane < 16 && s.ud >= 0 && s.ud <= s.d && s.td >= 0);
+    float t_min = 10.0f;
+    while (hit) {                                                  // uniform; usually one or two segments per ring
+        const int l = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const float td = __shfl_sync(0xffffffffu, s.td, l), d = __shfl_sync(0xffffffffu, s.d, l);
+        if (td < t_min * d) t_min = td / d;
     }
-#pragma unroll
-    for (int k = 0; k < 8; k++) out[k] = fover_isec(c, grad, e[k], e[(k + 1) & 7]);    // segments (0,1) ... (6,7), (7,0)
+    return t_min;
 }
 
 // One warp optimises one pixel (morph.cu:1030-1083: compute_gradient, prevent_foldover, golden_section_search).
@@ -199,7 +216,7 @@ __device__ __forceinline__ void fover_ring(int SIGN, int px, int py, const float
 // and the bracket [0, c] are known, the lanes prefetch the cache lines of both images along the search segment into L1, so
 // the ~15 dependent bilinear fetches of the line search hit L1 instead of paying an L2 round trip each.
 template <bool LAT, bool PF = false>
-__device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float eps, const float2 *nb, unsigned inb, bool spec, float2 &d_out TR_ARG) {
+__device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float eps, float2 nbl, unsigned inb, bool spec, float2 &d_out TR_ARG) {
     float2 g;
     if (LAT) {
         const float2 dd[4] = {make_float2(eps, 0.0f), make_float2(-eps, 0.0f), make_float2(0.0f, eps), make_float2(0.0f, -eps)};
@@ -216,24 +233,7 @@ __device__ __forceinline__ bool optimize_pixel_warp(const PixelEval &E, float ep
     grad.x = grad.x / ng; grad.y = grad.y / ng;
     TR(9);
     // prevent_foldover, morph.cu:872-883
-    float t_min = 10.0f;
-    if (LAT) {
-        Isec sa[8], sb[8];
-        fover_ring(-1, E.px, E.py, nb, inb, make_float2(-E.v.x, -E.v.y), make_float2(-grad.x, -grad.y), sa);
-        fover_ring(1, E.px, E.py, nb, inb, E.v, grad, sb);
-#pragma unroll
-        for (int k = 0; k < 8; k++) fover_update(sa[k], t_min);
-#pragma unroll
-        for (int k = 0; k < 8; k++) fover_update(sb[k], t_min);
-    } else {
-#pragma unroll 1
-        for (int sgn = -1; sgn <= 1; sgn += 2) {
-            Isec sa[8];
-            fover_ring(sgn, E.px, E.py, nb, inb, make_float2((float)sgn * E.v.x, (float)sgn * E.v.y), make_float2((float)sgn * grad.x, (float)sgn * grad.y), sa);
-#pragma unroll
-            for (int k = 0; k < 8; k++) fover_update(sa[k], t_min);
-        }
-    }
+    const float t_min = fover_tmin_warp(E.px, E.py, nbl, inb, E.v, grad, E.lane);
     float c = maxf_std(t_min - eps, 0.0f);
     if (PF) E.prefetch_segment(grad, c);
     TR(10);

@@ -270,19 +270,11 @@ __device__ __forceinline__ void mj_pixel(MjShared &S, const KParams &P, unsigned
                 E.w_value = __ldcg(L.value + c); E.w_cnt = __ldcg(L.counter + c);
             }
         }
-        // neighbour vectors for the fold-over test (morph.cu:788-789)
-        float2 nb[8]; unsigned inb = 0;
-        {
-            const int OX[8] = {-1, 0, 1, 1, 1, 0, -1, -1}, OY[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int nx = px + OX[k], ny = py + OY[k];
-                nb[k] = make_float2(0.f, 0.f);
-                if (nx >= 0 && nx < L.w && ny >= 0 && ny < L.h) { inb |= 1u << k; nb[k] = __ldcg(L.v + ny * L.rs + nx); }
-            }
-        }
+        // neighbour vectors for the fold-over test (morph.cu:788-789), one per lane
+        float2 nbl; unsigned inb;
+        fover_neighbours(L.v, L.rs, L.w, L.h, px, py, lane, nbl, inb);
         float2 d;
-        ok = optimize_pixel_warp<true, true>(E, P.eps, nb, inb, spec, d);
+        ok = optimize_pixel_warp<true, true>(E, P.eps, nbl, inb, spec, d);
         if (ok) {
             // commit of the pixel's own cells (morph.cu:951-971,1017-1025,1320-1327) + the deltas for the gather
             const float2 newv = make_float2(E.v.x + d.x, E.v.y + d.y);
