@@ -65,6 +65,12 @@ struct PixelEval {
     float w_cross, w_value, w_cnt;
     bool w_valid, flag;
     float w_ui, w_tps, w_ssim, w_temp, ssim_clamp, inv_wh, factor_d;
+    // per-pixel invariants of the evaluations (the same products / differences every evaluation would form again)
+    float ol_xx, ol_yy, ol_xy, at_x, at_y;
+    __device__ __forceinline__ void prepare() {
+        ol_xx = old_luma.x * old_luma.x; ol_yy = old_luma.y * old_luma.y; ol_xy = old_luma.x * old_luma.y;
+        at_x = fabsf(v.x - tref.x); at_y = fabsf(v.y - tref.y);
+    }
 
     // morph.cu:672-761 (ssim_change + energy_change) for N displacements at once.  The N evaluations are independent
     // straight-line instruction streams (no branch anywhere: exact div / sqrt without the range-check branch, selects
@@ -73,28 +79,29 @@ struct PixelEval {
     __device__ __forceinline__ void energy_n(const float2 (&d)[N], float (&out)[N]) const {
         float term[N];
         // The 2N bilinear samples (image 0 at p - v - d_k, image 1 at p + v + d_k) are the same on every lane of the
-        // warp.  Instead of all 32 lanes computing all of them, lane f (mod 2N) computes sample f and the results are
-        // broadcast with one shuffle each: the same arithmetic on another lane, 2N times fewer instructions.
+        // warp.  Instead of all 32 lanes computing all of them, the four lanes 4f .. 4f + 3 compute sample f (mod 2N), one
+        // texel each (tex2d_quad), and the results are broadcast with one shuffle each: the same arithmetic spread over the
+        // lanes, a third of the instructions of one lane doing a whole sample.
         constexpr int NF = 2 * N;
         float fetched;
         {
-            const int fid = lane % NF, fk = fid >> 1, img = fid & 1;
+            const int fid = (lane >> 2) % NF, fk = fid >> 1, img = fid & 1;
             float2 dk = d[0];
 #pragma unroll
             for (int k = 1; k < N; k++) if (fk == k) dk = d[k];
             float2 nv = make_float2(v.x + dk.x, v.y + dk.y);
             // image 0: (float)px - nv.x + 0.5f ; image 1: (float)px + nv.x + 0.5f  (a - b == a + (-b) exactly)
             float ox = img ? nv.x : -nv.x, oy = img ? nv.y : -nv.y;
-            fetched = tex2d<true>(img ? I1 : I0, W, H, (float)px + ox + 0.5f, (float)py + oy + 0.5f);
+            fetched = tex2d_quad(img ? I1 : I0, W, H, (float)px + ox + 0.5f, (float)py + oy + 0.5f, lane & 3);
         }
 #pragma unroll
         for (int k = 0; k < N; k++) {
             float2 luma;
-            luma.x = __shfl_sync(0xffffffffu, fetched, 2 * k);
-            luma.y = __shfl_sync(0xffffffffu, fetched, 2 * k + 1);
+            luma.x = __shfl_sync(0xffffffffu, fetched, 8 * k);
+            luma.y = __shfl_sync(0xffffffffu, fetched, 8 * k + 4);
             float2 dmean = make_float2(luma.x - old_luma.x, luma.y - old_luma.y);
-            float2 dvar = make_float2(luma.x * luma.x - old_luma.x * old_luma.x, luma.y * luma.y - old_luma.y * old_luma.y);
-            float dcross = luma.x * luma.y - old_luma.x * old_luma.y;
+            float2 dvar = make_float2(luma.x * luma.x - ol_xx, luma.y * luma.y - ol_yy);
+            float dcross = luma.x * luma.y - ol_xy;
             float2 m = make_float2(w_mean.x + dmean.x, w_mean.y + dmean.y);
             float2 vr = make_float2(w_var.x + dvar.x, w_var.y + dvar.y);
             float cr = w_cross + dcross;
@@ -117,8 +124,8 @@ struct PixelEval {
             v_ui += ui_b.y * d[k].y;
             float v_temp = 0.0f;
             if (flag) {
-                v_temp += fabsf(v.x + d[k].x - tref.x) - fabsf(v.x - tref.x);
-                v_temp += fabsf(v.y + d[k].y - tref.y) - fabsf(v.y - tref.y);
+                v_temp += fabsf(v.x + d[k].x - tref.x) - at_x;
+                v_temp += fabsf(v.y + d[k].y - tref.y) - at_y;
             }
             out[k] = (w_ui * v_ui + w_ssim * term[k] + w_temp * v_temp * tmask * factor_d) * inv_wh + w_tps * v_tps;
         }

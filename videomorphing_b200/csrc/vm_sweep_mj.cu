@@ -259,6 +259,7 @@ __device__ __forceinline__ void mj_pixel(MjShared &S, const KParams &P, unsigned
         if (E.flag) { E.tref = __ldcg(L.temp_ref + pix); E.tmask = __ldcg(L.temp_mask + pix); }
         E.w_ui = P.w_ui; E.w_tps = P.w_tps; E.w_ssim = P.w_ssim; E.w_temp = P.w_temp; E.ssim_clamp = P.ssim_clamp;
         E.inv_wh = L.inv_wh; E.factor_d = L.factor_d;
+        E.prepare();
         const int B = border_class(py, L.h) * 5 + border_class(px, L.w);
         E.w_valid = false; E.w_mean = E.w_var = make_float2(0.f, 0.f); E.w_cross = E.w_value = 0.f; E.w_cnt = 0.f;
         if (lane < 25) {
