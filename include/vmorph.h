@@ -108,6 +108,12 @@ void vm_pyramid_destroy(vm_pyramid *p);
 /* pyramid.cu:219-236,463-477: level sizes only.  whd_out: 3 ints per level; returns #levels (<= max_levels)
  * or a negative status.  voxel_cap = 14000000 reproduces the reference (pyramid.cu:8). Pure host arithmetic. */
 int vm_level_schedule(int w, int h, int d, int start_res, int64_t voxel_cap, int max_levels, int32_t *whd_out, float *factor_d_out);
+/* Exact-mode multi-GPU schedule of a video (the reference runs the chains of morph.cu:1374-1439 on one
+ * GPU): whd = 3 ints per level as vm_level_schedule returns them, max_iters[l] = iteration cap of level l (morph.cu:131,163:
+ * max_iter / drop^(n-2-l) in float).  owner_out[2 * l + dir] = rank that runs the frame chain `dir` (0: the middle frame and
+ * the frames after it, 1: the frames before it) of level l, for the levels K .. 1 of the wavefront (-1 elsewhere); returns
+ * K.  The levels above K run on every rank (vm_morph_wavefront_prepare).  Pure host arithmetic. */
+int vm_wavefront_plan(int n_levels, const int32_t *whd, const float *max_iters, int world, int32_t *owner_out);
 /* Allocates all levels for w x h x d input (no image data yet).  A video whose full optimizer state would not fit (72 B per
  * pixel and frame: 143 GB for 3840x2160 x 240) keeps, for the levels of its wavefront, a WINDOW of 4 state pages per level
  * instead of one per frame (a frame chain only reads the previous frame's ssim.value); such a pyramid can only be run by

@@ -286,3 +286,26 @@ def test_frame_sharded_build_exchange_on_gloo(world, d):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res) and len(res) == world
+
+
+def test_c_abi_wavefront_plan_equals_the_python_plan():
+    """vm_wavefront_plan (what tools/vmorph_video.cpp and any non-Python host use) == dist.wavefront_plan."""
+    import ctypes as C
+    from videomorphing_b200 import _lib, dist as vd
+    L = _lib.load()
+    shapes = [(1280, 720, 120, 8, 1 << 62), (1280, 720, 120, 8, 14000000), (3840, 2160, 16, 8, 1 << 62), (96, 64, 9, 4, 1 << 62), (640, 360, 33, 8, 1 << 62)]
+    for w, h, d, sr, cap in shapes:
+        whd = (C.c_int32 * (3 * 32))()
+        n = L.vm_level_schedule(w, h, d, sr, cap, 32, whd, None)
+        assert n >= 3
+        depths = [whd[3 * l + 2] for l in range(n)]
+        dims = {l: (whd[3 * l], whd[3 * l + 1]) for l in range(n)}
+        mi = vd.level_max_iters(1000, 2, n)
+        mia = (C.c_float * n)(*[mi.get(l, 0.0) for l in range(n)])
+        for world in (1, 2, 3, 4, 5, 8):
+            owner = (C.c_int32 * (2 * n))()
+            K = L.vm_wavefront_plan(n, whd, mia, world, owner)
+            pl = vd.wavefront_plan(depths, dims, mi, world)
+            assert K == pl["K"]
+            got = {(l, dr): owner[2 * l + dr] for l in range(n) for dr in (0, 1) if owner[2 * l + dr] >= 0}
+            assert got == pl["owner"], (w, h, d, world)

@@ -52,6 +52,20 @@ def build_headless(force=False):
     return out
 
 
+def build_video_host(force=False):
+    """tools/vmorph_video: the multi-GPU video host in C++ (threads + peer copies over the C ABI), plain g++."""
+    src = os.path.join(HERE, "..", "tools", "vmorph_video.cpp")
+    out = os.path.join(HERE, "vmorph_video")
+    if not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(OUT)):
+        return out
+    cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-o", out, src, "-L" + HERE, "-l:libvmorph.so", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("g++ failed building vmorph_video")
+    return out
+
+
 def build_trace():
     """Development aid: libvmorph_trace.so = the same sources with -DVM_TRACE (per-phase cycle counters in the sweep)."""
     out = os.path.join(HERE, "libvmorph_trace.so")

@@ -196,6 +196,70 @@ int vm_level_schedule(int w, int h, int d, int start_res, int64_t voxel_cap, int
     return (int)s.size();
 }
 
+// Exact-mode multi-GPU schedule (the same split as videomorphing_b200/dist.py wavefront_plan, for hosts in any language).
+// Chains are (level, direction) for the levels K .. 1 of the wavefront; direction 0 (the middle frame and the frames after
+// it) goes to the first ceil(world / 2) ranks, direction 1 to the others; within a direction the levels are cut into
+// contiguous groups, one per rank, minimising the most expensive group, then the next most expensive one.  Cost of one tick
+// of a lock-step launch over a group: throughput terms add up, round-latency terms overlap (fitted to the 720p measurements,
+// profiles/r2_wavefront.md).
+static double plan_group_cost(const int *levels, int n, const int32_t *whd, const float *max_iters) {
+    double thr = 0, lat = 0;
+    for (int i = 0; i < n; i++) {
+        const int l = levels[i];
+        const double mi = (double)max_iters[l];
+        thr += (double)(whd[3 * l] * whd[3 * l + 1]) * (mi < 16.0 ? mi : 16.0) * 1e-6;
+        const double t = (mi < 50.0 ? mi : 50.0) * 16 * 0.02;
+        if (i == 0 || t > lat) lat = t;
+    }
+    return thr + lat;
+}
+static void plan_split_rec(const std::vector<int> &levels, int start, int left, std::vector<int> &cuts, const int32_t *whd, const float *max_iters,
+                           std::vector<double> &best_cost, std::vector<int> &best_cuts) {
+    const int n = (int)levels.size();
+    if (left == 1) {
+        std::vector<double> cost;
+        int b = 0;
+        for (size_t g = 0; g <= cuts.size(); g++) {
+            const int e = g < cuts.size() ? cuts[g] : n;
+            cost.push_back(plan_group_cost(levels.data() + b, e - b, whd, max_iters));
+            b = e;
+        }
+        std::sort(cost.begin(), cost.end(), [](double x, double y) { return x > y; });
+        if (best_cost.empty() || cost < best_cost) { best_cost = cost; best_cuts = cuts; }
+        return;
+    }
+    for (int end = start + 1; end <= n - left + 1; end++) {
+        cuts.push_back(end);
+        plan_split_rec(levels, end, left - 1, cuts, whd, max_iters, best_cost, best_cuts);
+        cuts.pop_back();
+    }
+}
+int vm_wavefront_plan(int n_levels, const int32_t *whd, const float *max_iters, int world, int32_t *owner_out) {
+    if (n_levels < 3 || !whd || !max_iters || !owner_out || world < 1) { set_error("bad wavefront_plan arguments"); return VM_ERR_ARG; }
+    int K = 1;
+    while (K + 1 <= n_levels - 2 && whd[3 * K + 2] == whd[3 * (K + 1) + 2]) K++;
+    if (2 * K > MJ_MAX_JOBS) K = MJ_MAX_JOBS / 2;
+    for (int i = 0; i < 2 * n_levels; i++) owner_out[i] = -1;
+    std::vector<int> levels;
+    for (int l = K; l >= 1; l--) levels.push_back(l);
+    const int g0 = (world + 1) / 2;
+    for (int dr = 0; dr < 2; dr++) {
+        const int first = (dr == 0 || world == 1) ? 0 : g0, nr = (dr == 0) ? g0 : (world == 1 ? 1 : world - g0);
+        const int g = std::max(1, std::min(nr, K));
+        std::vector<int> cuts, best_cuts; std::vector<double> best_cost;
+        plan_split_rec(levels, 0, g, cuts, whd, max_iters, best_cost, best_cuts);
+        // groups in the order coarse .. fine; the finest group goes to the direction's first rank
+        int b = 0;
+        for (int gi = 0; gi < g; gi++) {
+            const int e = gi < (int)best_cuts.size() ? best_cuts[gi] : K;
+            const int rank = first + (g - 1 - gi);
+            for (int i = b; i < e; i++) owner_out[2 * levels[i] + dr] = rank;
+            b = e;
+        }
+    }
+    return K;
+}
+
 // ---------------------------------------------------------------- pyramid
 int vm_pyramid_create(int device, vm_pyramid **out) {
     if (!out) { set_error("null out"); return VM_ERR_ARG; }
@@ -928,7 +992,7 @@ int vm_level_mark_v_valid(vm_pyramid *p, int level) {
 }
 int vm_dev_copy(int device, void *dst_dev, const void *src_dev, size_t nbytes, void *stream) {
     int rc = use_device(device); if (rc) return rc;
-    VM_CUDA(cudaMemcpyAsync(dst_dev, src_dev, nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    VM_CUDA(cudaMemcpyAsync(dst_dev, src_dev, nbytes, cudaMemcpyDefault, (cudaStream_t)stream));      // UVA: src may live on another GPU (peer copy)
     return VM_OK;
 }
 
