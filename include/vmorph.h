@@ -276,7 +276,12 @@ int vm_dev_alloc(int device, size_t nbytes, void **out_dev);
 int vm_dev_free(int device, void *dev);
 int vm_dev_upload(int device, void *dst_dev, const void *src_host, size_t nbytes, void *stream);
 int vm_dev_download(int device, void *dst_host, const void *src_dev, size_t nbytes, void *stream);
-int vm_dev_copy(int device, void *dst_dev, const void *src_dev, size_t nbytes, void *stream);
+int vm_dev_copy(int device, void *dst_dev, const void *src_dev, size_t nbytes, void *stream);   /* src may be another GPU's array */
+/* multi-GPU hosts in one process: direct GPU-to-GPU path for vm_dev_copy (else staged through the host); page-locking of the
+ * caller's host arrays so that the uploads of vm_pyramid_build* and the downloads run at the PCIe rate */
+int vm_device_enable_peer(int device, int peer_device);
+int vm_host_pin(void *host, size_t nbytes);
+int vm_host_unpin(void *host);
 int vm_stream_sync(int device, void *stream);
 /* counts kernels launched by this library since process start (bench.py's gpu_launches claim) */
 uint64_t vm_kernel_launch_count(void);

@@ -13,7 +13,7 @@
 //
 //   vmorph_video --size W H D --video0 v0.rgb --video1 v1.rgb --flows f0.bin f1.bin b0.bin b1.bin
 //                [--devices 0,1,2,3] [--settings settings.xml] [--start-res 8] [--max-iter 1000] [--voxel-cap N]
-//                [--vectors out.bin]
+//                [--vectors out.bin] [--repeat R]
 //   v*.rgb: D x H x W x 3 bytes (cv::Mat channel order); f/b*.bin: D x H x W x 2 float32; out.bin: D x H x W x 2 float32
 //   --devices: one entry per rank (the same device may appear several times: ranks then share it -- the one-GPU test).
 //
@@ -58,7 +58,7 @@ struct Shared {
     std::string err;
     Barrier *bar = nullptr;
     const uint8_t *v0 = nullptr, *v1 = nullptr; const float *fl[4] = {nullptr, nullptr, nullptr, nullptr};
-    vm_params prm; vm_tracks tr; int64_t cap = 14000000;
+    vm_params prm; vm_tracks tr; int64_t cap = 14000000; int repeat = 1;
     std::vector<double> opt_ms, build_ms;
     std::vector<float> *vectors_out = nullptr;
 };
@@ -96,9 +96,13 @@ bool rank_main(Shared &S, int r) {
         S.field_ptr[r][l * VM_FIELD_COUNT + field] = p; S.field_bytes[r][l * VM_FIELD_COUNT + field] = n;
         return true;
     };
+    RANK_TRY(vm_pyramid_create(dev, &pyr));
+    for (int q = 0; q < world; q++)                                   // direct GPU-to-GPU copies where the node has them (else staged: still correct)
+        if (S.devices[q] != dev) vm_device_enable_peer(dev, S.devices[q]);
+    std::vector<size_t> page(S.n_levels, 0);
+  for (int rep = 0; rep < S.repeat; rep++) {                          // --repeat: the whole job again (the reported times are the last run's)
     auto t0 = std::chrono::steady_clock::now();
     // ---------------- Pyramid::build, sharded by frame
-    RANK_TRY(vm_pyramid_create(dev, &pyr));
     const bool shard = world > 1 && d >= world;
     int Kb = 0;
     if (!shard) {
@@ -133,15 +137,17 @@ bool rank_main(Shared &S, int r) {
         if (S.failed) return false;
         RANK_TRY(vm_pyramid_build_finish(pyr, nullptr));
     }
-    RANK_TRY(vm_morph_create(&S.prm, pyr, nullptr, &m));
-    if (S.tr.n_groups > 0)
-        RANK_TRY(vm_morph_set_tracks(m, S.tr.n_left, S.tr.left_len, S.tr.left, S.tr.n_right, S.tr.right_len, S.tr.right, S.tr.n_groups, S.tr.group_len, S.tr.connects));
+    if (!m) {
+        RANK_TRY(vm_morph_create(&S.prm, pyr, nullptr, &m));
+        if (S.tr.n_groups > 0)
+            RANK_TRY(vm_morph_set_tracks(m, S.tr.n_left, S.tr.left_len, S.tr.left, S.tr.n_right, S.tr.right_len, S.tr.right, S.tr.n_groups, S.tr.group_len, S.tr.connects));
+    }
     for (int l = 1; l <= S.K; l++) if (!publish(l, VM_FIELD_V)) return false;
-    std::vector<size_t> page(S.n_levels, 0);
     for (int l = 1; l < S.n_levels; l++) { vm_level_info li; RANK_TRY(vm_pyramid_level_info(pyr, l, &li)); page[l] = (size_t)li.pagestride * 8; }
     RANK_TRY(vm_stream_sync(dev, nullptr));
     auto t1 = std::chrono::steady_clock::now();
     S.build_ms[r] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (r == 0) for (auto &x : S.ready) x.store(0);
     S.bar->wait();
     if (S.failed) return false;
 
@@ -205,6 +211,7 @@ bool rank_main(Shared &S, int r) {
     S.opt_ms[r] = std::chrono::duration<double, std::milli>(t3 - t2).count();
     S.bar->wait();                                                    // every chain is finished on its GPU
     if (S.failed) return false;
+  }
     // ---------------- GPU 0 collects the level-1 field (the halves of the two level-1 owners) and writes the vectors
     if (r == 0) {
         if (world > 1) {
@@ -236,6 +243,7 @@ int main(int argc, char **argv) {
         else if (a == "--devices") devs = next(); else if (a == "--settings") settings = next();
         else if (a == "--start-res") start_res = atoi(next()); else if (a == "--max-iter") max_iter = atoi(next());
         else if (a == "--voxel-cap") S.cap = atoll(next()); else if (a == "--vectors") vecs = next();
+        else if (a == "--repeat") { S.repeat = atoi(next()); if (S.repeat < 1) S.repeat = 1; }
         else if (a == "--version") { printf("%s (%d CUDA devices)\n", vm_version(), vm_device_count()); return 0; }
         else { fprintf(stderr, "usage: vmorph_video --size W H D --video0 v0.rgb --video1 v1.rgb --flows f0.bin f1.bin b0.bin b1.bin [--devices 0,1,..]\n"
                                "                    [--settings settings.xml] [--start-res N] [--max-iter N] [--voxel-cap N] [--vectors out.bin] | --version\n"); return 2; }
@@ -255,6 +263,10 @@ int main(int argc, char **argv) {
     if (!read_file(p0, v0.data(), v0.size()) || !read_file(p1, v1.data(), v1.size())) { fprintf(stderr, "vmorph_video: cannot read the videos\n"); return 2; }
     for (int k = 0; k < 4; k++) { fl[k].resize(npx * 2); if (!read_file(pf[k], fl[k].data(), npx * 8)) { fprintf(stderr, "vmorph_video: cannot read %s\n", pf[k].c_str()); return 2; } }
     S.v0 = v0.data(); S.v1 = v1.data(); for (int k = 0; k < 4; k++) S.fl[k] = fl[k].data();
+    if (vm_device_count() > 0) {                                      // page-lock the inputs: uploads at the PCIe rate
+        vm_host_pin(v0.data(), v0.size()); vm_host_pin(v1.data(), v1.size());
+        for (int k = 0; k < 4; k++) vm_host_pin(fl[k].data(), npx * 8);
+    }
     vm_params_default(&S.prm); memset(&S.tr, 0, sizeof(S.tr));
     if (!settings.empty() && vm_params_parse_xml(settings.c_str(), &S.prm, &S.tr) < 0) { fprintf(stderr, "vmorph_video: %s\n", vm_last_error()); return 3; }
     if (max_iter > 0) S.prm.max_iter = max_iter;
@@ -292,5 +304,7 @@ int main(int argc, char **argv) {
     for (int l = 1; l <= S.K; l++) printf("%s[%d, %d]", l > 1 ? ", " : "", S.owner[2 * l], S.owner[2 * l + 1]);
     printf("], \"kernel_launches\": %llu}\n", (unsigned long long)vm_kernel_launch_count());
     vm_tracks_free(&S.tr);
+    vm_host_unpin(v0.data()); vm_host_unpin(v1.data());
+    for (int k = 0; k < 4; k++) vm_host_unpin(fl[k].data());
     return 0;
 }

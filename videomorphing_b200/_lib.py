@@ -39,7 +39,7 @@ class VmTracks(C.Structure):
 EXPORTS = [
     "vm_last_error", "vm_device_count", "vm_version", "vm_params_default", "vm_params_parse_xml", "vm_params_write_xml", "vm_tracks_free",
     "vm_pyramid_create", "vm_pyramid_destroy", "vm_level_schedule", "vm_pyramid_alloc", "vm_pyramid_build",
-    "vm_pyramid_build_frames", "vm_pyramid_build_finish", "vm_wavefront_plan",
+    "vm_pyramid_build_frames", "vm_pyramid_build_finish", "vm_wavefront_plan", "vm_device_enable_peer", "vm_host_pin", "vm_host_unpin",
     "vm_pyramid_num_levels", "vm_pyramid_level_info", "vm_level_get", "vm_level_set", "vm_morph_create", "vm_morph_destroy",
     "vm_morph_set_tracks", "vm_morph_set_constraints", "vm_morph_run", "vm_morph_progress", "vm_morph_executed_pixel_iters",
     "vm_morph_sweep_ms", "vm_morph_attempted_updates", "vm_morph_sweep_busy_ms", "vm_morph_updates_log", "vm_morph_ms_log", "vm_morph_iters_log", "vm_level_cpu_solve", "vm_level_upsample", "vm_level_initialize", "vm_level_init_temp", "vm_level_upsample_frames", "vm_level_initialize_frames",
@@ -75,6 +75,9 @@ def load():
     L.vm_pyramid_build.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp]
     L.vm_pyramid_build_frames.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i32, i32, vp]
     L.vm_pyramid_build_finish.argtypes = [vp, vp]
+    L.vm_device_enable_peer.argtypes = [i32, i32]
+    L.vm_host_pin.argtypes = [vp, C.c_size_t]
+    L.vm_host_unpin.argtypes = [vp]
     L.vm_wavefront_plan.argtypes = [i32, C.POINTER(C.c_int32), C.POINTER(f32), i32, C.POINTER(C.c_int32)]
     L.vm_pyramid_num_levels.argtypes = [vp]
     L.vm_pyramid_level_info.argtypes = [vp, i32, C.POINTER(VmLevelInfo)]

@@ -990,6 +990,35 @@ int vm_level_mark_v_valid(vm_pyramid *p, int level) {
     p->lv[level].v_valid = true;
     return VM_OK;
 }
+// Direct GPU-to-GPU copies (NVLink) for vm_dev_copy between the arrays of two devices; without it such a copy is staged
+// through host memory.  Idempotent; a device without a peer path to `peer_device` is an error.
+int vm_device_enable_peer(int device, int peer_device) {
+    int rc = use_device(device); if (rc) return rc;
+    if (device == peer_device) return VM_OK;
+    int can = 0;
+    VM_CUDA(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    if (!can) { set_error("device %d cannot access device %d directly", device, peer_device); return VM_ERR_STATE; }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return VM_OK; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    return VM_OK;
+}
+// Page-locks a host array the caller owns (the videos / flows handed to vm_pyramid_build*, result buffers): H2D / D2H copies
+// of pinned memory run at the PCIe rate and asynchronously.  vm_host_unpin before the memory is freed.
+int vm_host_pin(void *host, size_t nbytes) {
+    if (!host || !nbytes) { set_error("vm_host_pin: null / empty range"); return VM_ERR_ARG; }
+    cudaError_t e = cudaHostRegister(host, nbytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return VM_OK; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostRegister");
+    return VM_OK;
+}
+int vm_host_unpin(void *host) {
+    if (!host) return VM_OK;
+    cudaError_t e = cudaHostUnregister(host);
+    if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return VM_OK; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostUnregister");
+    return VM_OK;
+}
 int vm_dev_copy(int device, void *dst_dev, const void *src_dev, size_t nbytes, void *stream) {
     int rc = use_device(device); if (rc) return rc;
     VM_CUDA(cudaMemcpyAsync(dst_dev, src_dev, nbytes, cudaMemcpyDefault, (cudaStream_t)stream));      // UVA: src may live on another GPU (peer copy)
