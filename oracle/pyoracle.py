@@ -59,6 +59,7 @@ def lib(native=False):
     L.vo_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.vo_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.vo_coarse_solve.argtypes = [C.c_void_p]
+    L.vo_coarse_assemble.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _fp]
     L.vo_upsample.argtypes = [C.c_void_p, C.c_int]
     L.vo_initialize_level.argtypes = [C.c_void_p, C.c_int]
     L.vo_initialize_temp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -203,6 +204,14 @@ class Oracle:
 
     def coarse_solve(self):
         self.L.vo_coarse_solve(self.h)
+
+    def coarse_assemble(self, z):
+        """The dense system (A, Bx, By) of frame z of the coarsest level as coarse_solve assembles it (morph.cu:433-561)."""
+        i = self.info(self.num_levels - 1)
+        num = i["w"] * i["h"]
+        A, bx, by = np.zeros((num, num), np.float32), np.zeros(num, np.float32), np.zeros(num, np.float32)
+        assert self.L.vo_coarse_assemble(self.h, z, _ptr(A, _fp), _ptr(bx, _fp), _ptr(by, _fp)) == num
+        return A, bx, by
 
     def upsample(self, dst):
         self.L.vo_upsample(self.h, dst)

@@ -48,6 +48,7 @@ def lib():
         L.ref_infill_frame.argtypes = [C.POINTER(RefLevelC), C.c_int]
         u8 = C.POINTER(C.c_uint8)
         L.ref_render_halfway.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, u8, u8, fp, fp]
+        L.ref_coarse_assemble.argtypes = [C.c_int] * 5 + [C.c_float, C.c_float] + [C.c_int] * 3 + [C.c_float] * 3 + [C.c_int, C.c_int, ip, fp, ip, fp, fp, fp, fp, fp]
         _lib = L
     return _lib
 
@@ -60,6 +61,26 @@ def stencils(impmask_rowstride):
     ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
     lib().ref_stencils_get(impmask_rowstride, io.ctypes.data_as(ip), im.ctypes.data_as(ip), off.ctypes.data_as(ip), tps.ctypes.data_as(fp))
     return io, im, off, tps
+
+
+def coarse_assemble(oracle, lp, lw, rp, rw):
+    """The reference's Morph::cpu_optimize_level (morph.cu:419-590) on the coarsest level of `oracle`'s pyramid: returns the
+    dense systems it assembles, A (d, num, num), Bx, By (d, num), and lvl.v (d, ps, 2) as its last loop stores the solution --
+    with the cv::Mat stand-in's "A^-1 B" = B (the inverse is OpenCV's, not reproduced here)."""
+    n = oracle.num_levels
+    i, i0 = oracle.info(n - 1), oracle.info(0)
+    num, d = i["w"] * i["h"], i["d"]
+    A, bx, by = np.zeros((d, num, num), np.float32), np.zeros((d, num), np.float32), np.zeros((d, num), np.float32)
+    v = np.zeros((d, i["pagestride"], 2), np.float32)
+    lp = np.ascontiguousarray(lp, np.int32).reshape(-1, 4); rp = np.ascontiguousarray(rp, np.int32).reshape(-1, 4)
+    lw = np.ascontiguousarray(lw, np.float32); rw = np.ascontiguousarray(rw, np.float32)
+    ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+    p = oracle.params
+    rc = lib().ref_coarse_assemble(i["w"], i["h"], d, i["rowstride"], i["pagestride"], i["inv_wh"], i["factor_d"], i0["w"], i0["h"], i0["d"], i0["factor_d"],
+                                   p["w_tps"], p["w_ui"], int(p["bcond"]), len(lp), lp.ctypes.data_as(ip), lw.ctypes.data_as(fp), rp.ctypes.data_as(ip), rw.ctypes.data_as(fp),
+                                   A.ctypes.data_as(fp), bx.ctypes.data_as(fp), by.ctypes.data_as(fp), v.ctypes.data_as(fp))
+    assert rc == 0
+    return A, bx, by, v
 
 
 def set_params(p):

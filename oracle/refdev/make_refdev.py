@@ -7,8 +7,8 @@ TEST INFRASTRUCTURE ONLY.  Nothing of the reference is copied into the repositor
 the reference files where they lie (by the anchors below, not by line number) into a temporary translation unit that is
 deleted after compilation; only the shared library lands in oracle/_ref/ (git-ignored, travels to the GPU box).
 The reference's headers (util/dmath.h, util/linalg.h, stencils.h, Pyramid.h, parameters.h) are included in place;
-stubs/ only holds three stand-ins for things that do not exist on this machine (OpenCV-C++, CUDA's internal
-device_functions.h, and the case-insensitive "pyramid.h").
+stubs/ only holds stand-ins for things that do not exist on this machine (OpenCV-C++: the handful of cv::Mat operations
+Morph::cpu_optimize_level uses; CUDA's internal device_functions.h; the case-insensitive "pyramid.h").
 
     python oracle/refdev/make_refdev.py [--ref /root/reference] [--keep]
 """
@@ -23,8 +23,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "..", "_ref")
 OUT = os.path.join(OUT_DIR, "libref_devfn.so")
 
-# (file, regex of the first line taken, regex of the first line NOT taken, regex of trailing lines to drop or None)
+# (file, regex of the first line taken, regex of the first line NOT taken, regex of trailing lines to drop or None[, substitutions])
 SPANS = [
+    # Morph::cpu_optimize_level                                      morph.cu:419-590.  The member function becomes a free function
+    # (ONE substitution, on its signature line: the body is the reference's text; m_params is passed in) because Morph's
+    # constructor and the rest of the class live in parts of morph.cu that need the GPU.  cv::Mat = stubs/opencv2/mat_stub.h.
+    ("Algorithm/morph.cu", r"^void Morph::cpu_optimize_level\(", r"^__constant__ KernParameters c_params;", r"^\s*$",
+     [(r"^void Morph::cpu_optimize_level\(PyramidLevel &lvl,PyramidLevel &lv0\)", "static void ref_cpu_optimize_level(Parameters &m_params, PyramidLevel &lvl, PyramidLevel &lv0)")]),
     # isignbit, calc_border, ssim                                   morph.cu:35-118
     ("Algorithm/morph.cu", r"^__device__ int isignbit\(", r"^// Level processing", None),
     # INIT_* constants, kernel_initialize_level, init_improving_mask  morph.cu:170-261
@@ -38,7 +43,7 @@ SPANS = [
 ]
 
 
-def cut(text, first, stop, drop, fname):
+def cut(text, first, stop, drop, fname, subs=()):
     lines = text.split("\n")
     a = next((i for i, l in enumerate(lines) if re.search(first, l)), None)
     if a is None:
@@ -48,7 +53,13 @@ def cut(text, first, stop, drop, fname):
         raise SystemExit(f"{fname}: stop anchor {stop!r} not found")
     while drop and b > a and re.search(drop, lines[b - 1]):
         b -= 1
-    return f"// ---- {fname}:{a + 1}-{b} (extracted at build time) ----\n" + "\n".join(lines[a:b]) + "\n"
+    body = lines[a:b]
+    for pat, rep in subs:
+        hits = [i for i, l in enumerate(body) if re.search(pat, l)]
+        if len(hits) != 1:
+            raise SystemExit(f"{fname}: substitution anchor {pat!r} matched {len(hits)} lines")
+        body[hits[0]] = re.sub(pat, rep, body[hits[0]])
+    return f"// ---- {fname}:{a + 1}-{b} (extracted at build time) ----\n" + "\n".join(body) + "\n"
 
 
 def main():
@@ -62,9 +73,10 @@ def main():
         return 0
     os.makedirs(OUT_DIR, exist_ok=True)
     parts = ['#include "simt.h"\n#include <util/dmath.h>\n#include <util/linalg.h>\n#include "stencils.h"\n#include "Pyramid.h"\n#include "prelude.h"\n']
-    for fname, first, stop, drop in SPANS:
+    for span in SPANS:
+        fname, first, stop, drop = span[:4]
         with open(os.path.join(ref, fname), encoding="latin-1") as f:
-            parts.append(cut(f.read().replace("\r\n", "\n"), first, stop, drop, fname))
+            parts.append(cut(f.read().replace("\r\n", "\n"), first, stop, drop, fname, span[4] if len(span) > 4 else ()))
     parts.append('#include "capi.inc"\n')
     tmp = tempfile.mkdtemp(prefix="refdev_")
     tu = os.path.join(tmp, "refdev_tu.cpp")

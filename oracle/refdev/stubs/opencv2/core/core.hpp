@@ -1,4 +1,5 @@
 // oracle/refdev/stubs/opencv2/core/core.hpp -- stand-in: the reference headers Pyramid.h / parameters.h only NAME cv::Mat
-// in declarations (std::vector<cv::Mat>&); OpenCV-C++ is not installed here and none of it is called by the device code.
+// in declarations (std::vector<cv::Mat>&); Morph::cpu_optimize_level uses the handful of operations of mat_stub.h.
+// OpenCV-C++ is not installed here.
 #pragma once
-namespace cv { class Mat; }
+#include "../mat_stub.h"

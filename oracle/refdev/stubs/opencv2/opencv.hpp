@@ -1,4 +1,3 @@
-// oracle/refdev/stubs/opencv2/opencv.hpp -- stand-in: the reference headers Pyramid.h / parameters.h only NAME cv::Mat
-// in declarations (std::vector<cv::Mat>&); OpenCV-C++ is not installed here and none of it is called by the device code.
+// oracle/refdev/stubs/opencv2/opencv.hpp -- stand-in (see core/core.hpp, mat_stub.h): OpenCV-C++ is not installed here.
 #pragma once
-namespace cv { class Mat; }
+#include "mat_stub.h"

@@ -18,9 +18,12 @@
 //      whole launches, frames and pyramids (sum_mode = 0), tests/test_oracle_refdev.py;
 //  (d) temp_ref / interpolate_temp_ref / kernel_initialize_temp / smooth / fill_zeros_x (upsample.cu): the same way,
 //      within 2e-5 (float atomics there, order-free fixed point here);
-//  (e) the reference-internal cross-checks of SURVEY.md section 4.
-// Still "parity unpinned" (host / third-party code of the reference that cannot run here): the coarse dense solve
-// (cv::Mat::inv, D4), rod::upsample's hardware-bilinear prolongation, the host UI splat, MatchingThread's Resize,
+//  (e) Morph::cpu_optimize_level (morph.cu:419-590): the reference's text on the host with a cv::Mat stand-in -- the dense
+//      systems it ASSEMBLES (TPS rows, UI splat, boundary conditions, every frame) and the layout of the stored solution
+//      are bit-equal (tests/test_oracle_refdev.py::test_coarse_system_*); the inverse itself is OpenCV's cv::Mat::inv (D4);
+//  (f) the reference-internal cross-checks of SURVEY.md section 4.
+// Still "parity unpinned" (host / third-party code of the reference that cannot run here): the INVERSE of the coarse dense
+// system (cv::Mat::inv, D4), rod::upsample's hardware-bilinear prolongation, the host UI splat, MatchingThread's Resize,
 // QuadraticPath (cuBLAS / cuSPARSE CG, D6).  The texture unit itself (D1) and -use_fast_math are not modelled.
 //
 // Each function cites the reference file:line it follows
@@ -136,6 +139,7 @@ void pyramid_build(Pyramid &P, const uint8_t *rgb0, const uint8_t *rgb1,
 
 // --- optimizer ---
 void coarse_solve(Pyramid &P);                                              // morph.cu:419-590
+void coarse_assemble(Pyramid &P, int z, std::vector<float> &A, std::vector<float> &Bx, std::vector<float> &By);   // morph.cu:433-561
 void upsample_level(Pyramid &P, int dst);                                   // upsample.cu:260-340
 void initialize_level(Pyramid &P, int l);                                   // morph.cu:264-390
 void initialize_temp(Pyramid &P, int l, int frame, int dir);                // upsample.cu:214-258

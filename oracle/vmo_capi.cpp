@@ -108,6 +108,16 @@ int vo_set(void *h, int l, int id, const void *in) {
 }
 
 void vo_coarse_solve(void *h) { coarse_solve(*static_cast<Pyramid *>(h)); }
+// the assembled dense system of frame z of the coarsest level: A (num*num), Bx, By (num); returns num
+int vo_coarse_assemble(void *h, int z, float *A_out, float *Bx_out, float *By_out) {
+    Pyramid &P = *static_cast<Pyramid *>(h);
+    std::vector<float> A, Bx, By;
+    coarse_assemble(P, z, A, Bx, By);
+    if (A_out) memcpy(A_out, A.data(), sizeof(float) * A.size());
+    if (Bx_out) memcpy(Bx_out, Bx.data(), sizeof(float) * Bx.size());
+    if (By_out) memcpy(By_out, By.data(), sizeof(float) * By.size());
+    return (int)Bx.size();
+}
 void vo_upsample(void *h, int dst) { upsample_level(*static_cast<Pyramid *>(h), dst); }
 void vo_initialize_level(void *h, int l) { initialize_level(*static_cast<Pyramid *>(h), l); }
 void vo_initialize_temp(void *h, int l, int frame, int dir) { initialize_temp(*static_cast<Pyramid *>(h), l, frame, dir); }

@@ -288,15 +288,16 @@ static void solve_dense(std::vector<float> &Af, std::vector<float> &Bx, std::vec
     }
 }
 
-void coarse_solve(Pyramid &P) {
+// the dense system of frame z, assembled in the reference's statement order (morph.cu:433-561); checked against the
+// reference's own text in tests/test_oracle_refdev.py::test_coarse_system_*
+void coarse_assemble(Pyramid &P, int z, std::vector<float> &A, std::vector<float> &Bx, std::vector<float> &By) {
     Level &lvl = P.lv.back(); Level &lv0 = P.lv[0];
     const Params &pr = P.prm;
     int w = lvl.w, h = lvl.h, d = lvl.d;
     int factor = (int)(lv0.factor_d / lvl.factor_d);       // morph.cu:425
     int num = w * h;
-    lvl.v.assign((size_t)lvl.ps * d, mk2(0, 0));           // morph.cu:428-429
-    for (int z = 0; z < d; z++) {
-        std::vector<float> A((size_t)num * num, 0.0f), Bx(num, 0.0f), By(num, 0.0f), X, Y;
+    {
+        A.assign((size_t)num * num, 0.0f); Bx.assign(num, 0.0f); By.assign(num, 0.0f);
         auto at = [&](int i, int j) -> float & { return A[(size_t)i * num + j]; };
         const float wt = pr.w_tps;
         for (int y = 0; y < h; y++)
@@ -343,6 +344,17 @@ void coarse_solve(Pyramid &P) {
                 for (int y = 1; y < h - 1; y++) { int i1 = y * w; at(i1, i1) += bd; int i2 = y * w + w - 1; at(i2, i2) += bd; }
             }
         }
+    }
+}
+
+void coarse_solve(Pyramid &P) {
+    Level &lvl = P.lv.back();
+    int w = lvl.w, h = lvl.h, d = lvl.d;
+    int num = w * h;
+    lvl.v.assign((size_t)lvl.ps * d, mk2(0, 0));           // morph.cu:428-429
+    for (int z = 0; z < d; z++) {
+        std::vector<float> A, Bx, By, X, Y;
+        coarse_assemble(P, z, A, Bx, By);
         solve_dense(A, Bx, By, num, X, Y);                  // morph.cu:565-570 (D4)
         for (int y = 0; y < h; ++y)
             for (int x = 0; x < w; ++x) {                   // morph.cu:574-584

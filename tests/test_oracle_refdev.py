@@ -216,3 +216,40 @@ def test_render_equals_reference_kernel(oracle_lib, color_from):
         a = rd.render_halfway(w, h, ex, fa, fa, color_from, e0, e1, vec, q)
         b = oracle_lib.render_halfway(w, h, ex, fa, fa, color_from, e0, e1, vec, q)
         np.testing.assert_array_equal(a[:, :w], b[:, :w])
+
+
+@pytest.mark.parametrize("bcond", [0, 1, 2])
+def test_coarse_system_is_the_reference_s_own_assembly(oracle_lib, bcond):
+    """Morph::cpu_optimize_level (morph.cu:419-590) cut out of the reference and run on the host with a cv::Mat stand-in: the
+    dense systems it assembles (TPS stencil rows, UI constraints splatted bilinearly with the frame test of morph.cu:472-479,
+    the three boundary conditions incl. BCOND_BORDER's repetition over the frames) equal the oracle's bit for bit for every
+    frame, and its final loop stores the solution where the oracle stores it.  (The inverse itself is OpenCV's cv::Mat::inv,
+    a third-party operation: oracle deviation D4.)"""
+    from videomorphing_b200 import synth
+    w, h, d = 96, 64, 9
+    v0, v1, flows, field = synth.video_pair(w, h, d, 71, 72, 3.0)
+    o = oracle_lib.Oracle(dict(start_res=4, bcond=bcond, w_ui=1234.5, w_tps=0.07))
+    lp, lw, rp, rw = synth.video_tracks(w, h, d, 73, 72, field, ntracks=3, margin=12)
+    lw = np.asarray(lw, np.float32) * np.float32(0.75)            # unequal weights: MIN(l, r) matters
+    o.set_constraints(lp, lw, rp, rw)
+    n = o.build(v0, v1, flows, voxel_cap=1 << 62)
+    i = o.info(n - 1)
+    assert i["d"] > 1                                             # several coarse frames: conz = min(z * factor, d0 - 1)
+    A, bx, by, v = rd.coarse_assemble(o, lp, lw, rp, rw)
+    num = i["w"] * i["h"]
+    hit = 0
+    for z in range(i["d"]):
+        Ao, bxo, byo = o.coarse_assemble(z)
+        np.testing.assert_array_equal(A[z], Ao)
+        np.testing.assert_array_equal(bx[z], bxo)
+        np.testing.assert_array_equal(by[z], byo)
+        hit += int(np.count_nonzero(bxo) + np.count_nonzero(byo))
+        # layout of the stored solution (stand-in X = Bx, Y = By): element (x, y) of frame z at y * rowstride + x of page z
+        # (the reference's staging array is a bare new[]: the row padding holds whatever was there)
+        idx = (np.arange(i["h"])[:, None] * i["rowstride"] + np.arange(i["w"])[None, :]).ravel()
+        np.testing.assert_array_equal(v[z][idx, 0], bx[z])
+        np.testing.assert_array_equal(v[z][idx, 1], by[z])
+    assert hit > 0                                                # the UI constraints reached the right-hand sides
+    o.coarse_solve()
+    vo = o.get(n - 1, "v")
+    assert vo.shape[0] == i["d"] and np.isfinite(vo).all()
