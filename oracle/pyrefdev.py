@@ -48,6 +48,7 @@ def lib():
         L.ref_infill_frame.argtypes = [C.POINTER(RefLevelC), C.c_int]
         u8 = C.POINTER(C.c_uint8)
         L.ref_render_halfway.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, u8, u8, fp, fp]
+        L.ref_ui_splat_level.argtypes = [C.POINTER(RefLevelC), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, ip, fp, ip, fp]
         L.ref_coarse_assemble.argtypes = [C.c_int] * 5 + [C.c_float, C.c_float] + [C.c_int] * 3 + [C.c_float] * 3 + [C.c_int, C.c_int, ip, fp, ip, fp, fp, fp, fp, fp]
         _lib = L
     return _lib
@@ -133,6 +134,15 @@ class RefLevel:
 
     def infill_frame(self, frame):
         lib().ref_infill_frame(C.byref(self.c), frame)
+
+    def ui_splat(self, info0, lp, lw, rp, rw):
+        """The host loop at the end of Morph::initialize_level (morph.cu:341-388): ui_axy / ui_b of this level from its v."""
+        lp = np.ascontiguousarray(lp, np.int32).reshape(-1, 4); rp = np.ascontiguousarray(rp, np.int32).reshape(-1, 4)
+        lw = np.ascontiguousarray(lw, np.float32); rw = np.ascontiguousarray(rw, np.float32)
+        ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+        rc = lib().ref_ui_splat_level(C.byref(self.c), info0["w"], info0["h"], info0["d"], info0["factor_d"], len(lp),
+                                      lp.ctypes.data_as(ip), lw.ctypes.data_as(fp), rp.ctypes.data_as(ip), rw.ctypes.data_as(fp))
+        assert rc == 0
 
 
 def render_halfway(w, h, ex, color_fa, geo_fa, color_from, ext0, ext1, vec, qpath=None):

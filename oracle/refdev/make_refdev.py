@@ -23,13 +23,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "..", "_ref")
 OUT = os.path.join(OUT_DIR, "libref_devfn.so")
 
-# (file, regex of the first line taken, regex of the first line NOT taken, regex of trailing lines to drop or None[, substitutions])
+# (file, regex of the first line taken, regex of the first line NOT taken, regex of trailing lines to drop or None
+#  [, substitutions [, prefix, suffix]])
 SPANS = [
     # Morph::cpu_optimize_level                                      morph.cu:419-590.  The member function becomes a free function
     # (ONE substitution, on its signature line: the body is the reference's text; m_params is passed in) because Morph's
     # constructor and the rest of the class live in parts of morph.cu that need the GPU.  cv::Mat = stubs/opencv2/mat_stub.h.
     ("Algorithm/morph.cu", r"^void Morph::cpu_optimize_level\(", r"^__constant__ KernParameters c_params;", r"^\s*$",
      [(r"^void Morph::cpu_optimize_level\(PyramidLevel &lvl,PyramidLevel &lv0\)", "static void ref_cpu_optimize_level(Parameters &m_params, PyramidLevel &lvl, PyramidLevel &lv0)")]),
+    # the host UI splat at the end of Morph::initialize_level          morph.cu:341-388.  Only the tail of that function can be
+    # compiled here (its head launches kernels); the cut lines are wrapped (prefix / suffix below, not reference text) into a
+    # function with the three names the body uses.  fabs / floor / ceil of a float are the float overloads, as under MSVC.
+    ("Algorithm/morph.cu", r"^\s*// initialize ui data in cpu", r"^void Morph::clear_level", r"^\s*$|^\}\s*$", [],
+     "namespace ref_host { using std::fabs; using std::floor; using std::ceil;\nstatic void ref_ui_splat(Parameters &m_params, PyramidLevel &lvl, PyramidLevel &lv0)\n{\n", "}\n}\n"),
     # isignbit, calc_border, ssim                                   morph.cu:35-118
     ("Algorithm/morph.cu", r"^__device__ int isignbit\(", r"^// Level processing", None),
     # INIT_* constants, kernel_initialize_level, init_improving_mask  morph.cu:170-261
@@ -43,7 +49,7 @@ SPANS = [
 ]
 
 
-def cut(text, first, stop, drop, fname, subs=()):
+def cut(text, first, stop, drop, fname, subs=(), prefix="", suffix=""):
     lines = text.split("\n")
     a = next((i for i, l in enumerate(lines) if re.search(first, l)), None)
     if a is None:
@@ -59,7 +65,7 @@ def cut(text, first, stop, drop, fname, subs=()):
         if len(hits) != 1:
             raise SystemExit(f"{fname}: substitution anchor {pat!r} matched {len(hits)} lines")
         body[hits[0]] = re.sub(pat, rep, body[hits[0]])
-    return f"// ---- {fname}:{a + 1}-{b} (extracted at build time) ----\n" + "\n".join(body) + "\n"
+    return f"// ---- {fname}:{a + 1}-{b} (extracted at build time) ----\n" + prefix + "\n".join(body) + "\n" + suffix
 
 
 def main():
@@ -72,11 +78,12 @@ def main():
         print(f"reference tree absent ({ref}): keeping prebuilt oracle/_ref/libref_devfn.so")
         return 0
     os.makedirs(OUT_DIR, exist_ok=True)
-    parts = ['#include "simt.h"\n#include <util/dmath.h>\n#include <util/linalg.h>\n#include "stencils.h"\n#include "Pyramid.h"\n#include "prelude.h"\n']
+    parts = ['#include <cmath>\n#include "simt.h"\n#include <util/dmath.h>\n#include <util/linalg.h>\n#include "stencils.h"\n#include "Pyramid.h"\n#include "prelude.h"\n']
     for span in SPANS:
         fname, first, stop, drop = span[:4]
         with open(os.path.join(ref, fname), encoding="latin-1") as f:
-            parts.append(cut(f.read().replace("\r\n", "\n"), first, stop, drop, fname, span[4] if len(span) > 4 else ()))
+            parts.append(cut(f.read().replace("\r\n", "\n"), first, stop, drop, fname, span[4] if len(span) > 4 else (),
+                             span[5] if len(span) > 5 else "", span[6] if len(span) > 6 else ""))
     parts.append('#include "capi.inc"\n')
     tmp = tempfile.mkdtemp(prefix="refdev_")
     tu = os.path.join(tmp, "refdev_tu.cpp")

@@ -21,10 +21,12 @@
 //  (e) Morph::cpu_optimize_level (morph.cu:419-590): the reference's text on the host with a cv::Mat stand-in -- the dense
 //      systems it ASSEMBLES (TPS rows, UI splat, boundary conditions, every frame) and the layout of the stored solution
 //      are bit-equal (tests/test_oracle_refdev.py::test_coarse_system_*); the inverse itself is OpenCV's cv::Mat::inv (D4);
-//  (f) the reference-internal cross-checks of SURVEY.md section 4.
+//  (f) the host UI splat at the end of Morph::initialize_level (morph.cu:341-388): the reference's loop, cut out and wrapped
+//      into a function, bit-equal on every level of a video (tests/test_oracle_refdev.py::test_ui_splat_*);
+//  (g) the reference-internal cross-checks of SURVEY.md section 4.
 // Still "parity unpinned" (host / third-party code of the reference that cannot run here): the INVERSE of the coarse dense
-// system (cv::Mat::inv, D4), rod::upsample's hardware-bilinear prolongation, the host UI splat, MatchingThread's Resize,
-// QuadraticPath (cuBLAS / cuSPARSE CG, D6).  The texture unit itself (D1) and -use_fast_math are not modelled.
+// system (cv::Mat::inv, D4), rod::upsample's hardware-bilinear prolongation, MatchingThread's Resize, QuadraticPath
+// (cuBLAS / cuSPARSE CG, D6).  The texture unit itself (D1) and -use_fast_math are not modelled.
 //
 // Each function cites the reference file:line it follows
 // (paths relative to /root/reference).

@@ -253,3 +253,32 @@ def test_coarse_system_is_the_reference_s_own_assembly(oracle_lib, bcond):
     o.coarse_solve()
     vo = o.get(n - 1, "v")
     assert vo.shape[0] == i["d"] and np.isfinite(vo).all()
+
+
+def test_ui_splat_is_the_reference_s_own_host_loop(oracle_lib):
+    """The host loop at the end of Morph::initialize_level (morph.cu:341-388: every UI pair splatted bilinearly into ui.axy /
+    ui.b of the frames it belongs to, against the level's current v) cut out of the reference: bit-equal to the oracle's
+    initialize_level on every level of a video -- levels with all frames and temporally halved ones (conz = min(z * factor,
+    d0 - 1)), unequal weights, a non-zero field."""
+    from videomorphing_b200 import synth
+    w, h, d = 64, 48, 17                                         # levels 64x48 .. 16x12 x 17 frames, 8x6 x 9 (halved), dense solve 4x3 x 5
+    v0, v1, flows, field = synth.video_pair(w, h, d, 81, 82, 3.0)
+    o = oracle_lib.Oracle(dict(start_res=4, w_ui=777.0))
+    lp, lw, rp, rw = synth.video_tracks(w, h, d, 83, 82, field, ntracks=5, margin=8)
+    lw = np.asarray(lw, np.float32) * np.float32(0.6)
+    o.set_constraints(lp, lw, rp, rw)
+    n = o.build(v0, v1, flows, voxel_cap=1 << 62)
+    o.coarse_solve()
+    seen_halved = False
+    for l in range(n - 2, 0, -1):
+        o.upsample(l)                                            # a non-zero v at this level
+        i = o.info(l)
+        seen_halved |= i["d"] < d
+        R = rd.RefLevel(o, l)
+        o.initialize_level(l)
+        R.a["ui_axy"][...] = 0; R.a["ui_b"][...] = 0
+        R.ui_splat(o.info(0), lp, lw, rp, rw)
+        assert np.count_nonzero(R.a["ui_axy"]) > 0
+        np.testing.assert_array_equal(R.a["ui_axy"], o.get(l, "ui_axy"), err_msg=f"level {l}")
+        np.testing.assert_array_equal(R.a["ui_b"], o.get(l, "ui_b"), err_msg=f"level {l}")
+    assert seen_halved
