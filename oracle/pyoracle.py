@@ -285,6 +285,27 @@ def render_halfway(w, h, ex, color_fa, geo_fa, color_from, ext0, ext1, vec, qpat
     return out
 
 
+def qpath_system(vec):
+    """Right-hand sides (Bx, By) of the two Poisson systems of one frame (QuadraticPath.cpp:24-169)."""
+    vec = np.ascontiguousarray(vec, np.float32)
+    h, w, _ = vec.shape
+    bx, by = np.zeros(h * w, np.float32), np.zeros(h * w, np.float32)
+    L = lib()
+    L.vo_qpath_system.argtypes = [_fp, C.c_int, C.c_int, _fp, _fp]
+    L.vo_qpath_system(_ptr(vec, _fp), w, h, _ptr(bx, _fp), _ptr(by, _fp))
+    return bx, by
+
+
+def qpath_apply(p, w, h):
+    """The 5-point operator of QuadraticPath.cpp:170-202 applied to p (h*w floats)."""
+    p = np.ascontiguousarray(p, np.float32)
+    out = np.zeros(h * w, np.float32)
+    L = lib()
+    L.vo_qpath_apply.argtypes = [_fp, _fp, C.c_int, C.c_int]
+    L.vo_qpath_apply(_ptr(p, _fp), _ptr(out, _fp), w, h)
+    return out
+
+
 def qpath_optimize(vec, max_iter=10000, tol=1e-12):
     vec = np.ascontiguousarray(vec, np.float32)
     h, w, _ = vec.shape

@@ -49,6 +49,7 @@ def lib():
         u8 = C.POINTER(C.c_uint8)
         L.ref_render_halfway.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, u8, u8, fp, fp]
         L.ref_ui_splat_level.argtypes = [C.POINTER(RefLevelC), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, ip, fp, ip, fp]
+        L.ref_qpath_assemble.argtypes = [fp, C.c_int, C.c_int, fp, fp, fp, ip, ip, fp]
         L.ref_coarse_assemble.argtypes = [C.c_int] * 5 + [C.c_float, C.c_float] + [C.c_int] * 3 + [C.c_float] * 3 + [C.c_int, C.c_int, ip, fp, ip, fp, fp, fp, fp, fp]
         _lib = L
     return _lib
@@ -82,6 +83,22 @@ def coarse_assemble(oracle, lp, lw, rp, rw):
                                    A.ctypes.data_as(fp), bx.ctypes.data_as(fp), by.ctypes.data_as(fp), v.ctypes.data_as(fp))
     assert rc == 0
     return A, bx, by, v
+
+
+def qpath_assemble(vec):
+    """CQuadraticPath::optimize (QuadraticPath.cpp:24-223) of the reference for one frame with a recording solver: returns
+    Bx, By, the CSR matrix (values, rowindex, columns) and the pasted result (h, w, 2) for the stand-in solution X = B."""
+    vec = np.ascontiguousarray(vec, np.float32)
+    h, w, _ = vec.shape
+    N = h * w
+    bx, by = np.zeros(N, np.float32), np.zeros(N, np.float32)
+    A, col, row = np.zeros(5 * N, np.float32), np.zeros(5 * N, np.int32), np.zeros(N + 1, np.int32)
+    qp = np.zeros((h, w, 2), np.float32)
+    ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+    nz = lib().ref_qpath_assemble(vec.ctypes.data_as(fp), w, h, bx.ctypes.data_as(fp), by.ctypes.data_as(fp), A.ctypes.data_as(fp),
+                                  row.ctypes.data_as(ip), col.ctypes.data_as(ip), qp.ctypes.data_as(fp))
+    assert nz > 0
+    return bx, by, A[:nz], row, col[:nz], qp
 
 
 def set_params(p):

@@ -36,6 +36,14 @@ SPANS = [
     # function with the three names the body uses.  fabs / floor / ceil of a float are the float overloads, as under MSVC.
     ("Algorithm/morph.cu", r"^\s*// initialize ui data in cpu", r"^void Morph::clear_level", r"^\s*$|^\}\s*$", [],
      "namespace ref_host { using std::fabs; using std::floor; using std::ceil;\nstatic void ref_ui_splat(Parameters &m_params, PyramidLevel &lvl, PyramidLevel &lv0)\n{\n", "}\n}\n"),
+    # CQuadraticPath::optimize                                         QuadraticPath.cpp:24-223: blended Jacobians, the right-hand
+    # sides and the CSR matrix of the two Poisson systems.  The class is a QThread; its optimize() becomes a member of a plain
+    # struct with the same member names (ONE substitution, on the signature line), whose cudaSolver (cuSPARSE / cuBLAS in the
+    # reference, QuadraticPath.cpp:225-318) records the system it is handed.  sqrt of a float is the float overload, as under MSVC.
+    ("Algorithm/QuadraticPath.cpp", r"^void CQuadraticPath::optimize\(\)", r"^void CQuadraticPath::cudaSolver\(", r"^\s*$",
+     [(r"^void CQuadraticPath::optimize\(\)", "void RefQPath::optimize()")],
+     "namespace ref_host { using std::sqrt; using cv::Vec2f;\nstruct RefQPath { std::vector<cv::Mat> &_vector, &_qpath; int times, rows, cols;\n"
+     "    void cudaSolver(float *A, int *rowindex, int *columns, int N, int nz, float *B, float *X); void optimize(); };\n", "}\n"),
     # isignbit, calc_border, ssim                                   morph.cu:35-118
     ("Algorithm/morph.cu", r"^__device__ int isignbit\(", r"^// Level processing", None),
     # INIT_* constants, kernel_initialize_level, init_improving_mask  morph.cu:170-261
@@ -78,7 +86,7 @@ def main():
         print(f"reference tree absent ({ref}): keeping prebuilt oracle/_ref/libref_devfn.so")
         return 0
     os.makedirs(OUT_DIR, exist_ok=True)
-    parts = ['#include <cmath>\n#include "simt.h"\n#include <util/dmath.h>\n#include <util/linalg.h>\n#include "stencils.h"\n#include "Pyramid.h"\n#include "prelude.h"\n']
+    parts = ['#include <cmath>\n#include <ctime>\n#include "simt.h"\n#include <util/dmath.h>\n#include <util/linalg.h>\n#include "stencils.h"\n#include "Pyramid.h"\n#include "prelude.h"\n']
     for span in SPANS:
         fname, first, stop, drop = span[:4]
         with open(os.path.join(ref, fname), encoding="latin-1") as f:

@@ -1,6 +1,6 @@
 // oracle/refdev/stubs/opencv2/mat_stub.h -- stand-in for the few cv::Mat operations Morph::cpu_optimize_level uses
-// (morph.cu:433-437 zeros, 440-561 at<float>, 565-570 inv / countNonZero / operator*, 581-582 at<float>).  OpenCV-C++ is
-// not installed here.  The ASSEMBLY of the dense system is the reference's text running on this class; the inverse itself
+// (morph.cu:433-437 zeros, 440-561 at<float>, 565-570 inv / countNonZero / operator*, 581-582 at<float>) and for the
+// at<Vec2f>(y, x) element access of CQuadraticPath::optimize (QuadraticPath.cpp:38-64, 213).  OpenCV-C++ is not installed here.  The ASSEMBLY of the dense system is the reference's text running on this class; the inverse itself
 // (cv::Mat::inv of OpenCV, a third-party operation) is NOT reproduced: inv() only marks the matrix, and the product
 // "A^-1 * B" RECORDS (A, B) for the test and returns B, so that the reference's load of X / Y into lvl.v (morph.cu:573-584)
 // can be checked for its layout.  The oracle's own solve is deviation D4 (oracle/vmo.h).  TEST INFRASTRUCTURE ONLY.
@@ -15,13 +15,21 @@
 #endif
 namespace cv {
 enum { DECOMP_LU = 0, DECOMP_SVD = 1 };
+struct Vec2f {
+    float val[2];
+    Vec2f() { val[0] = val[1] = 0.0f; }
+    Vec2f(float a, float b) { val[0] = a; val[1] = b; }
+    float &operator[](int i) { return val[i]; }
+    const float &operator[](int i) const { return val[i]; }
+};
 class Mat {
 public:
     int rows = 0, cols = 0;
     bool inverse = false;
-    std::vector<float> d;
+    std::vector<float> d;                            // rows * cols elements of sizeof(T) / 4 floats each
     static Mat zeros(int r, int c, int) { Mat m; m.rows = r; m.cols = c; m.d.assign((size_t)r * c, 0.0f); return m; }
-    template <class T> T &at(int i, int j) { return d[(size_t)i * cols + j]; }
+    static Mat zeros2(int r, int c) { Mat m; m.rows = r; m.cols = c; m.d.assign((size_t)r * c * 2, 0.0f); return m; }   // CV_32FC2
+    template <class T> T &at(int i, int j) { return reinterpret_cast<T *>(d.data())[(size_t)i * cols + j]; }
     Mat inv(int = DECOMP_LU) const { Mat m = *this; m.inverse = true; return m; }
 };
 struct SolveCapture { std::vector<Mat> A, B; };

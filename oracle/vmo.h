@@ -23,10 +23,13 @@
 //      are bit-equal (tests/test_oracle_refdev.py::test_coarse_system_*); the inverse itself is OpenCV's cv::Mat::inv (D4);
 //  (f) the host UI splat at the end of Morph::initialize_level (morph.cu:341-388): the reference's loop, cut out and wrapped
 //      into a function, bit-equal on every level of a video (tests/test_oracle_refdev.py::test_ui_splat_*);
-//  (g) the reference-internal cross-checks of SURVEY.md section 4.
+//  (g) CQuadraticPath::optimize (QuadraticPath.cpp:24-223): the reference's text with its cuSPARSE / cuBLAS solver replaced
+//      by a recorder -- the right-hand sides of the two Poisson systems are bit-equal, the CSR matrix it assembles is the
+//      oracle's matrix-free operator (tests/test_oracle_refdev.py::test_qpath_system_*); the CG's dot order is D6;
+//  (h) the reference-internal cross-checks of SURVEY.md section 4.
 // Still "parity unpinned" (host / third-party code of the reference that cannot run here): the INVERSE of the coarse dense
-// system (cv::Mat::inv, D4), rod::upsample's hardware-bilinear prolongation, MatchingThread's Resize, QuadraticPath
-// (cuBLAS / cuSPARSE CG, D6).  The texture unit itself (D1) and -use_fast_math are not modelled.
+// system (cv::Mat::inv, D4), rod::upsample's hardware-bilinear prolongation, MatchingThread's Resize, the summation order
+// of cuBLAS's dots inside QuadraticPath's CG (D6).  The texture unit itself (D1) and -use_fast_math are not modelled.
 //
 // Each function cites the reference file:line it follows
 // (paths relative to /root/reference).
@@ -158,5 +161,7 @@ void render_halfway(uint8_t *out, int rowstride, int w, int h, int ex, float col
                     int color_from, const uint8_t *ext0, const uint8_t *ext1,
                     const float *vec, const float *qpath);                  // render.cu:16-96
 void qpath_optimize(const float *vec, float *qpath, int w, int h, int max_iter, float tol, int *iters_out); // QuadraticPath.cpp:24-318
+void qpath_system(const float *vec, int cols, int rows, std::vector<float> &Bx, std::vector<float> &By);    // QuadraticPath.cpp:24-169
+void qpath_apply(int cols, int rows, const float *in, float *out);                                          // QuadraticPath.cpp:170-202
 
 }  // namespace vmo

@@ -166,5 +166,12 @@ void vo_render_halfway(uint8_t *out, int rowstride, int w, int hh, int ex, float
 void vo_qpath_optimize(const float *vec, float *qpath, int w, int hh, int max_iter, float tol, int *iters) {
     qpath_optimize(vec, qpath, w, hh, max_iter, tol, iters);
 }
+// right-hand sides of the two Poisson systems of one frame, and the 5-point operator applied to a vector
+void vo_qpath_system(const float *vec, int w, int hh, float *Bx_out, float *By_out) {
+    std::vector<float> Bx, By;
+    qpath_system(vec, w, hh, Bx, By);
+    memcpy(Bx_out, Bx.data(), sizeof(float) * Bx.size()); memcpy(By_out, By.data(), sizeof(float) * By.size());
+}
+void vo_qpath_apply(const float *in, float *out, int w, int hh) { qpath_apply(w, hh, in, out); }
 
 }  // extern "C"

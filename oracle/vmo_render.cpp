@@ -96,25 +96,27 @@ static float qp_dot(const float *a, const float *b, int N) {
         for (int t = 0; t < off; t++) gs[t] += gs[t + off];
     return (float)gs[0];
 }
+// the 5-point operator of QuadraticPath.cpp:170-202 (the CSR rows hold, in this order, up, left, diagonal, right, down)
+void qpath_apply(int cols, int rows, const float *in, float *out) {
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) {
+        int ii = y * cols + x; float diag = 0, s = 0;
+        if (y - 1 >= 0) { diag += 1.0f; s += -1.0f * in[ii - cols]; }
+        if (x - 1 >= 0) { diag += 1.0f; s += -1.0f * in[ii - 1]; }
+        float right = 0, down = 0; bool hr = false, hd = false;
+        if (x + 1 < cols) { diag += 1.0f; right = -1.0f * in[ii + 1]; hr = true; }
+        if (y + 1 < rows) { diag += 1.0f; down = -1.0f * in[ii + cols]; hd = true; }
+        if (diag != 0) s += diag * in[ii];
+        if (hr) s += right;
+        if (hd) s += down;
+        out[ii] = s;
+    }
+}
 static int cg_solve(int cols, int rows, const std::vector<float> &B, std::vector<float> &X, int max_iter, float tol) {
     int N = cols * rows;
     std::vector<float> r(B), p(N, 0.0f), om(N, 0.0f);
     auto dot = [&](const std::vector<float> &a, const std::vector<float> &b) { return qp_dot(a.data(), b.data(), N); };
-    auto spmv = [&](const std::vector<float> &in, std::vector<float> &out) {
-#pragma omp parallel for schedule(static)
-        for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) {
-            int ii = y * cols + x; float diag = 0, s = 0;
-            if (y - 1 >= 0) { diag += 1.0f; s += -1.0f * in[ii - cols]; }
-            if (x - 1 >= 0) { diag += 1.0f; s += -1.0f * in[ii - 1]; }
-            float right = 0, down = 0; bool hr = false, hd = false;
-            if (x + 1 < cols) { diag += 1.0f; right = -1.0f * in[ii + 1]; hr = true; }
-            if (y + 1 < rows) { diag += 1.0f; down = -1.0f * in[ii + cols]; hd = true; }
-            if (diag != 0) s += diag * in[ii];
-            if (hr) s += right;
-            if (hd) s += down;
-            out[ii] = s;
-        }
-    };
+    auto spmv = [&](const std::vector<float> &in, std::vector<float> &out) { qpath_apply(cols, rows, in.data(), out.data()); };
     int k = 0; float r0 = 0, r1 = dot(r, r);
     while (r1 > tol * tol && k <= max_iter) {
         k++;
@@ -131,8 +133,9 @@ static int cg_solve(int cols, int rows, const std::vector<float> &B, std::vector
     return k;
 }
 
-// QuadraticPath.cpp:24-223 for one frame.  vec/qpath: tight cols*rows float2.
-void qpath_optimize(const float *vec, float *qpath, int cols, int rows, int max_iter, float tol, int *iters_out) {
+// QuadraticPath.cpp:24-169 for one frame: the blended Jacobians and the two right-hand sides (checked against the
+// reference's own text in tests/test_oracle_refdev.py::test_qpath_system_*).  vec: tight cols*rows float2.
+void qpath_system(const float *vec, int cols, int rows, std::vector<float> &Bx, std::vector<float> &By) {
     const f2 *V = reinterpret_cast<const f2 *>(vec);
     int size = cols * rows;
     std::vector<float> j_opt((size_t)size * 4);
@@ -159,7 +162,7 @@ void qpath_optimize(const float *vec, float *qpath, int cols, int rows, int max_
         j_opt[index + 0] = nj[0] * la; j_opt[index + 2] = nj[2] * la;
         j_opt[index + 1] = nj[1] * lb; j_opt[index + 3] = nj[3] * lb;
     }
-    std::vector<float> Bx(size, 0.0f), By(size, 0.0f), X(size, 0.0f), Y(size, 0.0f);
+    Bx.assign(size, 0.0f); By.assign(size, 0.0f);
     auto J = [&](int yy, int xx, int c) { return j_opt[((size_t)yy * cols + xx) * 4 + c]; };
     for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) {     // QuadraticPath.cpp:134-169
         int ii = y * cols + x;
@@ -168,6 +171,13 @@ void qpath_optimize(const float *vec, float *qpath, int cols, int rows, int max_
         if (x + 1 < cols) { Bx[ii] -= J(y, x + 1, 0) - 1.0f; By[ii] -= J(y, x + 1, 2); }
         if (y + 1 < rows) { Bx[ii] -= J(y + 1, x, 1); By[ii] -= J(y + 1, x, 3) - 1.0f; }
     }
+}
+
+// QuadraticPath.cpp:24-223 for one frame.  vec/qpath: tight cols*rows float2.
+void qpath_optimize(const float *vec, float *qpath, int cols, int rows, int max_iter, float tol, int *iters_out) {
+    int size = cols * rows;
+    std::vector<float> Bx, By, X(size, 0.0f), Y(size, 0.0f);
+    qpath_system(vec, cols, rows, Bx, By);
     int k0 = cg_solve(cols, rows, Bx, X, max_iter, tol);
     int k1 = cg_solve(cols, rows, By, Y, max_iter, tol);
     if (iters_out) { iters_out[0] = k0; iters_out[1] = k1; }

@@ -282,3 +282,34 @@ def test_ui_splat_is_the_reference_s_own_host_loop(oracle_lib):
         np.testing.assert_array_equal(R.a["ui_axy"], o.get(l, "ui_axy"), err_msg=f"level {l}")
         np.testing.assert_array_equal(R.a["ui_b"], o.get(l, "ui_b"), err_msg=f"level {l}")
     assert seen_halved
+
+
+@pytest.mark.parametrize("w,h", [(37, 23), (64, 48), (5, 2)])
+def test_qpath_system_is_the_reference_s_own_assembly(oracle_lib, w, h):
+    """CQuadraticPath::optimize (QuadraticPath.cpp:24-223) cut out of the reference, its cuSPARSE / cuBLAS solver replaced by a
+    recorder: the right-hand sides of the two Poisson systems (blended Jacobians of the two warps) equal the oracle's bit for
+    bit, the CSR matrix it assembles applied to a vector (row sums in the stored order: up, left, diagonal, right, down) is the
+    oracle's matrix-free 5-point operator, and the paste loop interleaves X / Y the way the oracle does.  (The CG itself runs
+    on cuBLAS dots whose summation order is unspecified: oracle deviation D6.)"""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    rng = np.random.Generator(np.random.PCG64(w * 31 + h))
+    v = np.stack([2 * np.sin(xx / 7) * np.cos(yy / 5), 1.5 * np.cos(xx / 6 + yy / 9)], -1).astype(np.float32)
+    v += (rng.standard_normal(v.shape) * 0.05).astype(np.float32)
+    bx, by, A, row, col, qp = rd.qpath_assemble(v)
+    bxo, byo = oracle_lib.qpath_system(v)
+    np.testing.assert_array_equal(bx, bxo)
+    np.testing.assert_array_equal(by, byo)
+    assert np.count_nonzero(bx) > 0 and np.count_nonzero(by) > 0
+    np.testing.assert_array_equal(qp[..., 0].ravel(), bx)             # paste: (X, Y) interleaved per pixel
+    np.testing.assert_array_equal(qp[..., 1].ravel(), by)
+    # the CSR matrix as an operator, summed in the stored order in float32, against the oracle's matrix-free operator
+    N = w * h
+    assert row[0] == 0 and row[N] == len(A) and np.all(np.diff(row) >= 2)
+    p = rng.standard_normal(N).astype(np.float32)
+    out = np.zeros(N, np.float32)
+    for i in range(N):
+        s = np.float32(0)
+        for k in range(row[i], row[i + 1]):
+            s = np.float32(s + np.float32(A[k] * p[col[k]]))
+        out[i] = s
+    np.testing.assert_array_equal(out, oracle_lib.qpath_apply(p, w, h))
