@@ -107,7 +107,9 @@ def main():
     # IEEE fp32, no contraction: the arithmetic contract of DESIGN.md section 2 (the reference binary itself was built with
     # -use_fast_math, which no CPU can reproduce)
     flags = ["-O2", "-std=c++17", "-fPIC", "-w", "-DNDEBUG", "-DCUDA_SM=35", "-ffp-contract=off", "-fno-fast-math", "-include", pre]
-    cmd = [cxx] + flags + inc + ["-shared", "-o", OUT, tu, os.path.join(ref, "Algorithm", "stencils.cpp")]
+    # -Bsymbolic: the host stand-ins for cudaMemcpy / cudaMemset defined in capi.inc must be the ones this library calls, also
+    # in a process that has the real CUDA runtime loaded (torch)
+    cmd = [cxx] + flags + inc + ["-shared", "-Wl,-Bsymbolic", "-o", OUT, tu, os.path.join(ref, "Algorithm", "stencils.cpp")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-6000:])
