@@ -49,6 +49,7 @@ def lib():
         u8 = C.POINTER(C.c_uint8)
         L.ref_render_halfway.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, u8, u8, fp, fp]
         L.ref_ui_splat_level.argtypes = [C.POINTER(RefLevelC), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, ip, fp, ip, fp]
+        L.ref_resize_field.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int]
         L.ref_qpath_assemble.argtypes = [fp, C.c_int, C.c_int, fp, fp, fp, ip, ip, fp]
         L.ref_coarse_assemble.argtypes = [C.c_int] * 5 + [C.c_float, C.c_float] + [C.c_int] * 3 + [C.c_float] * 3 + [C.c_int, C.c_int, ip, fp, ip, fp, fp, fp, fp, fp]
         _lib = L
@@ -83,6 +84,16 @@ def coarse_assemble(oracle, lp, lw, rp, rw):
                                    A.ctypes.data_as(fp), bx.ctypes.data_as(fp), by.ctypes.data_as(fp), v.ctypes.data_as(fp))
     assert rc == 0
     return A, bx, by, v
+
+
+def resize_field(src, dw, dh):
+    """CMatchingThread::Resize (MatchingThread.cpp:86-136) of the reference: (sh, sw, 2) float32 -> (dh, dw, 2)."""
+    src = np.ascontiguousarray(src, np.float32)
+    sh, sw, _ = src.shape
+    dst = np.zeros((dh, dw, 2), np.float32)
+    fp = C.POINTER(C.c_float)
+    lib().ref_resize_field(src.ctypes.data_as(fp), sw, sh, dst.ctypes.data_as(fp), dw, dh)
+    return dst
 
 
 def qpath_assemble(vec):

@@ -44,6 +44,12 @@ SPANS = [
      [(r"^void CQuadraticPath::optimize\(\)", "void RefQPath::optimize()")],
      "namespace ref_host { using std::sqrt; using cv::Vec2f;\nstruct RefQPath { std::vector<cv::Mat> &_vector, &_qpath; int times, rows, cols;\n"
      "    void cudaSolver(float *A, int *rowindex, int *columns, int N, int nz, float *B, float *X); void optimize(); };\n", "}\n"),
+    # CMatchingThread::Resize + BiLinear                                MatchingThread.cpp:86-136: the spatial resample of update_result.
+    # The class is a QThread: the two member definitions become members of a plain struct (one substitution each, class name only).
+    ("Algorithm/MatchingThread.cpp", r"^void CMatchingThread::Resize\(", r"^void CMatchingThread::run\(\)", r"^\s*$",
+     [(r"^void CMatchingThread::Resize\(Mat& src,Mat& dst\)", "void RefMatch::Resize(cv::Mat& src, cv::Mat& dst)"),
+      (r"^inline T CMatchingThread::BiLinear\(", "inline T RefMatch::BiLinear(")],
+     "namespace ref_host { using std::floor; using std::ceil; using cv::Vec2f;\nstruct RefMatch { void Resize(cv::Mat &src, cv::Mat &dst); template <class T> T BiLinear(cv::Mat &img, float2 p); };\n", "}\n"),
     # isignbit, calc_border, ssim                                   morph.cu:35-118
     ("Algorithm/morph.cu", r"^__device__ int isignbit\(", r"^// Level processing", None),
     # INIT_* constants, kernel_initialize_level, init_improving_mask  morph.cu:170-261

@@ -26,10 +26,13 @@
 //  (g) CQuadraticPath::optimize (QuadraticPath.cpp:24-223): the reference's text with its cuSPARSE / cuBLAS solver replaced
 //      by a recorder -- the right-hand sides of the two Poisson systems are bit-equal, the CSR matrix it assembles is the
 //      oracle's matrix-free operator (tests/test_oracle_refdev.py::test_qpath_system_*); the CG's dot order is D6;
-//  (h) the reference-internal cross-checks of SURVEY.md section 4.
-// Still "parity unpinned" (host / third-party code of the reference that cannot run here): the INVERSE of the coarse dense
-// system (cv::Mat::inv, D4), rod::upsample's hardware-bilinear prolongation, MatchingThread's Resize, the summation order
-// of cuBLAS's dots inside QuadraticPath's CG (D6).  The texture unit itself (D1) and -use_fast_math are not modelled.
+//  (h) CMatchingThread::Resize + BiLinear (MatchingThread.cpp:86-136, the spatial resample of update_result): the reference's
+//      text, bit-equal to extract_vectors_level on every level (tests/test_oracle_refdev.py::test_update_result_resize_*);
+//  (i) the reference-internal cross-checks of SURVEY.md section 4.
+// Still "parity unpinned" (third-party code of the reference that cannot run here): the INVERSE of the coarse dense system
+// (cv::Mat::inv, D4), rod::upsample's hardware-bilinear prolongation (the texture unit), the temporal in-fill of
+// update_result (a cv::Mat expression evaluated inside OpenCV), the summation order of cuBLAS's dots inside
+// QuadraticPath's CG (D6).  The texture unit itself (D1) and -use_fast_math are not modelled.
 //
 // Each function cites the reference file:line it follows
 // (paths relative to /root/reference).

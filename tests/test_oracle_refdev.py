@@ -313,3 +313,27 @@ def test_qpath_system_is_the_reference_s_own_assembly(oracle_lib, w, h):
             s = np.float32(s + np.float32(A[k] * p[col[k]]))
         out[i] = s
     np.testing.assert_array_equal(out, oracle_lib.qpath_apply(p, w, h))
+
+
+def test_update_result_resize_is_the_reference_s_own_code(oracle_lib):
+    """CMatchingThread::Resize + BiLinear (MatchingThread.cpp:86-136), the spatial resample of update_result, cut out of the
+    reference: the oracle's extraction of a coarser level's vectors at full resolution (ratio scaling of 42-52 + Resize) is
+    bit-equal, for every level of a pair whose sizes do not divide evenly.  (The temporal in-fill of update_result is a
+    cv::Mat expression, beg * (1 - fa) + end * fa, evaluated inside OpenCV.)"""
+    from videomorphing_b200 import synth
+    w, h = 150, 70
+    rgb0, rgb1, _ = synth.image_pair(w, h, 91, 92, 3.0)
+    o = oracle_lib.Oracle(dict(max_iter=12))
+    n = o.build(rgb0, rgb1)
+    o.run()
+    for l in range(1, n - 1):
+        i = o.info(l)
+        v = o.get(l, "v").reshape(i["d"], i["h"], i["rowstride"], 2)[0, :, :i["w"], :]
+        rx, ry = np.float32(w) / np.float32(i["w"]), np.float32(h) / np.float32(i["h"])
+        temp = v.copy()
+        if rx != 1 or ry != 1:
+            temp = np.stack([v[..., 0] * rx, v[..., 1] * ry], -1).astype(np.float32)
+        want = o.extract_vectors(level=l)[0]
+        got = rd.resize_field(temp, w, h) if (i["w"] != w or i["h"] != h) else temp
+        assert float(np.abs(want).max()) > 0
+        np.testing.assert_array_equal(got, want, err_msg=f"level {l}")
