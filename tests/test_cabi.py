@@ -63,6 +63,17 @@ def test_argument_validation(vm):
     assert b"bad schedule" in L.vm_last_error()
     assert L.vm_params_default(None) == -1
     assert L.vm_render_halfway_dev(None, 0, 0, 0, 0, 0.5, 0.5, 1, None, None, None, None, None) == -1
+    # round-2 entry points: the multi-GPU plan, the frame-sharded build, pinning
+    own = (C.c_int32 * 8)()
+    assert L.vm_wavefront_plan(2, None, None, 2, own) == -1 and b"wavefront_plan" in L.vm_last_error()
+    whd = (C.c_int32 * 12)(64, 48, 9, 64, 48, 9, 32, 24, 9, 16, 12, 5)
+    mi = (C.c_float * 4)(0, 50, 100, 0)
+    assert L.vm_wavefront_plan(4, whd, mi, 0, own) == -1
+    assert L.vm_wavefront_plan(4, whd, mi, 2, own) == 2 and list(own) == [-1, -1, 0, 1, 0, 1, -1, -1]     # levels 2, 1: forward on rank 0, backward on rank 1
+    assert L.vm_pyramid_build_frames(None, None, None, None, None, None, None, 64, 48, 9, 4, 14000000, 0, 9, None) == -1
+    assert L.vm_pyramid_build_finish(None, None) < 0
+    assert L.vm_host_pin(None, 16) == -1
+    assert L.vm_host_unpin(None) == 0
 
 
 def test_no_cpu_fallback(vm):

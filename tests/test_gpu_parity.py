@@ -490,3 +490,29 @@ def test_window_of_state_pages_gives_the_same_vectors(vm, oracle_lib, monkeypatc
         pyr.get(1, "mean")
     m.run()                                                   # again on the same objects
     _assert_vec(m.get_vectors(), o.extract_vectors(), "windowed arenas, second run")
+
+
+def test_frame_blocks_built_one_after_the_other_give_the_one_call_pyramid(vm):
+    """vm_pyramid_build_frames (what each GPU of a multi-GPU build runs on its frame block) called block by block on ONE
+    pyramid + vm_pyramid_build_finish == vm_pyramid_build: every gray image and flow field of every level, bit for bit
+    (17 frames: levels with all frames, one temporally halved optimised level, the dense-solve level).  Misuse is an error."""
+    from videomorphing_b200 import synth, _lib
+    w, h, d = 64, 48, 17
+    v0, v1, flows, _ = synth.video_pair(w, h, d, 61, 62, 3.0)
+    a = vm.Pyramid(0); n = a.build(v0, v1, flows, start_res=4, voxel_cap=1 << 62)
+    b = vm.Pyramid(0)
+    with pytest.raises(_lib.VmError):
+        b.build_finish()                                        # nothing built yet
+    with pytest.raises(_lib.VmError):
+        b.build_frames(v0, v1, flows, 10, 9, start_res=4, voxel_cap=1 << 62)      # frames [10, 19) of a 17-frame video
+    K = 0
+    for f0, nf in ((0, 6), (6, 1), (7, 10)):
+        K = b.build_frames(v0, v1, flows, f0, nf, start_res=4, voxel_cap=1 << 62)
+    assert K == 3                                               # levels 1..3 keep all 17 frames
+    with pytest.raises(_lib.VmError):
+        b.dev_ptr(1, "keep0")                                   # the retained planes belong to level K
+    assert b.dev_ptr(K, "keep0")[1] == 4 * 3 * b.info(K)["w"] * b.info(K)["h"] * d
+    assert b.build_finish() == n
+    for l in range(1, n - 1):
+        for nm in ("img0", "img1", "f0", "f1", "b0", "b1"):
+            np.testing.assert_array_equal(a.get(l, nm), b.get(l, nm), err_msg=f"level {l} {nm}")
