@@ -108,7 +108,8 @@ struct ResampleCache {
     std::map<int, TridiagDev> tri;
     // transient planes of a build, kept between builds of the same shape (no cudaMalloc / cudaFree per call)
     DevBuf keep[2], keep_next[2], pa, pb, stage, tmpf;
-    int keep_level = 0;                  // level whose linear-light planes keep[] holds
+    DevBuf keepK[2];                     // frame-sharded build: linear-light planes of the last level that keeps every frame, all frames
+    int keep_level = 0;                  // level whose linear-light planes keepK[] (after vm_pyramid_build_frames) / keep[] hold
 };
 
 static cudaError_t upload(DevBuf &b, const void *src, size_t bytes) {
@@ -616,9 +617,9 @@ static int build_level(vm_pyramid *p, Resampler &R, int el, const uint8_t *const
 // linear-light planes [d][3][h][w] of video vi at the level built last (the input of the next coarser level)
 int keep_planes(vm_pyramid *p, int vi, int *level, void **ptr, size_t *bytes) {
     ResampleCache *C = static_cast<ResampleCache *>(p->resample_cache);
-    if (!C || C->keep_level < 1 || !C->keep[vi].p) { set_error("no retained planes: call vm_pyramid_build_frames first"); return VM_ERR_STATE; }
+    if (!C || C->keep_level < 1 || !C->keepK[vi].p) { set_error("no retained planes: call vm_pyramid_build_frames first"); return VM_ERR_STATE; }
     const Level &L = p->lv[C->keep_level];
-    *level = C->keep_level; *ptr = C->keep[vi].p; *bytes = sizeof(float) * 3 * (size_t)L.w * L.h * L.d;
+    *level = C->keep_level; *ptr = C->keepK[vi].p; *bytes = sizeof(float) * 3 * (size_t)L.w * L.h * L.d;
     return VM_OK;
 }
 
@@ -649,6 +650,16 @@ int vm_pyramid_build_frames(vm_pyramid *p, const uint8_t *video0, const uint8_t 
         int rc = build_level(p, R, el, vids, fin, have_flow, frame0, nframes, false);
         if (rc != VM_OK) return rc;
     }
+    // the block's planes of level nfull go to a buffer that survives further calls (other blocks on this pyramid) and that
+    // the caller completes with the other GPUs' blocks (VM_FIELD_KEEP0 / 1)
+    const Level &LK = p->lv[nfull];
+    const size_t per = sizeof(float) * 3 * (size_t)LK.w * LK.h;
+    for (int vi = 0; vi < 2; vi++) {
+        VM_CUDA(R.cache->keepK[vi].ensure(per * LK.d));
+        if (nframes > 0)
+            VM_CUDA(cudaMemcpyAsync(static_cast<char *>(R.cache->keepK[vi].p) + per * frame0, static_cast<char *>(R.cache->keep[vi].p) + per * frame0,
+                                    per * nframes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
     return nfull;
 }
 
@@ -660,6 +671,7 @@ int vm_pyramid_build_finish(vm_pyramid *p, void *stream) {
     const uint8_t *vids[2] = {nullptr, nullptr};
     const float *fin[4] = {nullptr, nullptr, nullptr, nullptr};
     const bool have_flow = p->lv[1].flows_valid;
+    std::swap(R.cache->keep[0], R.cache->keepK[0]); std::swap(R.cache->keep[1], R.cache->keepK[1]);     // the complete planes feed the next level
     for (int el = nfull; el < maxl; el++) {
         if (el >= maxl - 1 && el > 0) break;                                  // coarsest level: no images / flows (pyramid.cu:329)
         int rc = build_level(p, R, el, vids, fin, have_flow, 0, 0, true);
