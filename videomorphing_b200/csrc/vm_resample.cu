@@ -292,20 +292,34 @@ __global__ void __launch_bounds__(TR_LINES) k_tridiag_rows(float *planes, long l
     __shared__ float tile[TR_LINES][33];
     __shared__ float sc[2][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARP = TR_LINES / 32;
+    constexpr int NWARP = TR_LINES / 32;             // a warp moves the lines warp, warp + NWARP, ...: 32 of them
     const long long line0 = (long long)blockIdx.x * TR_LINES;
     const int nl = (int)min((long long)TR_LINES, nlines - line0);
     float *base = planes + line0 * w;
+    // The 32 line segments of the NEXT chunk are requested before the current chunk is walked (all 32 loads of a lane in
+    // flight together, one memory round trip per chunk instead of one per four lines), so the sequential walk and the stores
+    // of a chunk overlap the next chunk's loads.
+    float nx[32];
+    auto fetch = [&](int c0) {
+        const int nc = min(32, w - c0);
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const int r = warp + k * NWARP;
+            nx[k] = (lane < nc && r < nl) ? base[(size_t)r * w + c0 + lane] : 0.f;
+        }
+    };
     float carry = 0.f;
+    fetch(0);
     for (int c0 = 0; c0 < w; c0 += 32) {
         const int nc = min(32, w - c0);
         if (lane < nc) {
-#pragma unroll 4
-            for (int r = warp; r < nl; r += NWARP) {
-                float x = base[(size_t)r * w + c0 + lane];
-                tile[r][lane] = CURVE ? srgb_curve(x) : x;
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                const int r = warp + k * NWARP;
+                if (r < nl) tile[r][lane] = CURVE ? srgb_curve(nx[k]) : nx[k];
             }
         }
+        if (c0 + 32 < w) fetch(c0 + 32);
         if (tid < nc) sc[0][tid] = __ldg(l + c0 + tid);
         __syncthreads();
         if (tid < nl) {
@@ -323,12 +337,18 @@ __global__ void __launch_bounds__(TR_LINES) k_tridiag_rows(float *planes, long l
         __syncthreads();
     }
     const int last0 = ((w - 1) / 32) * 32;
+    __threadfence_block();
+    fetch(last0);                                    // (this thread's own stores of the forward pass: program order)
     for (int c0 = last0; c0 >= 0; c0 -= 32) {
         const int nc = min(32, w - c0);
         if (lane < nc) {
-#pragma unroll 4
-            for (int r = warp; r < nl; r += NWARP) tile[r][lane] = base[(size_t)r * w + c0 + lane];
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                const int r = warp + k * NWARP;
+                if (r < nl) tile[r][lane] = nx[k];
+            }
         }
+        if (c0 - 32 >= 0) fetch(c0 - 32);
         if (tid < nc) { sc[0][tid] = __ldg(u + c0 + tid); sc[1][tid] = __ldg(dinv + c0 + tid); }
         __syncthreads();
         if (tid < nl) {
