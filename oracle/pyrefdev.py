@@ -49,6 +49,7 @@ def lib():
         u8 = C.POINTER(C.c_uint8)
         L.ref_render_halfway.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, u8, u8, fp, fp]
         L.ref_ui_splat_level.argtypes = [C.POINTER(RefLevelC), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, ip, fp, ip, fp]
+        L.ref_upsample_pages.argtypes = [C.POINTER(RefLevelC), C.POINTER(RefLevelC)]
         L.ref_resize_field.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int]
         L.ref_qpath_assemble.argtypes = [fp, C.c_int, C.c_int, fp, fp, fp, ip, ip, fp]
         L.ref_coarse_assemble.argtypes = [C.c_int] * 5 + [C.c_float, C.c_float] + [C.c_int] * 3 + [C.c_float] * 3 + [C.c_int, C.c_int, ip, fp, ip, fp, fp, fp, fp, fp]
@@ -127,16 +128,17 @@ class RefLevel:
             shp, dt = oracle._shape(l, n)
             have = oracle.L.vo_field_bytes(oracle.h, l, po_fields[n]) == int(np.prod(shp)) * 4
             self.a[n] = oracle.get(l, n).copy() if have else np.zeros(shp, dt)
-        self.img = {n: oracle.get(l, n).copy() for n in ("img0", "img1")}
-        self.flow = {}
-        if i["d"] > 1:
-            self.flow = {n: oracle.get(l, n).copy() for n in ("f0", "f1", "b0", "b1")}
+        self.img, self.flow = {}, {}
+        if i["has_images"]:                               # the coarsest level (dense solve) has a vector field only
+            self.img = {n: oracle.get(l, n).copy() for n in ("img0", "img1")}
+            if i["d"] > 1:
+                self.flow = {n: oracle.get(l, n).copy() for n in ("f0", "f1", "b0", "b1")}
         c = RefLevelC()
         c.w, c.h, c.d, c.rs, c.ps, c.irs, c.ips = i["w"], i["h"], i["d"], i["rowstride"], i["pagestride"], i["impmask_rowstride"], i["impmask_pagestride"]
         c.inv_wh, c.factor_d = i["inv_wh"], i["factor_d"]
         for n in STATE:
             setattr(c, n, self.a[n].ctypes.data)
-        c.img0, c.img1 = self.img["img0"].ctypes.data, self.img["img1"].ctypes.data
+        c.img0, c.img1 = (self.img["img0"].ctypes.data, self.img["img1"].ctypes.data) if self.img else (None, None)
         for n in ("f0", "f1", "b0", "b1"):
             setattr(c, n, self.flow[n].ctypes.data if n in self.flow else None)
         self.c = c
@@ -162,6 +164,11 @@ class RefLevel:
 
     def infill_frame(self, frame):
         lib().ref_infill_frame(C.byref(self.c), frame)
+
+    def upsample_from(self, coarse):
+        """The spatial prolongation of `upsample` (upsample.cu:259-285) from the RefLevel `coarse` into this level's v: pages
+        min(i * factor, d - 1); the other pages are zero (their temporal in-fill is infill_frame)."""
+        lib().ref_upsample_pages(C.byref(self.c), C.byref(coarse.c))
 
     def ui_splat(self, info0, lp, lw, rp, rw):
         """The host loop at the end of Morph::initialize_level (morph.cu:341-388): ui_axy / ui_b of this level from its v."""

@@ -50,6 +50,13 @@ SPANS = [
      [(r"^void CMatchingThread::Resize\(Mat& src,Mat& dst\)", "void RefMatch::Resize(cv::Mat& src, cv::Mat& dst)"),
       (r"^inline T CMatchingThread::BiLinear\(", "inline T RefMatch::BiLinear(")],
      "namespace ref_host { using std::floor; using std::ceil; using cv::Vec2f;\nstruct RefMatch { void Resize(cv::Mat &src, cv::Mat &dst); template <class T> T BiLinear(cv::Mat &img, float2 p); };\n", "}\n"),
+    # the prolongation of `upsample` (upsample.cu:259-285): internal_vector_to_image (pyramid.cu:627-644, its `template <class T>`
+    # line re-added as prefix), rod::kernel_upsample (imgop_upsample.cu:12-31, inside namespace rod as in the reference) and
+    # conv_to_block_of_arrays (upsample.cu:9-26)
+    ("Algorithm/pyramid.cu", r"^__global__ void internal_vector_to_image\(rod::dimage_ptr<T> res,", r"^template <class T>\s*$", r"^\s*$", [],
+     "template <class T>\n", ""),
+    ("include/util/imgop_upsample.cu", r"^const int BW = 32,", r"^template <class T, int C>\s*$", r"^\s*$", [], "namespace rod {\n", "}\n"),
+    ("Algorithm/upsample.cu", r"^__global__ void conv_to_block_of_arrays\(", r"^__global__ void temp_ref\(", r"^\s*$"),
     # isignbit, calc_border, ssim                                   morph.cu:35-118
     ("Algorithm/morph.cu", r"^__device__ int isignbit\(", r"^// Level processing", None),
     # INIT_* constants, kernel_initialize_level, init_improving_mask  morph.cu:170-261
@@ -92,7 +99,7 @@ def main():
         print(f"reference tree absent ({ref}): keeping prebuilt oracle/_ref/libref_devfn.so")
         return 0
     os.makedirs(OUT_DIR, exist_ok=True)
-    parts = ['#include <cmath>\n#include <ctime>\n#include "simt.h"\n#include <util/dmath.h>\n#include <util/linalg.h>\n#include "stencils.h"\n#include "Pyramid.h"\n#include "prelude.h"\n']
+    parts = ['#include <cmath>\n#include <ctime>\n#include "simt.h"\n#include <util/dmath.h>\n#include <util/linalg.h>\n#include "stencils.h"\n#include "Pyramid.h"\n#include <util/dimage.h>\n#include <util/box_sampler.h>\n#include "prelude.h"\n']
     for span in SPANS:
         fname, first, stop, drop = span[:4]
         with open(os.path.join(ref, fname), encoding="latin-1") as f:

@@ -28,9 +28,12 @@
 //      oracle's matrix-free operator (tests/test_oracle_refdev.py::test_qpath_system_*); the CG's dot order is D6;
 //  (h) CMatchingThread::Resize + BiLinear (MatchingThread.cpp:86-136, the spatial resample of update_result): the reference's
 //      text, bit-equal to extract_vectors_level on every level (tests/test_oracle_refdev.py::test_update_result_resize_*);
-//  (i) the reference-internal cross-checks of SURVEY.md section 4.
+//  (i) the spatial prolongation of `upsample` (upsample.cu:259-285): internal_vector_to_image, rod::kernel_upsample and
+//      conv_to_block_of_arrays, the reference's kernels under the emulator, bit-equal on every level of a video
+//      (tests/test_oracle_refdev.py::test_prolongation_*);
+//  (j) the reference-internal cross-checks of SURVEY.md section 4.
 // Still "parity unpinned" (third-party code of the reference that cannot run here): the INVERSE of the coarse dense system
-// (cv::Mat::inv, D4), rod::upsample's hardware-bilinear prolongation (the texture unit), the temporal in-fill of
+// (cv::Mat::inv, D4), the texture unit's 9-bit interpolation weights (D1), the temporal in-fill of
 // update_result (a cv::Mat expression evaluated inside OpenCV), the summation order of cuBLAS's dots inside
 // QuadraticPath's CG (D6).  The texture unit itself (D1) and -use_fast_math are not modelled.
 //

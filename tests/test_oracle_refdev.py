@@ -337,3 +337,37 @@ def test_update_result_resize_is_the_reference_s_own_code(oracle_lib):
         got = rd.resize_field(temp, w, h) if (i["w"] != w or i["h"] != h) else temp
         assert float(np.abs(want).max()) > 0
         np.testing.assert_array_equal(got, want, err_msg=f"level {l}")
+
+
+def test_prolongation_is_the_reference_s_own_kernels(oracle_lib):
+    """`upsample` (upsample.cu:259-285): internal_vector_to_image -> rod::kernel_upsample<box_sampler> -> conv_to_block_of_arrays,
+    the three kernels cut out of the reference and run by the emulator (the texture fetch is the shared D1 bilinear): the pages
+    the oracle's upsample writes before the temporal in-fill -- min(i * factor, d - 1) -- are bit-equal on every level of a
+    17-frame video, incl. the step from 9 to 17 frames and odd sizes."""
+    from videomorphing_b200 import synth
+    w, h, d = 70, 44, 17
+    v0, v1, flows, field = synth.video_pair(w, h, d, 101, 102, 3.0)
+    o = oracle_lib.Oracle(dict(start_res=4, max_iter=6))
+    n = o.build(v0, v1, flows, voxel_cap=1 << 62)
+    o.coarse_solve()
+    rng = np.random.Generator(np.random.PCG64(5))
+    doubled = False
+    for l in range(n - 2, 0, -1):
+        ic, i = o.info(l + 1), o.info(l)
+        # a rough, non-zero coarse field (the solve gives zeros without UI constraints)
+        vc = (rng.standard_normal((ic["d"], ic["h"], ic["rowstride"], 2)) * 2).astype(np.float32)
+        vc[:, :, ic["w"]:, :] = 0
+        o.set(l + 1, "v", vc)
+        Rc = rd.RefLevel(o, l + 1)
+        o.upsample(l)
+        Rd = rd.RefLevel(o, l)
+        Rd.upsample_from(Rc)
+        factor = 2 if i["d"] > ic["d"] else 1
+        doubled |= factor == 2
+        got = Rd.a["v"].reshape(i["d"], i["h"], i["rowstride"], 2)
+        want = o.get(l, "v").reshape(i["d"], i["h"], i["rowstride"], 2)
+        for k in range(ic["d"]):
+            p = min(k * factor, i["d"] - 1)
+            assert float(np.abs(want[p]).max()) > 0
+            np.testing.assert_array_equal(got[p], want[p], err_msg=f"level {l} page {p}")
+    assert doubled
