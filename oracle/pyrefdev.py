@@ -49,6 +49,7 @@ def lib():
         u8 = C.POINTER(C.c_uint8)
         L.ref_render_halfway.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, u8, u8, fp, fp]
         L.ref_ui_splat_level.argtypes = [C.POINTER(RefLevelC), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, ip, fp, ip, fp]
+        L.ref_compose_flows.argtypes = [fp, fp, fp, fp] + [C.c_int] * 5
         L.ref_upsample_pages.argtypes = [C.POINTER(RefLevelC), C.POINTER(RefLevelC)]
         L.ref_resize_field.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int]
         L.ref_qpath_assemble.argtypes = [fp, C.c_int, C.c_int, fp, fp, fp, ip, ip, fp]
@@ -85,6 +86,16 @@ def coarse_assemble(oracle, lp, lw, rp, rw):
                                    A.ctypes.data_as(fp), bx.ctypes.data_as(fp), by.ctypes.data_as(fp), v.ctypes.data_as(fp))
     assert rc == 0
     return A, bx, by, v
+
+
+def compose_flows(f0, f1, b0, b1, d, factor_t):
+    """The temporal flow composition of Pyramid::build (pyramid.cu:406-441) of the reference on four sets of prev_d rescaled
+    flow frames (prev_d, h, w, 2): returns the composed sets (the level's frame t is frame min(t * factor_t, prev_d - 1))."""
+    arrs = [np.ascontiguousarray(a, np.float32).copy() for a in (f0, f1, b0, b1)]
+    prev_d, h, w, _ = arrs[0].shape
+    fp = C.POINTER(C.c_float)
+    lib().ref_compose_flows(*[a.ctypes.data_as(fp) for a in arrs], d, h, w, prev_d, factor_t)
+    return arrs
 
 
 def resize_field(src, dw, dh):

@@ -57,6 +57,15 @@ SPANS = [
      "template <class T>\n", ""),
     ("include/util/imgop_upsample.cu", r"^const int BW = 32,", r"^template <class T, int C>\s*$", r"^\s*$", [], "namespace rod {\n", "}\n"),
     ("Algorithm/upsample.cu", r"^__global__ void conv_to_block_of_arrays\(", r"^__global__ void temp_ref\(", r"^\s*$"),
+    # the temporal flow composition of Pyramid::build (pyramid.cu:406-441: a block in the middle of that function, wrapped into a
+    # member of a plain struct with the locals it uses as parameters) and Pyramid::BiLinear (488-523, class name substituted)
+    ("Algorithm/pyramid.cu", r"^\t\t\tif\(factor_t>1\)\s*$", r"^\t\tfor\(int t=0;t<d;t\+\+\)\s*$", r"^\s*$", [],
+     "namespace ref_host { using std::floor; using std::ceil;\nstruct RefPyr { template <class T> T BiLinear(cv::Mat &img, float2 p);\n"
+     "    void compose(std::vector<cv::Mat> &forw0, std::vector<cv::Mat> &forw1, std::vector<cv::Mat> &back0, std::vector<cv::Mat> &back1, int d, int h, int w, int prev_d, int factor_t); };\n"
+     "void RefPyr::compose(std::vector<cv::Mat> &forw0, std::vector<cv::Mat> &forw1, std::vector<cv::Mat> &back0, std::vector<cv::Mat> &back1, int d, int h, int w, int prev_d, int factor_t)\n{\n",
+     "}\n}\n"),
+    ("Algorithm/pyramid.cu", r"^inline T Pyramid::BiLinear\(", r"^PyramidLevel &Pyramid::append_new\(", r"^\s*$",
+     [(r"^inline T Pyramid::BiLinear\(", "inline T RefPyr::BiLinear(")], "namespace ref_host { using cv::Vec2f;\ntemplate <class T>\n", "}\n"),
     # isignbit, calc_border, ssim                                   morph.cu:35-118
     ("Algorithm/morph.cu", r"^__device__ int isignbit\(", r"^// Level processing", None),
     # INIT_* constants, kernel_initialize_level, init_improving_mask  morph.cu:170-261

@@ -1,7 +1,8 @@
 // oracle/refdev/stubs/opencv2/mat_stub.h -- stand-in for the few cv::Mat operations Morph::cpu_optimize_level uses
 // (morph.cu:433-437 zeros, 440-561 at<float>, 565-570 inv / countNonZero / operator*, 581-582 at<float>) and for the
 // at<Vec2f>(y, x) element access of CQuadraticPath::optimize (QuadraticPath.cpp:38-64, 213) and CMatchingThread::Resize /
-// BiLinear (MatchingThread.cpp:86-136).  OpenCV-C++ is not installed here.  The ASSEMBLY of the dense system is the reference's text running on this class; the inverse itself
+// BiLinear (MatchingThread.cpp:86-136) and of the temporal flow composition of Pyramid::build (pyramid.cu:406-441, 488-523).
+// OpenCV-C++ is not installed here.  The ASSEMBLY of the dense system is the reference's text running on this class; the inverse itself
 // (cv::Mat::inv of OpenCV, a third-party operation) is NOT reproduced: inv() only marks the matrix, and the product
 // "A^-1 * B" RECORDS (A, B) for the test and returns B, so that the reference's load of X / Y into lvl.v (morph.cu:573-584)
 // can be checked for its layout.  The oracle's own solve is deviation D4 (oracle/vmo.h).  TEST INFRASTRUCTURE ONLY.
@@ -25,6 +26,7 @@ struct Vec2f {
     Vec2f(float a, float b) { val[0] = a; val[1] = b; }
     float &operator[](int i) { return val[i]; }
     const float &operator[](int i) const { return val[i]; }
+    Vec2f &operator+=(const Vec2f &b) { val[0] += b.val[0]; val[1] += b.val[1]; return *this; }
 };
 // cv::Vec arithmetic used by CMatchingThread::BiLinear (MatchingThread.cpp:133-134): element-wise in float
 inline Vec2f operator*(const Vec2f &a, float s) { return Vec2f(a.val[0] * s, a.val[1] * s); }

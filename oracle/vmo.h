@@ -31,7 +31,10 @@
 //  (i) the spatial prolongation of `upsample` (upsample.cu:259-285): internal_vector_to_image, rod::kernel_upsample and
 //      conv_to_block_of_arrays, the reference's kernels under the emulator, bit-equal on every level of a video
 //      (tests/test_oracle_refdev.py::test_prolongation_*);
-//  (j) the reference-internal cross-checks of SURVEY.md section 4.
+//  (j) the temporal flow composition of Pyramid::build (pyramid.cu:406-441) and Pyramid::BiLinear (488-523): the reference's
+//      text on the flows its compiled resampler gives, bit-equal to the four flow fields of every temporally halved level
+//      (tests/test_oracle_refdev.py::test_temporal_flow_composition_*);
+//  (k) the reference-internal cross-checks of SURVEY.md section 4.
 // Still "parity unpinned" (third-party code of the reference that cannot run here): the INVERSE of the coarse dense system
 // (cv::Mat::inv, D4), the texture unit's 9-bit interpolation weights (D1), the temporal in-fill of
 // update_result (a cv::Mat expression evaluated inside OpenCV), the summation order of cuBLAS's dots inside
