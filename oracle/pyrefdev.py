@@ -49,6 +49,7 @@ def lib():
         u8 = C.POINTER(C.c_uint8)
         L.ref_render_halfway.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, u8, u8, fp, fp]
         L.ref_ui_splat_level.argtypes = [C.POINTER(RefLevelC), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, ip, fp, ip, fp]
+        L.ref_level_schedule.argtypes = [C.c_int] * 5 + [ip]
         L.ref_compose_flows.argtypes = [fp, fp, fp, fp] + [C.c_int] * 5
         L.ref_upsample_pages.argtypes = [C.POINTER(RefLevelC), C.POINTER(RefLevelC)]
         L.ref_resize_field.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int]
@@ -86,6 +87,13 @@ def coarse_assemble(oracle, lp, lw, rp, rw):
                                    A.ctypes.data_as(fp), bx.ctypes.data_as(fp), by.ctypes.data_as(fp), v.ctypes.data_as(fp))
     assert rc == 0
     return A, bx, by, v
+
+
+def level_schedule(w, h, d, start_res=8, max_stage2=14000000):
+    """The level sizes of Pyramid::build (pyramid.cu:219-236, 463-465), the reference's own arithmetic: [(w, h, d), ...]."""
+    whd = np.zeros(3 * 64, np.int32)
+    n = lib().ref_level_schedule(w, h, d, start_res, max_stage2, whd.ctypes.data_as(C.POINTER(C.c_int)))
+    return [tuple(int(x) for x in whd[3 * i: 3 * i + 3]) for i in range(n)]
 
 
 def compose_flows(f0, f1, b0, b1, d, factor_t):

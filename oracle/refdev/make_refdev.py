@@ -66,6 +66,17 @@ SPANS = [
      "}\n}\n"),
     ("Algorithm/pyramid.cu", r"^inline T Pyramid::BiLinear\(", r"^PyramidLevel &Pyramid::append_new\(", r"^\s*$",
      [(r"^inline T Pyramid::BiLinear\(", "inline T RefPyr::BiLinear(")], "namespace ref_host { using cv::Vec2f;\ntemplate <class T>\n", "}\n"),
+    # the level schedule of Pyramid::build: the block that derives the number of levels (pyramid.cu:222-234) and the three lines
+    # that shrink w / h / d at the end of the level loop (463-465), stitched into a function whose loop skeleton (prefix /
+    # suffix strings below) records the sizes append_new() would be called with.  log2 / sqrt / ceil of a float are the float
+    # overloads, as under MSVC.
+    ("Algorithm/pyramid.cu", r"^\tfloat decres_fa=\(float\)\(w\*h\*d\)/\(float\)\(Max_stage2\);", r"^\tint factor_t=1;", r"^\s*$", [],
+     "namespace ref_host { using std::log2; using std::sqrt; using std::ceil;\n"
+     "static int ref_schedule(int w, int h, int d, int start_res, int Max_stage2, int *whd)\n{\n"
+     "    int n = 0; whd[0] = w; whd[1] = h; whd[2] = d; n++;        // append_new(w,h,d): level 0 (pyramid.cu:219)\n",
+     "    int factor_t = 1;\n    for (int el = 0; el < maxl; el++)\n    {\n        whd[3 * n] = w; whd[3 * n + 1] = h; whd[3 * n + 2] = d; n++;   // append_new(w,h,d) (pyramid.cu:239)\n"),
+    ("Algorithm/pyramid.cu", (r"\(float\)\(Max_stage2\);", r"^\t\tif\(maxl-el<=el_x\) w=ceil"), r"^\tfor\(int i=m_data\.size\(\)-2", r"^\s*$|^\t\}\s*$", [],
+     "", "    }\n    (void)factor_t;\n    return n;\n}\n}\n"),
     # isignbit, calc_border, ssim                                   morph.cu:35-118
     ("Algorithm/morph.cu", r"^__device__ int isignbit\(", r"^// Level processing", None),
     # INIT_* constants, kernel_initialize_level, init_improving_mask  morph.cu:170-261
@@ -81,7 +92,13 @@ SPANS = [
 
 def cut(text, first, stop, drop, fname, subs=(), prefix="", suffix=""):
     lines = text.split("\n")
-    a = next((i for i, l in enumerate(lines) if re.search(first, l)), None)
+    start = 0
+    if isinstance(first, tuple):                      # (anchor to search after, first line taken)
+        after, first = first
+        start = next((i for i, l in enumerate(lines) if re.search(after, l)), None)
+        if start is None:
+            raise SystemExit(f"{fname}: anchor {after!r} not found")
+    a = next((i for i in range(start, len(lines)) if re.search(first, lines[i])), None)
     if a is None:
         raise SystemExit(f"{fname}: anchor {first!r} not found")
     b = next((i for i in range(a + 1, len(lines)) if re.search(stop, lines[i])), None)

@@ -34,7 +34,10 @@
 //  (j) the temporal flow composition of Pyramid::build (pyramid.cu:406-441) and Pyramid::BiLinear (488-523): the reference's
 //      text on the flows its compiled resampler gives, bit-equal to the four flow fields of every temporally halved level
 //      (tests/test_oracle_refdev.py::test_temporal_flow_composition_*);
-//  (k) the reference-internal cross-checks of SURVEY.md section 4.
+//  (k) the level schedule of Pyramid::build (pyramid.cu:222-234, 463-465): the reference's arithmetic, stitched into a loop
+//      that records the level sizes; equal to level_schedule for the BASELINE configurations and 300 random sizes
+//      (tests/test_oracle_refdev.py::test_level_schedule_*);
+//  (l) the reference-internal cross-checks of SURVEY.md section 4.
 // Still "parity unpinned" (third-party code of the reference that cannot run here): the INVERSE of the coarse dense system
 // (cv::Mat::inv, D4), the texture unit's 9-bit interpolation weights (D1), the temporal in-fill of
 // update_result (a cv::Mat expression evaluated inside OpenCV), the summation order of cuBLAS's dots inside

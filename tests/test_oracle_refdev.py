@@ -405,3 +405,20 @@ def test_temporal_flow_composition_is_the_reference_s_own_code(oracle_lib):
             for t in range(i["d"]):
                 np.testing.assert_array_equal(T[min(t * factor_t, ip["d"] - 1)], want[t], err_msg=f"level {l} {nm} frame {t}")
     assert halved >= 1
+
+
+def test_level_schedule_is_the_reference_s_own_arithmetic(oracle_lib):
+    """The part of Pyramid::build that decides the pyramid (pyramid.cu:222-234: voxel cap, el_t / el_x / el_y from float log2,
+    number of levels; 463-465: the halving of w / h / d per level) cut out of the reference and replayed: the oracle's schedule
+    (and the product's, tests/test_cabi.py::test_schedule_bit_exact_vs_oracle) gives the same levels for the BASELINE
+    configurations and for a sweep of random sizes."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    cases = [(256, 256, 1), (512, 512, 1), (1920, 1080, 1), (1280, 720, 120), (3840, 2160, 240), (600, 338, 100), (64, 64, 1), (96, 64, 9), (64, 48, 17)]
+    cases += [(int(rng.integers(24, 2000)), int(rng.integers(24, 1200)), int(rng.integers(1, 130))) for _ in range(300)]
+    for w, h, d in cases:
+        for sr in (8, 4):
+            if w * h * d >= 2 ** 31:                       # the reference multiplies ints (3840 x 2160 x 240 still fits)
+                continue
+            got = rd.level_schedule(w, h, d, sr, 14000000)
+            want = [(e["w"], e["h"], e["d"]) for e in oracle_lib.schedule(w, h, d, sr, 14000000)]
+            assert got == want, (w, h, d, sr)
